@@ -1,0 +1,139 @@
+/*
+ * pp_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the hot path of tsturzl/rs-pathplanning
+ * (crate `pathplanning` v0.1.2): src/dubins.rs in full and the NN / edge /
+ * verify pieces of src/rrt.rs, plus the geo 0.12.2 predicates the latter
+ * calls.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product path
+ * (libpathplanning_b200.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+ *  and cannot be compiled here (no rustc/cargo), and
+ * geo/rstar are not vendored.  The restatement is pinned only by (i) an
+ * independent pure-Python transliteration (oracle/dubins_py.py) that must
+ * agree bit-for-bit, and (ii) the restatement-derived known answers of
+ * SURVEY.md Appendix C.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp (see oracle/Makefile).
+ * glibc libm is the same libm Rust's f64::{sin,cos,atan2,acos,hypot} reach on
+ * x86_64-unknown-linux-gnu, and no a*b+c is ever contracted, as in rustc.
+ */
+#ifndef PP_ORACLE_H
+#define PP_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* word ids follow ALL_PLANNERS order, src/dubins.rs:291 */
+enum { PPO_LSL = 0, PPO_RSR = 1, PPO_LSR = 2, PPO_RSL = 3, PPO_RLR = 4, PPO_LRL = 5, PPO_NONE = 0xFF };
+
+/* flags reported by ppo_dubins_eval for the parity harness */
+enum {
+    PPO_FLAG_NEAR_WRAP = 1, /* a mod2pi result of a contending word lies within PPO_WRAP_EPS of 0 or 2pi */
+    PPO_FLAG_NEAR_TIE = 2,  /* runner-up cost within PPO_TIE_REL (relative) of the best cost */
+    PPO_FLAG_NEAR_FEAS = 4  /* a feasibility test (p^2 >= 0, |tmp| <= 1) is within 1e-9 of flipping */
+};
+#define PPO_WRAP_EPS 1e-9
+#define PPO_TIE_REL 1e-9
+
+double ppo_mod2pi(double theta);  /* src/dubins.rs:14-20 */
+double ppo_pi_2_pi(double angle); /* src/dubins.rs:22-24 */
+
+/* one word: returns 1 if feasible and writes tpq[3]; src/dubins.rs:27-153 */
+int ppo_dubins_word(int word, double alpha, double beta, double d, double tpq[3]);
+
+/* normalisation + six words + selection (src/dubins.rs:401-408, 333-363).
+ * Returns the word id (0..5) or PPO_NONE.  cost is radius-normalised. */
+int ppo_dubins_eval(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
+                    double *cost, double tpq[3], uint32_t *flags);
+
+/* batch (n pairs, SoA); radius_arr may be NULL -> scalar radius.  nthreads<=0: all cores */
+void ppo_dubins_eval_batch(size_t n, const double *sx, const double *sy, const double *syaw, const double *ex,
+                           const double *ey, const double *eyaw, const double *radius_arr, double radius,
+                           double *cost, uint8_t *word, double *tpq, uint32_t *flags, int nthreads);
+
+/* full path, world frame: src/dubins.rs:401-428.  from_origin != 0 -> src/dubins.rs:326-399 semantics
+ * with (ex,ey,eyaw) the local goal and sx=sy=syaw ignored, c = 1/radius.
+ * Returns the number of samples (>= 0), -1 if no feasible word (None), -2 if cap too small,
+ * -3 if the reference would index out of its n_point buffer (panic).
+ * n_point_out (optional) receives the reference's buffer size (src/dubins.rs:369). */
+long ppo_dubins_path(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
+                     double step, int from_origin, double *px, double *py, double *pyaw, size_t cap,
+                     int *word, double *cost, long *n_point_out);
+
+/* sample counts only (same loop semantics), batch */
+void ppo_dubins_count_batch(size_t n, const double *sx, const double *sy, const double *syaw, const double *ex,
+                            const double *ey, const double *eyaw, double radius, double step, int64_t *counts,
+                            int nthreads);
+
+/* create_circle, src/rrt.rs:43-60, followed by Polygon::new's ring closing (geo-types 0.4).
+ * Returns the number of ring points written (<= cap) or -1. */
+long ppo_create_circle(double cx, double cy, double radius, double *rx, double *ry, size_t cap);
+
+/* compute_yaw, src/rrt.rs:267-271 */
+double ppo_compute_yaw(double fx, double fy, double tx, double ty);
+
+/* exact nearest neighbour: argmin_i (dx*dx + dy*dy), non-fused, lowest index wins ties
+ * (the intended contract of src/rrt.rs:378-391).  Also reports, in
+ * hypot_disagree (optional), how many queries have argmin(hypot) != argmin(d2). */
+void ppo_nn_brute(size_t n_nodes, const double *nx, const double *ny, size_t m, const double *qx,
+                  const double *qy, uint32_t *idx, double *d2, size_t *hypot_disagree, int nthreads);
+/* same answer through a uniform grid (the fair CPU comparator for rstar's O(log N) query) */
+void ppo_nn_grid(size_t n_nodes, const double *nx, const double *ny, size_t m, const double *qx, const double *qy,
+                 uint32_t *idx, double *d2, int nthreads);
+
+/* ---- geo 0.12.2 predicates on closed rings given as point arrays ---- */
+/* LineString::contains(&Point) */
+int ppo_ring_has_point(const double *rx, const double *ry, size_t n, double px, double py);
+/* get_position: 0 outside, 1 inside, 2 on boundary */
+int ppo_point_position(const double *rx, const double *ry, size_t n, double px, double py);
+/* LineString::intersects(&LineString): a = ring (outer loop), b = line */
+int ppo_lines_intersect(const double *ax, const double *ay, size_t na, const double *bx, const double *by,
+                        size_t nb);
+
+/* world = bounds ring + obstacle rings (CSR).  No interior rings (the reference never builds any). */
+typedef struct {
+    const double *bx, *by;
+    size_t nb; /* bounds exterior ring, closed */
+    const double *ox, *oy;
+    const uint32_t *ring_off; /* n_rings+1 offsets into ox/oy */
+    size_t n_rings;
+} ppo_world;
+
+/* Space::verify, src/rrt.rs:124-137, on one polyline (n >= 0 points) */
+int ppo_verify(const ppo_world *w, const double *lx, const double *ly, size_t n);
+/* same, with the exactness-preserving AABB culls of SURVEY B.1 (must agree with ppo_verify) */
+int ppo_verify_culled(const ppo_world *w, const double *lx, const double *ly, size_t n);
+
+/* straight 2-point edges a->b, batch */
+void ppo_verify_segments(const ppo_world *w, size_t m, const double *ax, const double *ay, const double *bx,
+                         const double *by, uint8_t *ok, int culled, int nthreads);
+
+/* Dubins edge polyline = samples(child->parent) ++ [parent point]  (SURVEY A.3 Q6/Q12);
+ * fallback [(sx,sy), parent] when no word is feasible (src/rrt.rs:313). Returns point count or <0. */
+long ppo_dubins_edge_polyline(double sx, double sy, double syaw, double ex, double ey, double eyaw,
+                              double radius, double step, double *lx, double *ly, size_t cap);
+/* verify of Dubins edges, batch; min_clear (optional) is not computed here */
+void ppo_verify_dubins_edges(const ppo_world *w, size_t m, const double *sx, const double *sy, const double *syaw,
+                             const double *ex, const double *ey, const double *eyaw, double radius, double step,
+                             uint8_t *ok, int culled, int nthreads);
+
+/* line_to_origin over a flat tree (src/rrt.rs:291-321, node->root chunk order). Returns points or <0. */
+long ppo_line_to_origin(const double *nx, const double *ny, const double *nyaw, const int32_t *parent,
+                        uint32_t node, double radius, double step, double *lx, double *ly, size_t cap);
+
+/* counter-based generator of SURVEY 8(d): uniform in [0,1) for (seed, stream, i) */
+double ppo_uniform(uint64_t seed, uint64_t stream, uint64_t i);
+void ppo_fill_uniform(uint64_t seed, uint64_t stream, size_t n, double lo, double hi, double *out);
+
+int ppo_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,349 @@
+// dubins.cu -- batched Dubins kernels: evaluate (six words + minimum), plan/count and sample fill.
+// Compiled with -fmad=false (see dubins_device.cuh).
+//
+// Reference arithmetic: src/dubins.rs:14-428.  Layout: SoA f64 arrays sx[], sy[], syaw[], ex[], ey[],
+// eyaw[] (one coalesced 8-byte load per lane and array); outputs cost[] f64, word[] u8, optional tpq[3n].
+#include "dubins_device.cuh"
+#include "pp_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: evaluate.  One thread per pose pair; FP64-pipe bound (about 800 DP instructions per
+// 57 algorithmic bytes), so the grid is simply n/128 CTAs of 4 warps: small CTAs keep the tail short.
+// ------------------------------------------------------------------------------------------------
+#define PP_EVAL_THREADS 128
+
+template <bool HAS_RADIUS_ARR, bool WANT_TPQ>
+__global__ void __launch_bounds__(PP_EVAL_THREADS)
+    pp_dubins_eval_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
+                          const double *__restrict__ syaw, const double *__restrict__ ex,
+                          const double *__restrict__ ey, const double *__restrict__ eyaw,
+                          const double *__restrict__ radius_arr, double radius, double *__restrict__ cost,
+                          uint8_t *__restrict__ word, double *__restrict__ tpq) {
+    size_t i = (size_t)blockIdx.x * PP_EVAL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    double lex, ley, leyaw, ss, cs;
+    pp_dubins_to_local(__ldg(sx + i), __ldg(sy + i), __ldg(syaw + i), __ldg(ex + i), __ldg(ey + i), __ldg(eyaw + i),
+                       &lex, &ley, &leyaw, &ss, &cs);
+    double r = HAS_RADIUS_ARR ? __ldg(radius_arr + i) : radius;
+    double c = 1.0 / r;  // src/dubins.rs:404
+    pp_dubins_frame f = pp_dubins_frame_from_local(lex, ley, leyaw, c);
+    pp_dubins_sol s = pp_dubins_solve<false>(f.alpha, f.beta, f.d, nullptr, nullptr);
+    cost[i] = s.cost;
+    word[i] = (uint8_t)s.word;
+    if (WANT_TPQ) {
+        tpq[3 * i + 0] = s.t;
+        tpq[3 * i + 1] = s.p;
+        tpq[3 * i + 2] = s.q;
+    }
+}
+
+int pp_launch_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
+                          const double *ex, const double *ey, const double *eyaw, const double *radius_arr,
+                          double radius, double *cost, uint8_t *word, double *tpq, cudaStream_t stream) {
+    if (n == 0) return PP_OK;
+    unsigned grid = (unsigned)((n + PP_EVAL_THREADS - 1) / PP_EVAL_THREADS);
+    pp_launch_scope scope(ctx, "dubins_eval");
+#define PP_GO(RA, TPQ)                                                                                          \
+    pp_dubins_eval_kernel<RA, TPQ><<<grid, PP_EVAL_THREADS, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius_arr, \
+                                                                         radius, cost, word, tpq)
+    if (radius_arr) {
+        if (tpq) PP_GO(true, true); else PP_GO(true, false);
+    } else {
+        if (tpq) PP_GO(false, true); else PP_GO(false, false);
+    }
+#undef PP_GO
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}
+
+// diagnostic: all six words for explicit (alpha, beta, d)
+__global__ void pp_dubins_words_kernel(size_t n, const double *__restrict__ alpha, const double *__restrict__ beta,
+                                       const double *__restrict__ d, double *__restrict__ tpq,
+                                       uint8_t *__restrict__ feas) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double all[18];
+    uint8_t fz[6];
+    pp_dubins_solve<true>(alpha[i], beta[i], d[i], all, fz);
+    for (int k = 0; k < 18; ++k) tpq[18 * i + k] = all[k];
+    for (int k = 0; k < 6; ++k) feas[6 * i + k] = fz[k];
+}
+
+int pp_launch_dubins_words(pp_ctx *ctx, size_t n, const double *alpha, const double *beta, const double *d,
+                           double *tpq, uint8_t *feas, cudaStream_t stream) {
+    if (n == 0) return PP_OK;
+    pp_launch_scope scope(ctx, "dubins_words");
+    pp_dubins_words_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, alpha, beta, d, tpq, feas);
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}
+
+__global__ void pp_mod2pi_kernel(size_t n, const double *__restrict__ x, double *__restrict__ out, int pi2pi) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = pi2pi ? pp_pi_2_pi(x[i]) : pp_mod2pi(x[i]);
+}
+
+int pp_launch_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi2pi, cudaStream_t stream) {
+    if (n == 0) return PP_OK;
+    pp_launch_scope scope(ctx, "mod2pi");
+    pp_mod2pi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, x, out, pi2pi);
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan / count: evaluate, then replay generate_local_course's index arithmetic (src/dubins.rs:200-289)
+// without producing samples: per segment the first `pd`, the number of loop iterations obtained by
+// the reference's own repeated addition (Q10), the carried remainder `ll`, and finally the trim rule
+// (Q6/Q7) which needs the local x of the trailing slots.  One thread per path; the replay is a
+// dependent DADD/DSETP chain (2 DP instructions per sample), cheap next to the fill pass.
+// ------------------------------------------------------------------------------------------------
+#define PP_PLAN_MAX_ITERS (1u << 26)
+
+__global__ void __launch_bounds__(128)
+    pp_dubins_plan_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
+                          const double *__restrict__ syaw, const double *__restrict__ ex,
+                          const double *__restrict__ ey, const double *__restrict__ eyaw, double radius, double step,
+                          int from_origin, uint32_t *__restrict__ counts, pp_dubins_plan *__restrict__ plans) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pp_dubins_plan pl;
+    double lex, ley, leyaw, ss, cs;
+    if (from_origin) {
+        lex = ex[i];
+        ley = ey[i];
+        leyaw = eyaw[i];
+        pl.sx = pl.sy = pl.syaw = 0.0;
+    } else {
+        pl.sx = sx[i];
+        pl.sy = sy[i];
+        pl.syaw = syaw[i];
+        pp_dubins_to_local(pl.sx, pl.sy, pl.syaw, ex[i], ey[i], eyaw[i], &lex, &ley, &leyaw, &ss, &cs);
+    }
+    double c = 1.0 / radius;
+    pp_dubins_frame f = pp_dubins_frame_from_local(lex, ley, leyaw, c);
+    pp_dubins_sol s = pp_dubins_solve<false>(f.alpha, f.beta, f.d, nullptr, nullptr);
+    pl.word = (uint8_t)s.word;
+    pl.from_origin = (uint8_t)(from_origin != 0);
+    pl.rinv = 1.0 / c;
+    pl.step = step;
+    pl.len[0] = s.t;
+    pl.len[1] = s.p;
+    pl.len[2] = s.q;
+    pl.n[0] = pl.n[1] = pl.n[2] = 0;
+    pl.pd0[0] = pl.pd0[1] = pl.pd0[2] = 0.0;
+    pl.count = 0;
+    for (int k = 0; k < 6; ++k) pl._pad[k] = 0;
+    if (s.word != PP_WORD_NONE) {
+        double ll = 0.0;
+        bool overflow = false;
+        for (int sgm = 0; sgm < 3; ++sgm) {
+            double l = pl.len[sgm];
+            double d = (l > 0.0) ? step : -step;  // :228
+            double pd = (sgm >= 1 && (pl.len[sgm - 1] * l) > 0.0) ? (-d - ll) : (d - ll);  // :233-237
+            pl.pd0[sgm] = pd;
+            uint32_t cnt = 0;
+            double al = fabs(l);
+            while (fabs(pd) <= al) {  // :239
+                pd += d;
+                if (++cnt >= PP_PLAN_MAX_ITERS) {
+                    overflow = true;
+                    break;
+                }
+            }
+            pl.n[sgm] = cnt;
+            ll = (l - pd) - d;  // :256
+        }
+        if (overflow) {
+            pl.count = 0xFFFFFFFFu;
+        } else {
+            // trim (:281-288): count = index of the last slot whose local x is non-zero
+            uint32_t N = pl.n[0] + pl.n[1] + pl.n[2];
+            pp_seg_origin o[3];
+            double gx;
+            pp_segment_origins(pl, o, &gx);
+            uint32_t cntout;
+            if (gx != 0.0) {
+                cntout = N + 1;
+            } else {
+                cntout = 0;
+                for (uint32_t k = N; k >= 1; --k) {
+                    double x, y, yaw;
+                    pp_plan_sample_local(pl, o, k, &x, &y, &yaw);
+                    if (x != 0.0) {
+                        cntout = k;
+                        break;
+                    }
+                }
+            }
+            pl.count = cntout;
+        }
+    }
+    counts[i] = pl.count;
+    if (plans) plans[i] = pl;
+}
+
+int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
+                          const double *ex, const double *ey, const double *eyaw, double radius, double step,
+                          int from_origin, uint32_t *counts, void *plans, cudaStream_t stream) {
+    if (n == 0) return PP_OK;
+    pp_launch_scope scope(ctx, "dubins_plan");
+    pp_dubins_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius, step,
+                                                                           from_origin, counts,
+                                                                           (pp_dubins_plan *)plans);
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fill: one warp per path, lane k takes samples k, k+32, ...; each warp iteration writes 32
+// consecutive (x,y,yaw) triples = 768 contiguous bytes.  HBM-store bound for straight segments,
+// near the FP64 ridge for arcs (sincos per sample).
+// ------------------------------------------------------------------------------------------------
+#define PP_FILL_THREADS 128
+
+__global__ void __launch_bounds__(PP_FILL_THREADS)
+    pp_dubins_fill_kernel(size_t n, const pp_dubins_plan *__restrict__ plans, const uint64_t *__restrict__ offsets,
+                          double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const size_t warps_total = (size_t)gridDim.x * (PP_FILL_THREADS / 32);
+    for (size_t path = (size_t)blockIdx.x * (PP_FILL_THREADS / 32) + (threadIdx.x >> 5); path < n;
+         path += warps_total) {
+        pp_dubins_plan pl = plans[path];
+        if (pl.count == 0 || pl.count == 0xFFFFFFFFu) continue;
+        pp_seg_origin o[3];
+        double gx;
+        pp_segment_origins(pl, o, &gx);
+        double ss = 0.0, cs = 1.0;
+        if (!pl.from_origin) sincos(pl.syaw, &ss, &cs);
+        double *dst = out + 3 * offsets[path];
+        for (uint32_t k = lane; k < pl.count; k += 32) {
+            double x = 0.0, y = 0.0, yaw = 0.0;  // slot 0 is the untouched zero of the reference's buffer
+            if (k > 0) pp_plan_sample_local(pl, o, k, &x, &y, &yaw);
+            if (!pl.from_origin) {  // src/dubins.rs:412-422
+                double xw = (cs * x + (-ss) * y) + pl.sx;
+                double yw = (ss * x + cs * y) + pl.sy;
+                x = xw;
+                y = yw;
+                yaw = pp_pi_2_pi(yaw + pl.syaw);
+            }
+            dst[3 * (size_t)k + 0] = x;
+            dst[3 * (size_t)k + 1] = y;
+            dst[3 * (size_t)k + 2] = yaw;
+        }
+    }
+}
+
+int pp_launch_dubins_fill(pp_ctx *ctx, size_t n, const void *plans, const uint64_t *offsets, double *out,
+                          cudaStream_t stream) {
+    if (n == 0) return PP_OK;
+    pp_launch_scope scope(ctx, "dubins_fill");
+    size_t warps = n;
+    size_t blocks = (warps + (PP_FILL_THREADS / 32) - 1) / (PP_FILL_THREADS / 32);
+    size_t max_blocks = (size_t)ctx->sm_count * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    pp_dubins_fill_kernel<<<(unsigned)blocks, PP_FILL_THREADS, 0, stream>>>(n, (const pp_dubins_plan *)plans, offsets,
+                                                                            out);
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of u32 counts into u64 offsets: single-pass chained scan is overkill for this
+// helper (n <= a few million, 12 B/elem): three small kernels (block sums, scan of sums, apply).
+// ------------------------------------------------------------------------------------------------
+#define PP_SCAN_THREADS 256
+#define PP_SCAN_ITEMS 8
+#define PP_SCAN_TILE (PP_SCAN_THREADS * PP_SCAN_ITEMS)
+
+__device__ __forceinline__ uint64_t pp_block_exclusive_scan(uint64_t v, uint64_t *total, uint64_t *smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = (lane < PP_SCAN_THREADS / 32) ? smem[lane] : 0;
+        uint64_t winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < PP_SCAN_THREADS / 32) smem[lane] = winc - w;
+        if (lane == PP_SCAN_THREADS / 32 - 1) smem[32] = winc;
+    }
+    __syncthreads();
+    uint64_t res = smem[warp] + inc - v;
+    *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(PP_SCAN_THREADS)
+    pp_scan_tile_sums(size_t n, const uint32_t *__restrict__ counts, uint64_t *__restrict__ tile_sums) {
+    __shared__ uint64_t sm[33];
+    size_t base = (size_t)blockIdx.x * PP_SCAN_TILE + (size_t)threadIdx.x * PP_SCAN_ITEMS;
+    uint64_t s = 0;
+    for (int k = 0; k < PP_SCAN_ITEMS; ++k)
+        if (base + k < n) {
+            uint32_t c = counts[base + k];
+            s += (c == 0xFFFFFFFFu) ? 0 : c;
+        }
+    uint64_t total;
+    pp_block_exclusive_scan(s, &total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(PP_SCAN_THREADS)
+    pp_scan_of_sums(size_t n_tiles, uint64_t *__restrict__ tile_sums, uint64_t *__restrict__ total_out) {
+    __shared__ uint64_t sm[33];
+    uint64_t carry = 0;
+    for (size_t base = 0; base < n_tiles; base += PP_SCAN_THREADS) {
+        size_t i = base + threadIdx.x;
+        uint64_t v = (i < n_tiles) ? tile_sums[i] : 0;
+        uint64_t total;
+        uint64_t e = pp_block_exclusive_scan(v, &total, sm);
+        if (i < n_tiles) tile_sums[i] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(PP_SCAN_THREADS)
+    pp_scan_apply(size_t n, const uint32_t *__restrict__ counts, const uint64_t *__restrict__ tile_sums,
+                  uint64_t *__restrict__ offsets) {
+    __shared__ uint64_t sm[33];
+    size_t base = (size_t)blockIdx.x * PP_SCAN_TILE + (size_t)threadIdx.x * PP_SCAN_ITEMS;
+    uint32_t c[PP_SCAN_ITEMS];
+    uint64_t s = 0;
+    for (int k = 0; k < PP_SCAN_ITEMS; ++k) {
+        uint32_t v = (base + k < n) ? counts[base + k] : 0;
+        c[k] = (v == 0xFFFFFFFFu) ? 0 : v;
+        s += c[k];
+    }
+    uint64_t total;
+    uint64_t e = pp_block_exclusive_scan(s, &total, sm) + tile_sums[blockIdx.x];
+    for (int k = 0; k < PP_SCAN_ITEMS; ++k) {
+        if (base + k < n) offsets[base + k] = e;
+        e += c[k];
+    }
+}
+
+int pp_launch_exclusive_scan(pp_ctx *ctx, size_t n, const uint32_t *counts, uint64_t *offsets, uint64_t *total_dev,
+                             uint64_t *tile_sums /* >= ceil(n/tile) */, cudaStream_t stream) {
+    if (n == 0) {
+        PP_CUDA(ctx, cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), stream));
+        return PP_OK;
+    }
+    size_t tiles = (n + PP_SCAN_TILE - 1) / PP_SCAN_TILE;
+    pp_launch_scope scope(ctx, "exclusive_scan", 3);
+    pp_scan_tile_sums<<<(unsigned)tiles, PP_SCAN_THREADS, 0, stream>>>(n, counts, tile_sums);
+    pp_scan_of_sums<<<1, PP_SCAN_THREADS, 0, stream>>>(tiles, tile_sums, total_dev);
+    pp_scan_apply<<<(unsigned)tiles, PP_SCAN_THREADS, 0, stream>>>(n, counts, tile_sums, offsets);
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}

@@ -1,0 +1,284 @@
+// dubins_device.cuh -- device-side Dubins mathematics (f64), shared by the evaluate, sample and
+// fused sample-and-verify kernels.
+//
+// Restates the arithmetic of src/dubins.rs (reference crate root) for one pose pair per thread.
+// Design notes (not a translation of the Rust control flow):
+//   * the six words are evaluated branch-free from ONE set of trig values (the reference
+//     recomputes sin/cos of alpha, beta five times per word, src/dubins.rs:28-32 etc.);
+//     identical sub-expressions are shared only where they are bit-identical
+//     (atan2 of RSR == RLR's, LRL's == -LSL's since atan2 is odd in y).
+//   * mod2pi (src/dubins.rs:14-20) is x - 2pi*floor(x/2pi).  The division is replaced by a
+//     reciprocal multiply plus an exact guard: when the quotient is within 1e-9 of an integer
+//     the IEEE division is redone, so the result is bit-identical to the reference form for
+//     every input (Q1/Q3 wrap behaviour included).  Where the argument range is known
+//     ([0,2pi], [pi,2pi] ...) the floor is resolved by a compare.
+//   * this translation unit is compiled with -fmad=false: outside the CUDA libm calls no
+//     multiply-add is fused, as in rustc's output.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/pathplanning_b200.h"
+
+#define PP_PI 3.14159265358979323846
+#define PP_TWO_PI 6.28318530717958647692   // == 2.0 * PI exactly in binary64
+#define PP_INV_TWO_PI 0.15915494309189533577
+
+// x - 2pi*floor(x/2pi), bit-exact with the division form (src/dubins.rs:14-20)
+__device__ __forceinline__ double pp_mod2pi(double x) {
+    double q = x * PP_INV_TWO_PI;
+    double k = floor(q);
+    double f = q - k;
+    // q is within 3 ulp of x/2pi; floor can only differ when q sits next to an integer
+    if (!(fabs(f - 0.5) < 0.5 - 1e-9) || !(fabs(q) < 1e5)) k = floor(x / PP_TWO_PI);
+    return x - PP_TWO_PI * k;
+}
+// mod2pi for x already known to lie in [0, 2pi]: only x == 2pi wraps (to 0)
+__device__ __forceinline__ double pp_mod2pi_unit(double x) { return (x == PP_TWO_PI) ? 0.0 : x; }
+
+// src/dubins.rs:22-24 ; Rust % == fmod
+__device__ __forceinline__ double pp_pi_2_pi(double a) { return fmod(a + PP_PI, PP_TWO_PI) - PP_PI; }
+
+struct pp_dubins_sol {
+    double t, p, q, cost;
+    int word;  // pp_word or PP_WORD_NONE
+};
+
+struct pp_dubins_frame {
+    double alpha, beta, d;
+};
+
+// src/dubins.rs:333-338 : d, theta, alpha, beta from the goal in the start frame
+__device__ __forceinline__ pp_dubins_frame pp_dubins_frame_from_local(double lex, double ley, double leyaw,
+                                                                      double c) {
+    pp_dubins_frame f;
+    f.d = hypot(lex, ley) * c;
+    double a = atan2(ley, lex);  // [-pi, pi]
+    // theta = mod2pi(a): floor(a/2pi) is -1 for a < 0, else 0 (and -0 -> +0)
+    double theta = (a < 0.0) ? (a + PP_TWO_PI) : (a + 0.0);
+    // alpha = mod2pi(-theta), theta in [0, 2pi]: floor(-theta/2pi) is -1 unless theta == 0
+    f.alpha = (theta > 0.0) ? (PP_TWO_PI - theta) : ((theta == 0.0) ? 0.0 : theta /*NaN*/);
+    f.beta = pp_mod2pi(leyaw - theta);
+    return f;
+}
+
+// src/dubins.rs:402-408
+__device__ __forceinline__ void pp_dubins_to_local(double sx, double sy, double syaw, double ex, double ey,
+                                                   double eyaw, double *lex, double *ley, double *leyaw,
+                                                   double *sin_s, double *cos_s) {
+    double ss, cs;
+    sincos(syaw, &ss, &cs);
+    double dx = ex - sx, dy = ey - sy;
+    *lex = cs * dx + ss * dy;
+    *ley = -ss * dx + cs * dy;
+    *leyaw = eyaw - syaw;
+    *sin_s = ss;
+    *cos_s = cs;
+}
+
+// the six words (src/dubins.rs:27-153) + the selection fold (src/dubins.rs:347-363).
+// WANT_ALL: also store every word's (t,p,q) / feasibility (diagnostic entry pp_dubins_words).
+template <bool WANT_ALL>
+__device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double beta, double d, double *all_tpq,
+                                                         uint8_t *all_feas) {
+    double sa, ca, sb, cb;
+    sincos(alpha, &sa, &ca);
+    sincos(beta, &sb, &cb);
+    const double c_ab = cos(alpha - beta);
+    const double dd = d * d;
+    const double two_cab = 2.0 * c_ab;
+    const double two_d = 2.0 * d;
+    const double mbeta = pp_mod2pi_unit(beta);  // mod2pi(beta), beta already in [0, 2pi]
+
+    pp_dubins_sol best;
+    best.cost = CUDART_INF;
+    best.word = PP_WORD_NONE;
+    best.t = best.p = best.q = CUDART_NAN;
+
+#define PP_CONSIDER(W, FEAS, T, P, Q)                              \
+    do {                                                           \
+        double _c = (fabs(T) + fabs(P)) + fabs(Q);                 \
+        bool _f = (FEAS);                                          \
+        if (WANT_ALL) {                                            \
+            all_feas[W] = _f ? 1 : 0;                              \
+            all_tpq[3 * W + 0] = _f ? (T) : CUDART_NAN;            \
+            all_tpq[3 * W + 1] = _f ? (P) : CUDART_NAN;            \
+            all_tpq[3 * W + 2] = _f ? (Q) : CUDART_NAN;            \
+        }                                                          \
+        if (_f && _c < best.cost) { /* strict: first word wins */ \
+            best.cost = _c;                                        \
+            best.word = W;                                         \
+            best.t = (T);                                          \
+            best.p = (P);                                          \
+            best.q = (Q);                                          \
+        }                                                          \
+    } while (0)
+
+    // ---- LSL (src/dubins.rs:27-48) and the shared atan2 of LRL
+    const double sa_m_sb = sa - sb;
+    const double base_csc = (2.0 + dd) - two_cab;
+    const double at_lsl = atan2(cb - ca, (d + sa) - sb);
+    {
+        double psq = base_csc + two_d * sa_m_sb;
+        double t = pp_mod2pi(-alpha + at_lsl);
+        double p = sqrt(fmax(psq, 0.0));
+        double q = pp_mod2pi(beta - at_lsl);
+        PP_CONSIDER(PP_LSL, !(psq < 0.0), t, p, q);
+    }
+    // ---- RSR (src/dubins.rs:51-71) and the shared atan2 of RLR
+    const double at_rsr = atan2(ca - cb, (d - sa) + sb);
+    {
+        double psq = base_csc + two_d * (sb - sa);
+        double t = pp_mod2pi(alpha - at_rsr);
+        double p = sqrt(fmax(psq, 0.0));
+        double q = pp_mod2pi(-beta + at_rsr);
+        PP_CONSIDER(PP_RSR, !(psq < 0.0), t, p, q);
+    }
+    // ---- LSR (src/dubins.rs:74-92)
+    const double sa_p_sb = sa + sb;
+    const double base_cross = (-2.0 + dd) + two_cab;
+    {
+        double psq = base_cross + two_d * sa_p_sb;
+        double p = sqrt(fmax(psq, 0.0));
+        double tmp = atan2(-ca - cb, (d + sa) + sb) - atan2(-2.0, p);
+        double t = pp_mod2pi(-alpha + tmp);
+        double q = pp_mod2pi(-mbeta + tmp);
+        PP_CONSIDER(PP_LSR, !(psq < 0.0), t, p, q);
+    }
+    // ---- RSL (src/dubins.rs:95-113)
+    {
+        double psq = base_cross - two_d * sa_p_sb;
+        double p = sqrt(fmax(psq, 0.0));
+        double tmp = atan2(ca + cb, (d - sa) - sb) - atan2(2.0, p);
+        double t = pp_mod2pi(alpha - tmp);
+        double q = pp_mod2pi(beta - tmp);
+        PP_CONSIDER(PP_RSL, !(psq < 0.0), t, p, q);
+    }
+    // ---- RLR (src/dubins.rs:116-133): p in [pi,2pi] -> mod2pi(p/2) = p/2 and mod2pi(p) = p exactly
+    const double base_ccc = (6.0 - dd) + two_cab;
+    {
+        double tmp = (base_ccc + two_d * sa_m_sb) * 0.125;
+        bool feas = !(fabs(tmp) > 1.0);
+        double ac = acos(fmin(fmax(tmp, -1.0), 1.0));
+        double p = pp_mod2pi_unit(PP_TWO_PI - ac);
+        double t = pp_mod2pi((alpha - at_rsr) + p * 0.5);
+        double q = pp_mod2pi(((alpha - beta) - t) + p);
+        PP_CONSIDER(PP_RLR, feas, t, p, q);
+    }
+    // ---- LRL (src/dubins.rs:136-153): atan2(ca-cb, d+sa-sb) == -atan2(cb-ca, d+sa-sb)
+    {
+        double tmp = (base_ccc + two_d * (sb - sa)) * 0.125;
+        bool feas = !(fabs(tmp) > 1.0);
+        double ac = acos(fmin(fmax(tmp, -1.0), 1.0));
+        double p = pp_mod2pi_unit(PP_TWO_PI - ac);
+        double t = pp_mod2pi((-alpha + at_lsl) + p * 0.5);
+        double q = pp_mod2pi(((mbeta - alpha) - t) + p);
+        PP_CONSIDER(PP_LRL, feas, t, p, q);
+    }
+#undef PP_CONSIDER
+    return best;
+}
+
+// segment modes per word (src/dubins.rs:26,50,73,94,115,135): 2 bits per segment, 0 L / 1 S / 2 R
+__device__ __forceinline__ int pp_word_mode(int word, int seg) {
+    // LSL 0,1,0  RSR 2,1,2  LSR 0,1,2  RSL 2,1,0  RLR 2,0,2  LRL 0,2,0
+    const uint32_t table = (0u | 1u << 2 | 0u << 4) | ((2u | 1u << 2 | 2u << 4) << 6) | ((0u | 1u << 2 | 2u << 4) << 12) |
+                           ((2u | 1u << 2 | 0u << 4) << 18) | ((2u | 0u << 2 | 2u << 4) << 24);
+    if (word == PP_LRL) return (seg == 1) ? PP_MODE_R : PP_MODE_L;
+    return (int)((table >> (6 * word + 2 * seg)) & 3u);
+}
+
+// src/dubins.rs:155-198 with the per-segment constants hoisted: (so, co) = sincos(origin_yaw), rinv = 1/c.
+// (the reference divides by c per sample; multiplying by 1/c differs by <= 1 ulp, inside the 1e-9 contract)
+__device__ __forceinline__ void pp_interpolate(int mode, double len, double ox, double oy, double oyaw, double so,
+                                               double co, double rinv, double *x, double *y, double *yaw) {
+    if (mode == PP_MODE_S) {
+        double l = len * rinv;
+        *x = ox + l * co;
+        *y = oy + l * so;
+        *yaw = oyaw;
+    } else {
+        double sl, cl;
+        sincos(len, &sl, &cl);
+        double ldx = sl * rinv;
+        double ldy = (1.0 - cl) * rinv;
+        if (mode == PP_MODE_R) ldy = -ldy;
+        // cos(-o) = co, sin(-o) = -so
+        double gdx = co * ldx + (-so) * ldy;
+        double gdy = so * ldx + co * ldy;
+        *x = ox + gdx;
+        *y = oy + gdy;
+        *yaw = (mode == PP_MODE_L) ? (oyaw + len) : (oyaw - len);
+    }
+}
+
+// per-path plan record shared by the count / fill / collide kernels (PP_DUBINS_PLAN_BYTES)
+struct __align__(16) pp_dubins_plan {
+    double len[3];   // t, p, q
+    double pd0[3];   // first `pd` of each segment's loop (src/dubins.rs:233-237)
+    double sx, sy, syaw;
+    uint32_t n[3];   // loop iterations per segment (src/dubins.rs:239-255)
+    uint32_t count;  // samples the reference returns after its trim loop (src/dubins.rs:281-288)
+    double rinv;     // turn radius (1/c)
+    double step;
+    uint8_t word;    // pp_word or PP_WORD_NONE
+    uint8_t from_origin;
+    uint8_t _pad[6];
+};
+static_assert(sizeof(pp_dubins_plan) == PP_DUBINS_PLAN_BYTES, "plan record size is part of the ABI");
+
+struct pp_seg_origin {
+    double ox, oy, oyaw, so, co;
+};
+
+// origins of the three segments: segment i starts at segment i-1's end point, written by
+// interpolate(ind, l) at src/dubins.rs:258-271 and read back at :230.
+__device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_seg_origin o[3], double *gx) {
+    o[0].ox = 0.0;
+    o[0].oy = 0.0;
+    o[0].oyaw = 0.0;
+    o[0].so = 0.0;
+    o[0].co = 1.0;
+    for (int i = 0; i < 3; ++i) {
+        double x, y, yaw;
+        pp_interpolate(pp_word_mode(pl.word, i), pl.len[i], o[i].ox, o[i].oy, o[i].oyaw, o[i].so, o[i].co, pl.rinv,
+                       &x, &y, &yaw);
+        if (i < 2) {
+            o[i + 1].ox = x;
+            o[i + 1].oy = y;
+            o[i + 1].oyaw = yaw;
+            sincos(yaw, &o[i + 1].so, &o[i + 1].co);
+        } else {
+            *gx = x;
+        }
+    }
+}
+
+// local-frame sample of output slot k (1 <= k <= n0+n1+n2)
+__device__ __forceinline__ void pp_plan_sample_local(const pp_dubins_plan &pl, const pp_seg_origin o[3], uint32_t k,
+                                                     double *x, double *y, double *yaw) {
+    uint32_t j = k - 1;
+    int seg = 0;
+    if (j >= pl.n[0]) {
+        j -= pl.n[0];
+        seg = 1;
+        if (j >= pl.n[1]) {
+            j -= pl.n[1];
+            seg = 2;
+        }
+    }
+    double d = (pl.len[seg] > 0.0) ? pl.step : -pl.step;
+    double pd = pl.pd0[seg] + (double)j * d;  // reference accumulates; differs by <= j ulp (Q10)
+    pp_interpolate(pp_word_mode(pl.word, seg), pd, o[seg].ox, o[seg].oy, o[seg].oyaw, o[seg].so, o[seg].co, pl.rinv, x,
+                   y, yaw);
+}
+
+
+// local -> world (src/dubins.rs:412-422); (ss, cs) = sincos(syaw)
+__device__ __forceinline__ void pp_local_to_world(double ss, double cs, double sx, double sy, double x, double y,
+                                                  double *xw, double *yw) {
+    *xw = (cs * x + (-ss) * y) + sx;
+    *yw = (ss * x + cs * y) + sy;
+}

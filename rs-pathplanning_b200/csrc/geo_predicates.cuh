@@ -1,0 +1,95 @@
+// geo_predicates.cuh -- the geo 0.12.2 predicates behind Space::verify (src/rrt.rs:124-137), written
+// for host and device.  Semantics per SURVEY.md Appendix B.1:
+//   Polygon::contains(&LineString)   -> every line point strictly inside the exterior ring
+//   LineString::intersects(&Polygon) -> a ring segment meets a line segment (parameter test with two
+//                                       IEEE divisions, parallel pairs skipped), or a line point is
+//                                       inside the polygon
+// All arithmetic is plain IEEE f64 in the reference's operation order; every translation unit that
+// includes this header is compiled without multiply-add contraction (-fmad=false / -ffp-contract=off),
+// which is what makes the flags bit-exact with the oracle.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PP_HD __host__ __device__ __forceinline__
+#else
+#define PP_HD inline
+#endif
+
+#define PP_F64_EPSILON 2.220446049250313e-16
+
+// `impl Contains<Point> for LineString`: vertex equality, then the per-segment tx/ty test
+PP_HD bool pp_ring_has_point(const double *rx, const double *ry, uint32_t n, double px, double py) {
+    if (n == 0) return false;
+    if (n == 1) return rx[0] == px && ry[0] == py;
+    for (uint32_t i = 0; i < n; ++i)
+        if (rx[i] == px && ry[i] == py) return true;
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        const double x0 = rx[i], y0 = ry[i];
+        const double dx = rx[i + 1] - x0, dy = ry[i + 1] - y0;
+        bool hit;
+        if (dx == 0.0 && dy == 0.0) {
+            hit = (px == x0 && py == y0);
+        } else if (dy == 0.0) {
+            const double t = (px - x0) / dx;
+            hit = (py == y0 && 0.0 <= t && t <= 1.0);
+        } else if (dx == 0.0) {
+            const double t = (py - y0) / dy;
+            hit = (px == x0 && 0.0 <= t && t <= 1.0);
+        } else {
+            const double tx = (px - x0) / dx;
+            const double ty = (py - y0) / dy;
+            hit = (fabs(tx - ty) <= PP_F64_EPSILON && 0.0 <= tx && tx <= 1.0);
+        }
+        if (hit) return true;
+    }
+    return false;
+}
+
+// `get_position`: 0 outside, 1 inside, 2 on boundary
+PP_HD int pp_point_position(const double *rx, const double *ry, uint32_t n, double px, double py) {
+    if (n == 0) return 0;
+    if (pp_ring_has_point(rx, ry, n, px, py)) return 2;
+    double xints = 0.0;
+    uint32_t crossings = 0;
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        const double x0 = rx[i], y0 = ry[i], x1 = rx[i + 1], y1 = ry[i + 1];
+        const double ymin = (y0 < y1) ? y0 : y1, ymax = (y0 > y1) ? y0 : y1;
+        const double xmax = (x0 > x1) ? x0 : x1;
+        if (py > ymin && py <= ymax && px <= xmax) {
+            if (y0 != y1) xints = (py - y0) * (x1 - x0) / (y1 - y0) + x0;
+            if (x0 == x1 || px <= xints) crossings += 1;
+        }
+    }
+    return (int)(crossings & 1u);
+}
+
+// `impl Intersects<LineString> for LineString` with the ring as `self` and one line segment b0->b1
+PP_HD bool pp_ring_hits_segment(const double *rx, const double *ry, uint32_t n, double b0x, double b0y, double b1x,
+                                double b1y) {
+    const double b_dx = b1x - b0x, b_dy = b1y - b0y;
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        const double a0x = rx[i], a0y = ry[i];
+        const double a_dx = rx[i + 1] - a0x, a_dy = ry[i + 1] - a0y;
+        const double u_b = b_dy * a_dx - b_dx * a_dy;
+        if (u_b == 0.0) continue;
+        const double ua_t = b_dx * (a0y - b0y) - b_dy * (a0x - b0x);
+        const double ub_t = a_dx * (a0y - b0y) - a_dy * (a0x - b0x);
+        const double u_a = ua_t / u_b;
+        const double u_b2 = ub_t / u_b;
+        if (0.0 <= u_a && u_a <= 1.0 && 0.0 <= u_b2 && u_b2 <= 1.0) return true;
+    }
+    return false;
+}
+
+// Conservative pad of a ring's AABB.  Outside the padded box neither the crossing-number test nor
+// (away from near-collinear rounding noise) the parameter test can fire: the
+// rounding error of `xints` and of the quotients is below 2^-48 * max|coordinate|.
+PP_HD double pp_aabb_pad(double minx, double miny, double maxx, double maxy) {
+    double m = fabs(minx);
+    if (fabs(maxx) > m) m = fabs(maxx);
+    if (fabs(miny) > m) m = fabs(miny);
+    if (fabs(maxy) > m) m = fabs(maxy);
+    return m * 0x1p-40 + 0x1p-1000;
+}

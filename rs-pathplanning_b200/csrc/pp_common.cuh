@@ -1,0 +1,166 @@
+// pp_common.cuh -- context, error plumbing and sm_100a async-copy primitives shared by all kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pathplanning_b200.h"
+
+#define PP_SM_COUNT_B200 148
+
+// ---------------------------------------------------------------------------------------------
+// device mirrors
+// ---------------------------------------------------------------------------------------------
+struct pp_tree_dev {
+    size_t n = 0, cap = 0;
+    double *x = nullptr, *y = nullptr, *yaw = nullptr;
+    int32_t *parent = nullptr;
+    float *x32 = nullptr;  // fl32(x), for the exact fp32 pre-rejection of the NN scan
+    // uniform grid over the nodes (PP_NN_GRID), rebuilt lazily when `grid_n != n`
+    size_t grid_n = (size_t)-1;
+    int gx = 0, gy = 0;
+    double gminx = 0, gminy = 0, gcell = 1, ginv = 1;
+    uint32_t *cell_start = nullptr;  // gx*gy+1
+    uint32_t *cell_items = nullptr;  // n, ascending node index inside each cell
+    size_t cell_cap = 0, item_cap = 0;
+};
+
+struct pp_ring_meta {  // per obstacle ring
+    double minx, miny, maxx, maxy;  // exact AABB of the ring's points
+    double pad;                     // conservative rounding pad (see collide.cu)
+    uint32_t first, count;          // points [first, first+count) in ox/oy (closed ring)
+    uint32_t _r0, _r1;
+};
+
+struct pp_world_dev {
+    bool valid = false;
+    // bounds ring
+    double *bx = nullptr, *by = nullptr;
+    uint32_t nb = 0;
+    // obstacle rings
+    double *ox = nullptr, *oy = nullptr;
+    uint32_t n_pts = 0, n_rings = 0;
+    pp_ring_meta *meta = nullptr;
+    float4 *aabb32 = nullptr;  // outward-rounded padded AABBs (minx, miny, maxx, maxy) for the fp32 broad phase
+    uint32_t n_aabb_tiles = 0;
+    // byte grid classifying cells of the bounds' AABB: 0 outside, 1 inside, 2 needs the exact test
+    uint8_t *bcls = nullptr;
+    int bgx = 1, bgy = 1;
+    double bminx = 0, bminy = 0, binvx = 1, binvy = 1;
+    // uniform grid over padded ring AABBs
+    int gx = 0, gy = 0;
+    double gminx = 0, gminy = 0, gcell = 1, ginv = 1;
+    uint32_t *cell_start = nullptr, *cell_items = nullptr;
+};
+
+struct pp_timing_slot {
+    double total_ms = 0;
+    uint64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct pp_ctx {
+    int device = 0;
+    int sm_count = PP_SM_COUNT_B200;
+    cudaStream_t stream = nullptr;             // stream of the _dev entry points (may be caller-owned)
+    cudaStream_t own_stream_handle = nullptr;  // the stream created with the ctx
+    cudaStream_t active_stream = nullptr;      // stream the current API call launches on (set under `mu`)
+    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
+    std::mutex mu;
+    std::string last_error;
+    uint64_t launches = 0;
+    bool timing = false;
+    std::map<std::string, pp_timing_slot> timings;
+    std::vector<cudaEvent_t> event_pool;
+    pp_tree_dev tree;
+    pp_world_dev world;
+    // scratch (grown on demand)
+    unsigned int *tickets = nullptr;  // 64 zeroed counters for last-block-done reductions
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+int pp_fail(pp_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess);
+
+#define PP_CUDA(ctx, call)                                                    \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return pp_fail((ctx), PP_ERR_CUDA, #call, _e); \
+    } while (0)
+
+// RAII kernel-launch accounting (+ optional CUDA-event timing on the ctx stream)
+struct pp_launch_scope {
+    pp_ctx *ctx;
+    const char *name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    pp_launch_scope(pp_ctx *c, const char *n, int n_launches = 1);
+    ~pp_launch_scope();
+};
+
+int pp_scratch_reserve(pp_ctx *ctx, size_t bytes);
+
+// kernel-side view of pp_world_dev (passed by value)
+struct pp_world_view {
+    const double *bx, *by;
+    uint32_t nb;
+    const uint8_t *bcls;
+    int bgx, bgy;
+    double bminx, bminy, binvx, binvy;
+    const double *ox, *oy;
+    const pp_ring_meta *meta;
+    uint32_t n_rings;
+    const float4 *aabb32;
+    uint32_t n_aabb_tiles;
+    const uint32_t *cell_start, *cell_items;
+    int gx, gy;
+    double gminx, gminy, ginv;
+};
+
+
+// ---------------------------------------------------------------------------------------------
+// sm_100a primitives: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t pp_smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void pp_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pp_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pp_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void pp_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pp_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pp_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(pp_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completion on `bar`
+__device__ __forceinline__ void pp_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pp_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(pp_smem_u32(bar))
+                 : "memory");
+}
+#endif

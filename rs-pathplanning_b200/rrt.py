@@ -1,0 +1,257 @@
+"""Host mirror of the crate's `rrt` module (/root/reference/src/rrt.rs) over the C-ABI.
+
+Kept from the reference: Robot (:17-40), create_circle (:43-60), Space (:70-159; verify on the GPU),
+Node / NodeIter (:161-265), line_to_origin (:291-321, node->root chunk order), RRT (:325-619) with
+get_nearest_node, get_random_node, verify_node, check_finish, optimize, optimize_from_goal, finalize,
+plan_one and plan.  The tree lives twice: Python Node objects (parent links, as Arc<Node>) and a flat SoA
+mirror on the GPU that the NN kernel scans.
+Out of scope: Space::new's geo-offset inflation -- bounds and obstacles
+are taken as already shrunk / inflated; rand_point uses a seedable numpy Generator instead of thread_rng.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi, synth
+from .dubins import DubinsConfig
+
+RECURSION_LIMIT = 16  # src/rrt.rs:14
+Ring = Tuple[np.ndarray, np.ndarray]
+
+
+class Robot:  # src/rrt.rs:17-40
+    def __init__(self, width: float, height: float, max_steer: float):
+        self.width, self.height, self.max_steer = width, height, max_steer
+
+    def get_width(self):
+        return self.width
+
+    def get_steer(self):
+        return self.max_steer
+
+
+def create_circle(center: Tuple[float, float], radius: float) -> Ring:  # src/rrt.rs:43-60
+    return synth.create_circle(float(center[0]), float(center[1]), float(radius))
+
+
+def _closed(ring: Ring) -> Ring:
+    x, y = np.asarray(ring[0], np.float64), np.asarray(ring[1], np.float64)
+    if x.size and (x[0] != x[-1] or y[0] != y[-1]):  # Polygon::new closes rings
+        x, y = np.append(x, x[0]), np.append(y, y[0])
+    return x, y
+
+
+class Space:  # src/rrt.rs:70-159
+    def __init__(self, bounds: Ring, robot: Robot, obstacle_list: Sequence[Ring], ctx=None, seed=None):
+        from . import default_context
+        self.ctx = ctx or default_context()
+        self.bounds = _closed(bounds)
+        self.robot = robot
+        self.obstacles = [_closed(o) for o in obstacle_list]
+        bx, by = self.bounds
+        self.minx, self.maxx, self.miny, self.maxy = float(bx.min()), float(bx.max()), float(by.min()), float(by.max())
+        self._rng = np.random.default_rng(seed)
+        self.ctx.obstacles_upload(self.bounds, self.obstacles)
+
+    def verify(self, line: Ring) -> bool:  # src/rrt.rs:124-137
+        return bool(self.ctx.verify_polylines([line])[0])
+
+    def verify_many(self, lines: Sequence[Ring]) -> np.ndarray:
+        return self.ctx.verify_polylines(list(lines)).astype(bool)
+
+    def rand_point(self) -> Tuple[float, float]:  # src/rrt.rs:139-146
+        return (float(self._rng.uniform(self.minx, self.maxx)), float(self._rng.uniform(self.miny, self.maxy)))
+
+    def get_steer(self):
+        return self.robot.get_steer()
+
+    def get_obs(self):
+        return list(self.obstacles)
+
+    def get_bounds(self):
+        return self.bounds
+
+
+def compute_yaw(frm: Tuple[float, float], to: Tuple[float, float]) -> float:  # src/rrt.rs:267-271
+    return math.atan2(to[1] - frm[1], to[0] - frm[0])
+
+
+class Node:  # src/rrt.rs:161-214
+    __slots__ = ("point", "parent", "yaw")
+
+    def __init__(self, point: Tuple[float, float], parent: "Node"):
+        self.point = (float(point[0]), float(point[1]))
+        self.parent = parent
+        self.yaw = compute_yaw(self.point, parent.get_point())
+
+    @classmethod
+    def new_root(cls, point, yaw) -> "Node":
+        n = object.__new__(cls)
+        n.point, n.parent, n.yaw = (float(point[0]), float(point[1])), None, float(yaw)
+        return n
+
+    @classmethod
+    def new_goal(cls, point, parent: "Node", yaw) -> "Node":
+        n = object.__new__(cls)
+        n.point, n.parent, n.yaw = (float(point[0]), float(point[1])), parent, float(yaw)
+        return n
+
+    def get_parent(self) -> Optional["Node"]:
+        return self.parent
+
+    def get_above(self) -> "NodeIter":
+        return NodeIter(self.parent)
+
+    def get_point(self):
+        return self.point
+
+    def get_coord(self):
+        return self.point
+
+    def get_yaw(self):
+        return self.yaw
+
+
+class NodeIter:  # src/rrt.rs:248-265
+    def __init__(self, curr: Optional[Node]):
+        self.curr = curr
+
+    def __iter__(self) -> Iterator[Node]:
+        return self
+
+    def __next__(self) -> Node:
+        if self.curr is None:
+            raise StopIteration
+        c = self.curr
+        self.curr = c.get_parent()
+        return c
+
+
+def _chain_edges(node: Node):
+    """(child, parent) pose pairs along node -> root"""
+    sx, sy, syaw, ex, ey, eyaw = [], [], [], [], [], []
+    for n in NodeIter(node):
+        p = n.get_parent()
+        if p is None:
+            break
+        sx.append(n.point[0]); sy.append(n.point[1]); syaw.append(n.yaw)
+        ex.append(p.point[0]); ey.append(p.point[1]); eyaw.append(p.yaw)
+    return sx, sy, syaw, ex, ey, eyaw
+
+
+def line_to_origin(node: Node, turn_radius: float, step_size: float, ctx=None) -> Ring:  # src/rrt.rs:291-321
+    """polyline node -> root: per-edge Dubins samples (one batched GPU call), then the root's point"""
+    from . import default_context
+    ctx = ctx or default_context()
+    sx, sy, syaw, ex, ey, eyaw = _chain_edges(node)
+    xs: List[np.ndarray] = []
+    ys: List[np.ndarray] = []
+    if sx:
+        counts, plan = ctx.dubins_sample_count(sx, sy, syaw, ex, ey, eyaw, turn_radius, step_size)
+        out, offsets = ctx.dubins_sample_fill(plan, counts)
+        words = np.frombuffer(plan, np.uint8).reshape(-1, _ffi.PLAN_BYTES)[:, 104]
+        for i in range(len(sx)):
+            if words[i] == _ffi.WORD_NONE:  # src/rrt.rs:313
+                xs.append(np.array([sx[i]])); ys.append(np.array([sy[i]]))
+            else:
+                o, c = int(offsets[i]), int(counts[i])
+                xs.append(out[o:o + c, 0]); ys.append(out[o:o + c, 1])
+    root = node
+    while root.get_parent() is not None:
+        root = root.get_parent()
+    xs.append(np.array([root.point[0]])); ys.append(np.array([root.point[1]]))
+    return np.concatenate(xs), np.concatenate(ys)
+
+
+def euclidean_length(line: Ring) -> float:
+    x, y = line
+    return float(np.hypot(np.diff(x), np.diff(y)).sum()) if len(x) > 1 else 0.0
+
+
+class RRT:  # src/rrt.rs:325-619
+    def __init__(self, start, start_yaw, goal, goal_yaw, max_iter: int, step_size: float, space: Space):
+        self.goal, self.goal_yaw = (float(goal[0]), float(goal[1])), float(goal_yaw)
+        self.max_iter, self.step_size, self.space = int(max_iter), float(step_size), space
+        self.ctx = space.ctx
+        root = Node.new_root(start, start_yaw)
+        self.nodes: List[Node] = [root]  # index i <-> device tree slot i (replaces the RTree, :345-346)
+        self.ctx.tree_upload([root.point[0]], [root.point[1]], [root.yaw], [-1])
+
+    # -- src/rrt.rs:378-391
+    def get_nearest_node(self, point) -> Optional[Node]:
+        idx = self.ctx.nn([point[0]], [point[1]], want_d2=False)
+        return None if idx[0] == 0xFFFFFFFF else self.nodes[int(idx[0])]
+
+    # -- src/rrt.rs:406-412
+    def get_random_node(self) -> Optional[Node]:
+        point = self.space.rand_point()
+        nearest = self.get_nearest_node(point)
+        return None if nearest is None else Node(point, nearest)
+
+    # -- src/rrt.rs:414-426 : verify of the whole chain = AND over its edges (each = samples ++ [parent])
+    def verify_node(self, node: Node) -> bool:
+        sx, sy, syaw, ex, ey, eyaw = _chain_edges(node)
+        if not sx:
+            return self.space.verify((np.array([node.point[0]]), np.array([node.point[1]])))
+        ok = self.ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, self.space.get_steer(), self.step_size)
+        return bool(ok.all())
+
+    def _insert(self, node: Node):  # src/rrt.rs:586-589
+        self.nodes.append(node)
+        par = self.nodes.index(node.parent) if node.parent is not None else -1
+        self.ctx.tree_append([node.point[0]], [node.point[1]], [node.yaw], [par])
+
+    # -- src/rrt.rs:428-438
+    def check_finish(self, node: Node) -> Optional[Ring]:
+        goal_node = Node.new_goal(self.goal, node, self.goal_yaw)
+        line = self.finalize(goal_node)
+        return line if self.space.verify(line) else None
+
+    # -- src/rrt.rs:463-487
+    def optimize(self, node: Node, i: int) -> Optional[Node]:
+        if i >= RECURSION_LIMIT:
+            return None
+        nodes_vec = list(NodeIter(node))
+        for to_node in reversed(nodes_vec):
+            new_node = Node(node.get_coord(), to_node)
+            if self.verify_node(new_node):
+                deeper = self.optimize(to_node, i + 1)
+                return Node(node.get_coord(), deeper) if deeper is not None else new_node
+        return None
+
+    # -- src/rrt.rs:489-501
+    def optimize_from_goal(self, goal_node: Node) -> Node:
+        parent = goal_node.get_parent()
+        if parent is None:
+            return goal_node
+        n = self.optimize(parent, 0)
+        return Node.new_goal(goal_node.get_coord(), n, self.goal_yaw) if n is not None else goal_node
+
+    # -- src/rrt.rs:503-540 : root contributes nothing, result reversed (start -> goal)
+    def finalize(self, goal_node: Node) -> Ring:
+        top = self.optimize_from_goal(goal_node)
+        lx, ly = line_to_origin(top, self.space.get_steer(), self.step_size, self.ctx)
+        lx, ly = lx[:-1], ly[:-1]  # drop the root's own point (None => vec![] at :532)
+        return lx[::-1].copy(), ly[::-1].copy()
+
+    # -- src/rrt.rs:583-597
+    def plan_one(self) -> Optional[Ring]:
+        rnd = self.get_random_node()
+        if rnd is not None and self.verify_node(rnd):
+            self._insert(rnd)
+            return self.check_finish(rnd)
+        return None
+
+    # -- src/rrt.rs:599-619 (the reference's 4 racy workers become sequential iterations)
+    def plan(self) -> Optional[Ring]:
+        best, best_len = None, math.inf
+        for _ in range(self.max_iter):
+            r = self.plan_one()
+            if r is not None:
+                l = euclidean_length(r)
+                if l < best_len:
+                    best, best_len = r, l
+        return best

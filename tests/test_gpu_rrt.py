@@ -1,0 +1,206 @@
+"""GPU parity: nearest neighbour, Space::verify on segments / polylines / Dubins edges and the batched
+extend step against the CPU oracle, through the C-ABI.  NN indices and straight-edge flags are bit-exact."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NN_DEFAULT, NN_PLAIN, NN_GRID = 0, 1, 2
+DEFAULT, NO_CULL, USE_GRID = 0, 1, 2
+
+
+def _bench_world(pp):
+    """benches/all.rs:8-30 (no geo-offset inflation)"""
+    rings = [pp.rrt.create_circle(c, r) for c, r in
+             [((5.0, 5.0), 1.0), ((3.0, 6.0), 2.0), ((3.0, 8.0), 2.0), ((3.0, 10.0), 2.0), ((7.0, 5.0), 2.0), ((9.0, 5.0), 2.0)]]
+    bounds = (np.array([-6.0, -6.0, 15.0, 15.0, -6.0]), np.array([-6.0, 15.0, 15.0, -6.0, -6.0]))
+    return bounds, rings
+
+
+@pytest.mark.parametrize("n_nodes,m", [(1, 10), (7, 300), (1000, 5000), (1024, 2048), (50_000, 20_000), (3000, 3)])
+@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID])
+def test_nn_bit_exact(ctx, O, pp, n_nodes, m, flags):
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(m, n_nodes, world=1000.0)
+    ctx.tree_upload(nx, ny, nyaw)
+    idx, d2 = ctx.nn(qx, qy, flags=flags)
+    oidx, od2 = O.nn_brute(nx, ny, qx, qy)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(d2, od2)  # same non-fused arithmetic -> same bits
+
+
+@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID])
+def test_nn_ties_lowest_index(ctx, O, flags):
+    # lattice nodes duplicated 3x: every query has exact ties, some at equal distance to 4 lattice points
+    g = np.arange(0, 20, dtype=np.float64)
+    gx, gy = np.meshgrid(g, g)
+    nx = np.tile(gx.ravel(), 3)
+    ny = np.tile(gy.ravel(), 3)
+    qx = np.concatenate([gx.ravel()[:150] + 0.5, gx.ravel()[:150], np.array([-5.0, 30.0, 9.5])])
+    qy = np.concatenate([gy.ravel()[:150] + 0.5, gy.ravel()[:150] + 0.25, np.array([-5.0, 30.0, 9.5])])
+    ctx.tree_upload(nx, ny)
+    idx, d2 = ctx.nn(qx, qy, flags=flags)
+    oidx, od2 = O.nn_brute(nx, ny, qx, qy)
+    assert np.array_equal(idx, oidx) and np.array_equal(d2, od2)
+    assert idx.max() < gx.size  # always the first copy
+
+
+def test_nn_empty_tree_and_append(ctx, O, pp):
+    ctx.tree_upload(np.zeros(0), np.zeros(0))
+    idx = ctx.nn([1.0, 2.0], [3.0, 4.0], want_d2=False)
+    assert np.all(idx == 0xFFFFFFFF)
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(500, 3000, world=50.0)
+    ctx.tree_upload(nx[:10], ny[:10], nyaw[:10])
+    for a, b in [(10, 11), (11, 1024), (1024, 1030), (1030, 3000)]:
+        ctx.tree_append(nx[a:b], ny[a:b], nyaw[a:b], np.arange(a, b) - 1)
+        assert ctx.tree_size == b
+        for flags in (NN_DEFAULT, NN_GRID):
+            idx = ctx.nn(qx, qy, flags=flags, want_d2=False)
+            assert np.array_equal(idx, O.nn_brute(nx[:b], ny[:b], qx, qy)[0])
+    one = ctx.nn([qx[0]], [qy[0]], want_d2=False)  # scalar call -> wide kernel
+    assert one[0] == O.nn_brute(nx, ny, qx[:1], qy[:1])[0][0]
+
+
+def test_nn_nonfinite(ctx, O):
+    nx = np.array([0.0, np.nan, 5.0, np.inf, 1.0])
+    ny = np.array([0.0, 1.0, np.nan, 2.0, 1.0])
+    qx = np.array([0.9, np.nan, 100.0])
+    qy = np.array([0.9, 0.0, 100.0])
+    ctx.tree_upload(nx, ny)
+    for flags in (NN_DEFAULT, NN_PLAIN, NN_GRID):
+        idx = ctx.nn(qx, qy, flags=flags, want_d2=False)
+        assert np.array_equal(idx, O.nn_brute(nx, ny, qx, qy)[0]), flags
+
+
+@pytest.mark.parametrize("flags", [DEFAULT, NO_CULL, USE_GRID])
+def test_collide_segments_random_world(ctx, O, pp, flags):
+    bounds, rings = pp.synth.circle_world(300, world=100.0, rmin=1.0, rmax=3.0)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    m = 20_000 if flags != NO_CULL else 4000
+    rng = np.random.default_rng(5)
+    ax, ay = rng.uniform(-2, 102, m), rng.uniform(-2, 102, m)
+    ln = rng.choice([0.3, 2.0, 15.0], m)
+    th = rng.uniform(-math.pi, math.pi, m)
+    bx, by = ax + ln * np.cos(th), ay + ln * np.sin(th)
+    ok = ctx.collide_segments(ax, ay, bx, by, flags=flags)
+    ook = W.verify_segments(ax, ay, bx, by)
+    assert np.array_equal(ok, ook)
+    assert 0 < ok.sum() < m  # both outcomes present
+
+
+def test_collide_segments_bench_world_and_boundary_cases(ctx, O, pp):
+    bounds, rings = _bench_world(pp)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    rx, ry = rings[1]
+    ax = np.array([-5.0, -6.0, 0.0, rx[0], rx[2], 3.0, 3.0, -5.9999999, 14.0, 5.0, 0.0, -7.0, 3.0 + 1e-13])
+    ay = np.array([-5.0, 0.0, 0.0, ry[0], ry[2], 6.0, 6.0, -5.0, 14.0, 3.9, 15.0, 0.0, 6.0])
+    bx = np.array([-4.0, -5.0, 14.0, rx[0], rx[3], 3.1, 12.0, -5.0, 14.5, 5.0, 0.0, 0.0, 3.0 + 1e-13])
+    by = np.array([-4.0, 0.0, 0.0, ry[0], ry[3], 6.1, 6.0, -5.0, 14.5, 4.1, 14.0, 0.0, 6.0])
+    for flags in (DEFAULT, NO_CULL, USE_GRID):
+        ok = ctx.collide_segments(ax, ay, bx, by, flags=flags)
+        assert np.array_equal(ok, W.verify_segments(ax, ay, bx, by)), flags
+    # degenerate segments (a == b) and points exactly on the bounds ring are not contained
+    on = ctx.collide_segments([-6.0, 15.0, 0.0], [0.0, 3.0, -6.0], [-6.0, 15.0, 0.0], [0.0, 3.0, -6.0])
+    assert not on.any()
+
+
+def test_collide_transit_fixture(ctx, O):
+    """the reference's only shipped world (examples/rrt/transit.debug.json), re-encoded as tests/golden/transit_world.json"""
+    path = os.path.join(os.path.dirname(__file__), "golden", "transit_world.json")
+    conf = json.load(open(path))
+    b = np.stack([np.array(conf["bounds_x"]), np.array(conf["bounds_y"])], axis=1)
+    rings = [(np.array(o["x"]), np.array(o["y"])) for o in conf["rings"]]
+    bounds = (b[:, 0].copy(), b[:, 1].copy())
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    rng = np.random.default_rng(9)
+    m = 30_000
+    ax = rng.uniform(b[:, 0].min() - 2, b[:, 0].max() + 2, m)
+    ay = rng.uniform(b[:, 1].min() - 2, b[:, 1].max() + 2, m)
+    th = rng.uniform(-math.pi, math.pi, m)
+    ln = rng.choice([0.1, 3.0, 30.0], m)
+    bx, by = ax + ln * np.cos(th), ay + ln * np.sin(th)
+    want = W.verify_segments(ax, ay, bx, by)
+    for flags in (DEFAULT, USE_GRID):
+        assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=flags), want), flags
+    assert 0 < want.sum() < m
+    # start -> goal as one straight line, and as the reference's start/goal poses
+    s, g = conf["start"], conf["goal"]
+    assert ctx.collide_segments([s[0]], [s[1]], [g[0]], [g[1]])[0] == W.verify_segments([s[0]], [s[1]], [g[0]], [g[1]])[0]
+
+
+def test_verify_polylines(ctx, O, pp):
+    bounds, rings = pp.synth.circle_world(200, world=100.0)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    rng = np.random.default_rng(11)
+    lines = []
+    for k in range(400):
+        npts = int(rng.choice([0, 1, 2, 3, 31, 32, 33, 64, 100]))
+        x0, y0 = rng.uniform(5, 95, 2)
+        stepx, stepy = rng.normal(0, 0.4, npts), rng.normal(0, 0.4, npts)
+        lines.append((x0 + np.cumsum(stepx), y0 + np.cumsum(stepy)))
+    want = np.array([W.verify(lx, ly) for lx, ly in lines], np.uint8)
+    for flags in (DEFAULT, NO_CULL):
+        assert np.array_equal(ctx.verify_polylines(lines, flags=flags), want), flags
+    assert 0 < want.sum() < len(lines)
+
+
+@pytest.mark.parametrize("radius,step", [(1.0, 0.05), (0.8, 0.1)])
+def test_collide_dubins_edges(ctx, O, pp, radius, step):
+    bounds, rings = pp.synth.circle_world(400, world=100.0, rmin=0.5, rmax=1.5)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    e = 3000
+    sx, sy, syaw, ex, ey, eyaw = pp.synth.dubins_edges(e, world=100.0, reach=12.0)
+    ok = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, radius, step)
+    want = W.verify_dubins_edges(sx, sy, syaw, ex, ey, eyaw, radius, step)
+    # sample coordinates agree to 1e-9, so a flag can only differ when a sample grazes an edge within that
+    assert (ok != want).sum() <= 2
+    assert 0 < want.sum() < e
+    ok2 = ctx.collide_dubins(sx[:300], sy[:300], syaw[:300], ex[:300], ey[:300], eyaw[:300], radius, step, flags=NO_CULL)
+    assert (ok2 != want[:300]).sum() <= 1
+
+
+def test_extend_step(ctx, O, pp):
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(30_000, 20_000, world=200.0)
+    bounds, rings = pp.synth.circle_world(500, world=200.0)
+    ctx.tree_upload(nx, ny, nyaw)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    oidx, _ = O.nn_brute(nx, ny, qx, qy)
+    want = W.verify_segments(qx, qy, nx[oidx], ny[oidx])
+    wyaw = np.arctan2(ny[oidx] - qy, nx[oidx] - qx)
+    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_PLAIN, DEFAULT)]:
+        idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=nnf, collide_flags=cf)
+        assert np.array_equal(idx, oidx) and np.array_equal(ok, want)
+        assert np.abs(yaw - wyaw).max() < 1e-12
+    assert 0 < want.sum() < want.size
+
+
+def test_rrt_planner_drop_in(pp, ctx, O):
+    """benches/all.rs:6-46 world through the module mirror: plan_one keeps tree and GPU mirror in step"""
+    r = pp.rrt
+    bounds, rings = _bench_world(pp)
+    space = r.Space(bounds, r.Robot(1.0, 1.0, 0.8), rings, ctx=ctx, seed=1234)
+    planner = r.RRT((-5.0, -5.0), math.radians(-45.0), (6.0, 10.0), math.radians(45.0), 8000, 0.1, space)
+    W = O.OracleWorld(bounds, rings)
+    for _ in range(40):
+        planner.plan_one()
+    assert ctx.tree_size == len(planner.nodes) >= 2
+    # every node in the tree has a chain the oracle also accepts (same polyline, same verify)
+    nx = np.array([n.point[0] for n in planner.nodes]); ny = np.array([n.point[1] for n in planner.nodes])
+    nyaw = np.array([n.yaw for n in planner.nodes])
+    par = np.array([planner.nodes.index(n.parent) if n.parent is not None else -1 for n in planner.nodes], np.int32)
+    for i in range(1, min(len(planner.nodes), 12)):
+        lx, ly = O.line_to_origin(nx, ny, nyaw, par, i, 0.8, 0.1)
+        gx, gy = r.line_to_origin(planner.nodes[i], 0.8, 0.1, ctx)
+        assert len(lx) == len(gx) and np.abs(lx - gx).max() < 1e-9 and np.abs(ly - gy).max() < 1e-9
+        assert W.verify(lx, ly)
+    q = (1.0, 1.0)
+    assert planner.get_nearest_node(q) is planner.nodes[int(O.nn_brute(nx, ny, [q[0]], [q[1]])[0][0])]
