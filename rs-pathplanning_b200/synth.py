@@ -1,6 +1,6 @@
 """Counter-based synthetic inputs: element i of any array is
 u = splitmix64_finalise(seed + stream*2^56 + (i+1)*0x9E3779B97F4A7C15), uniform = (u >> 11) * 2^-53,
-U[a,b) = a + (b-a)*uniform (non-fused).  Identical bit-for-bit to oracle/pp_oracle.c:ppo_uniform."""
+U[a,b) = a + (b-a)*uniform (non-fused); one `stream` id per array, so element i is position-independent."""
 from __future__ import annotations
 
 import numpy as np
