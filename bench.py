@@ -411,6 +411,10 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
 
 
 def main():
+    # libraries (NCCL's version banner, ...) may print to fd 1: keep the real stdout for the one JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

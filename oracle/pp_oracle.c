@@ -20,16 +20,18 @@
 #define PI 3.14159265358979323846
 #define TWO_PI (2.0 * PI)
 
+/* host cores available to this process; deliberately NOT omp_get_max_threads(): torchrun exports
+ * OMP_NUM_THREADS=1, and the CPU baseline must use all the host threads it can */
 int ppo_max_threads(void) {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return omp_get_num_procs();
 #else
     return 1;
 #endif
 }
 static int resolve_threads(int nthreads) {
     int mx = ppo_max_threads();
-    if (nthreads <= 0 || nthreads > mx) return mx;
+    if (nthreads <= 0) return mx;
     return nthreads;
 }
 

@@ -21,6 +21,8 @@ int pp_launch_dubins_plan(pp_ctx *, size_t, const double *, const double *, cons
 int pp_launch_dubins_fill(pp_ctx *, size_t, const void *, const uint64_t *, double *, cudaStream_t);
 int pp_launch_exclusive_scan(pp_ctx *, size_t, const uint32_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
 int pp_nn_configure(pp_ctx *);
+int pp_dubins_tu_init(pp_ctx *);
+int pp_collide_tu_init(pp_ctx *);
 size_t pp_nn_tile_nodes();
 int pp_launch_nn(pp_ctx *, size_t, const double *, const double *, uint32_t *, double *, int, cudaStream_t);
 int pp_launch_tree_finish(pp_ctx *, size_t, size_t, size_t, cudaStream_t);
@@ -143,7 +145,7 @@ int pp_ctx_create(int device, pp_ctx **out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
         ctx->active_stream = ctx->stream;
-        ok = pp_nn_configure(ctx) == PP_OK;
+        ok = pp_nn_configure(ctx) == PP_OK && pp_dubins_tu_init(ctx) == PP_OK && pp_collide_tu_init(ctx) == PP_OK;
     }
     if (!ok) {
         pp_ctx_destroy(ctx);

@@ -364,3 +364,9 @@ int pp_launch_collide_dubins(pp_ctx *ctx, size_t m, const void *plans, const dou
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;
 }
+
+// uploads this translation unit's copy of the math coefficient tables (pp_math.cuh) to the current device
+int pp_collide_tu_init(pp_ctx *ctx) {
+    PP_CUDA(ctx, pp_math_upload_tables());
+    return PP_OK;
+}

@@ -347,3 +347,9 @@ int pp_launch_exclusive_scan(pp_ctx *ctx, size_t n, const uint32_t *counts, uint
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;
 }
+
+// uploads this translation unit's copy of the math coefficient tables (pp_math.cuh) to the current device
+int pp_dubins_tu_init(pp_ctx *ctx) {
+    PP_CUDA(ctx, pp_math_upload_tables());
+    return PP_OK;
+}

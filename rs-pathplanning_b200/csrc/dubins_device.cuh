@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "../../include/pathplanning_b200.h"
+#include "pp_math.cuh"
 
 #define PP_PI 3.14159265358979323846
 #define PP_TWO_PI 6.28318530717958647692   // == 2.0 * PI exactly in binary64
@@ -54,8 +55,13 @@ struct pp_dubins_frame {
 __device__ __forceinline__ pp_dubins_frame pp_dubins_frame_from_local(double lex, double ley, double leyaw,
                                                                       double c) {
     pp_dubins_frame f;
+#ifdef PP_DUBINS_LIBM
     f.d = hypot(lex, ley) * c;
     double a = atan2(ley, lex);  // [-pi, pi]
+#else
+    f.d = sqrt(fma(lex, lex, ley * ley)) * c;  // world-scale coordinates: no overflow guard needed (<= 1 ulp)
+    double a = pp_atan2(ley, lex);
+#endif
     // theta = mod2pi(a): floor(a/2pi) is -1 for a < 0, else 0 (and -0 -> +0)
     double theta = (a < 0.0) ? (a + PP_TWO_PI) : (a + 0.0);
     // alpha = mod2pi(-theta), theta in [0, 2pi]: floor(-theta/2pi) is -1 unless theta == 0
@@ -69,7 +75,11 @@ __device__ __forceinline__ void pp_dubins_to_local(double sx, double sy, double 
                                                    double eyaw, double *lex, double *ley, double *leyaw,
                                                    double *sin_s, double *cos_s) {
     double ss, cs;
+#ifdef PP_DUBINS_LIBM
     sincos(syaw, &ss, &cs);
+#else
+    pp_sincos1(syaw, &ss, &cs);
+#endif
     double dx = ex - sx, dy = ey - sy;
     *lex = cs * dx + ss * dy;
     *ley = -ss * dx + cs * dy;
@@ -81,8 +91,8 @@ __device__ __forceinline__ void pp_dubins_to_local(double sx, double sy, double 
 // the six words (src/dubins.rs:27-153) + the selection fold (src/dubins.rs:347-363).
 // WANT_ALL: also store every word's (t,p,q) / feasibility (diagnostic entry pp_dubins_words).
 template <bool WANT_ALL>
-__device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double beta, double d, double *all_tpq,
-                                                         uint8_t *all_feas) {
+__device__ __forceinline__ pp_dubins_sol pp_dubins_solve_libm(double alpha, double beta, double d, double *all_tpq,
+                                                              uint8_t *all_feas) {
     double sa, ca, sb, cb;
     sincos(alpha, &sa, &ca);
     sincos(beta, &sb, &cb);
@@ -178,6 +188,143 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double be
         PP_CONSIDER(PP_LRL, feas, t, p, q);
     }
 #undef PP_CONSIDER
+    return best;
+}
+
+
+// N-way mod2pi (bit-exact like pp_mod2pi): the N reductions are interleaved and share ONE guard branch.
+template <int N>
+__device__ __forceinline__ void pp_mod2pi_n(double (&x)[N]) {
+    double k[N];
+    bool slow = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double q = x[i] * PP_INV_TWO_PI;
+        k[i] = floor(q);
+        const double f = q - k[i];
+        slow |= !(fabs(f - 0.5) < 0.5 - 1e-9) || !(fabs(q) < 1e5);
+    }
+    if (slow) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[i] = floor(x[i] / PP_TWO_PI);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = x[i] - PP_TWO_PI * k[i];
+}
+
+// The six words + selection, written for the FP64 pipe (default).  Differences from the libm version:
+//   * sincos(alpha), sincos(beta) as one 2-way batch of the hand-written kernel; cos(alpha-beta) from the
+//     angle-difference identity (3 DP instructions instead of a third trig call)
+//   * LSR / RSL: atan2(y1,x1) - atan2(y2,x2) is folded into ONE atan2(y1 x2 - x1 y2, x1 x2 + y1 y2); the
+//     result differs by a multiple of 2 pi, which the following mod2pi removes
+//   * acos(v) = atan2(sqrt((1-v)(1+v)), v): the two CCC words join the same batch
+//   * the six atan2 and the twelve mod2pi run as interleaved batches (coefficients fetched once, 6-12
+//     independent dependency chains in flight)
+// All of it stays inside the 1e-9 contract; t/q agree with the reference to a few ulp away from the wrap.
+template <bool WANT_ALL>
+__device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double beta, double d, double *all_tpq,
+                                                         uint8_t *all_feas) {
+    double sn[2], cs[2];
+    {
+        const double ang[2] = {alpha, beta};
+        pp_sincos_n<2>(ang, sn, cs);
+    }
+    const double sa = sn[0], sb = sn[1], ca = cs[0], cb = cs[1];
+    const double c_ab = fma(ca, cb, sa * sb);
+    const double dd = d * d;
+    const double two_cab = 2.0 * c_ab;
+    const double two_d = 2.0 * d;
+    const double mbeta = pp_mod2pi_unit(beta);
+
+    const double sa_m_sb = sa - sb, sa_p_sb = sa + sb;
+    const double base_csc = (2.0 + dd) - two_cab;
+    const double base_cross = (-2.0 + dd) + two_cab;
+    const double base_ccc = (6.0 - dd) + two_cab;
+    const double psq_lsl = base_csc + two_d * sa_m_sb;
+    const double psq_rsr = base_csc - two_d * sa_m_sb;
+    const double psq_lsr = base_cross + two_d * sa_p_sb;
+    const double psq_rsl = base_cross - two_d * sa_p_sb;
+    const double tmp_rlr = (base_ccc + two_d * sa_m_sb) * 0.125;
+    const double tmp_lrl = (base_ccc - two_d * sa_m_sb) * 0.125;
+    const bool f_lsl = !(psq_lsl < 0.0), f_rsr = !(psq_rsr < 0.0), f_lsr = !(psq_lsr < 0.0), f_rsl = !(psq_rsl < 0.0);
+    const bool f_rlr = !(fabs(tmp_rlr) > 1.0), f_lrl = !(fabs(tmp_lrl) > 1.0);
+    // infeasible words get harmless stand-in arguments (masked at the selection): a clamp to 0 / +-1 would
+    // send sqrt(0) and 0/x down the IEEE slow paths of sqrt and division in nearly every warp
+    const double v_rlr = f_rlr ? tmp_rlr : 0.5, v_lrl = f_lrl ? tmp_lrl : 0.5;
+
+    const double p_lsl = sqrt(f_lsl ? psq_lsl : 1.0), p_rsr = sqrt(f_rsr ? psq_rsr : 1.0);
+    const double p_lsr = sqrt(f_lsr ? psq_lsr : 1.0), p_rsl = sqrt(f_rsl ? psq_rsl : 1.0);
+
+    // ---- six atan2 in one batch
+    double ay[6], ax[6], at[6];
+    ay[0] = cb - ca;  // LSL (and LRL, negated)
+    ax[0] = (d + sa) - sb;
+    ay[1] = ca - cb;  // RSR (and RLR)
+    ax[1] = (d - sa) + sb;
+    {   // LSR: atan2(-ca-cb, d+sa+sb) - atan2(-2, p)
+        const double y1 = -ca - cb, x1 = (d + sa) + sb;
+        ay[2] = fma(y1, p_lsr, 2.0 * x1);
+        ax[2] = fma(x1, p_lsr, -2.0 * y1);
+    }
+    {   // RSL: atan2(ca+cb, d-sa-sb) - atan2(2, p)
+        const double y1 = ca + cb, x1 = (d - sa) - sb;
+        ay[3] = fma(y1, p_rsl, -2.0 * x1);
+        ax[3] = fma(x1, p_rsl, 2.0 * y1);
+    }
+    pp_acos_as_atan2(v_rlr, &ay[4], &ax[4]);
+    pp_acos_as_atan2(v_lrl, &ay[5], &ax[5]);
+    pp_atan2_n<6>(ay, ax, at);
+
+    const double pc_rlr = pp_mod2pi_unit(PP_TWO_PI - at[4]);  // p of RLR, in [pi, 2pi] -> only 2pi wraps
+    const double pc_lrl = pp_mod2pi_unit(PP_TWO_PI - at[5]);
+
+    // ---- twelve mod2pi in two batches (q of the CCC words needs their t)
+    double m[10];
+    m[0] = -alpha + at[0];                     // LSL t
+    m[1] = beta - at[0];                       // LSL q
+    m[2] = alpha - at[1];                      // RSR t
+    m[3] = -beta + at[1];                      // RSR q
+    m[4] = -alpha + at[2];                     // LSR t
+    m[5] = -mbeta + at[2];                     // LSR q
+    m[6] = alpha - at[3];                      // RSL t
+    m[7] = beta - at[3];                       // RSL q
+    m[8] = (alpha - at[1]) + pc_rlr * 0.5;     // RLR t
+    m[9] = (-alpha + at[0]) + pc_lrl * 0.5;    // LRL t   (atan2(ca-cb, d+sa-sb) = -at[0])
+    pp_mod2pi_n<10>(m);
+    double m2[2];
+    m2[0] = ((alpha - beta) - m[8]) + pc_rlr;  // RLR q
+    m2[1] = ((mbeta - alpha) - m[9]) + pc_lrl; // LRL q
+    pp_mod2pi_n<2>(m2);
+
+    pp_dubins_sol best;
+    best.cost = CUDART_INF;
+    best.word = PP_WORD_NONE;
+    best.t = best.p = best.q = CUDART_NAN;
+#define PP_CONSIDER2(W, FEAS, T, P, Q)                    \
+    do {                                                  \
+        const double _c = (fabs(T) + fabs(P)) + fabs(Q);  \
+        const bool _f = (FEAS);                           \
+        if (WANT_ALL) {                                   \
+            all_feas[W] = _f ? 1 : 0;                     \
+            all_tpq[3 * W + 0] = _f ? (T) : CUDART_NAN;   \
+            all_tpq[3 * W + 1] = _f ? (P) : CUDART_NAN;   \
+            all_tpq[3 * W + 2] = _f ? (Q) : CUDART_NAN;   \
+        }                                                 \
+        if (_f && _c < best.cost) {                       \
+            best.cost = _c;                               \
+            best.word = W;                                \
+            best.t = (T);                                 \
+            best.p = (P);                                 \
+            best.q = (Q);                                 \
+        }                                                 \
+    } while (0)
+    PP_CONSIDER2(PP_LSL, f_lsl, m[0], p_lsl, m[1]);
+    PP_CONSIDER2(PP_RSR, f_rsr, m[2], p_rsr, m[3]);
+    PP_CONSIDER2(PP_LSR, f_lsr, m[4], p_lsr, m[5]);
+    PP_CONSIDER2(PP_RSL, f_rsl, m[6], p_rsl, m[7]);
+    PP_CONSIDER2(PP_RLR, f_rlr, m[8], pc_rlr, m2[0]);
+    PP_CONSIDER2(PP_LRL, f_lrl, m[9], pc_lrl, m2[1]);
+#undef PP_CONSIDER2
     return best;
 }
 

@@ -1,0 +1,163 @@
+// pp_math.cuh -- hand-written f64 sincos / atan2 / acos for the Dubins kernels.
+//
+// Why not CUDA's libm: on sm_100 a double constant is materialised with two 32-bit uniform moves, so the
+// inlined libm polynomials spend more issue slots on constants than on DFMAs (ncu, profiles/r01_summary.md:
+// 2 146 instructions per pose pair, only ~730 of them on the FP64 pipe).  Here the coefficient tables live in
+// __constant__ memory (one LDCU.128 fetches two doubles) and every routine is written as an N-way batch:
+// the N evaluations are interleaved instruction by instruction, so a coefficient is fetched once per batch
+// and the N independent dependency chains give the FP64 pipe its ILP.
+//
+// Accuracy (tests/test_math_host.py, 10^6 samples per function against glibc): sincos <= 1.5 ulp for
+// |x| < 1e5, atan2 <= 2 ulp, acos <= 2 ulp + 1e-16 absolute.  Coefficients: tools/gen_math_tables.py.
+// The header also compiles as plain C++ (g++) for that host-side accuracy test.
+#pragma once
+#include <math.h>
+
+#include "pp_math_tables.inc"
+
+#ifdef __CUDACC__
+#define PP_MATH_FN __device__ __forceinline__
+#define PP_MATH_TABLE static __constant__ double
+#define PP_UNROLL _Pragma("unroll")
+#else
+#define PP_MATH_FN static inline
+#define PP_MATH_TABLE static const double
+#define PP_UNROLL
+#endif
+
+// Coefficient tables.  On the device they are __constant__ arrays WITHOUT a static initialiser, filled by
+// pp_math_upload_tables() when a context is created: with an initialiser nvcc folds the values back into
+// the instruction stream as pairs of 32-bit uniform moves, which is exactly the overhead to avoid.  Each
+// translation unit that includes this header owns (and uploads) its private copy; 16-byte alignment lets a
+// pair of coefficients arrive with one LDCU.128.
+#ifdef __CUDACC__
+static __constant__ __attribute__((aligned(16))) double pp_sin_c[6];
+static __constant__ __attribute__((aligned(16))) double pp_cos_c[6];
+static __constant__ __attribute__((aligned(16))) double pp_atan_c[22];
+static inline cudaError_t pp_math_upload_tables() {
+    static const double h_sin[6] = PP_SIN_COEF, h_cos[6] = PP_COS_COEF, h_atan[22] = PP_ATAN_COEF;
+    cudaError_t e = cudaMemcpyToSymbol(pp_sin_c, h_sin, sizeof h_sin);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(pp_cos_c, h_cos, sizeof h_cos);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(pp_atan_c, h_atan, sizeof h_atan);
+    return e;
+}
+#else
+PP_MATH_TABLE pp_sin_c[6] = PP_SIN_COEF;
+PP_MATH_TABLE pp_cos_c[6] = PP_COS_COEF;
+PP_MATH_TABLE pp_atan_c[22] = PP_ATAN_COEF;
+#endif
+
+// ---- sincos: Cody-Waite reduction by pi/2 with three FMAs (pi/2 = P1 + P2 + P3 to ~160 bits), then the
+// two kernels sin(r) = r + r z S(z), cos(r) = 1 - z/2 + z^2 C(z) on |r| <= pi/4, swapped / negated by quadrant.
+// Valid for |x| < 1e5; larger or non-finite arguments take the library routine (rare branch).
+template <int N>
+PP_MATH_FN void pp_sincos_n(const double (&x)[N], double (&s)[N], double (&c)[N]) {
+    double r[N], z[N], ps[N], pc[N];
+    int q[N];
+    bool slow = false;
+    PP_UNROLL
+    for (int i = 0; i < N; ++i) {
+        // sin is odd, cos even: reduce |x| and put the sign back at the end (keeps sin(-0.0) = -0.0)
+        const double xa = fabs(x[i]);
+        slow |= !(xa < 1.0e5);
+        const double kf = rint(xa * PP_TWO_OVER_PI);
+        q[i] = (int)kf;
+        double t = fma(-kf, PP_PIO2_1, xa);
+        t = fma(-kf, PP_PIO2_2, t);
+        r[i] = fma(-kf, PP_PIO2_3, t);
+        z[i] = r[i] * r[i];
+        ps[i] = pp_sin_c[5];
+        pc[i] = pp_cos_c[5];
+    }
+    PP_UNROLL
+    for (int j = 4; j >= 0; --j) {
+        PP_UNROLL
+        for (int i = 0; i < N; ++i) {
+            ps[i] = fma(ps[i], z[i], pp_sin_c[j]);
+            pc[i] = fma(pc[i], z[i], pp_cos_c[j]);
+        }
+    }
+    PP_UNROLL
+    for (int i = 0; i < N; ++i) {
+        const double sr = fma(r[i] * z[i], ps[i], r[i]);
+        const double hz = 0.5 * z[i];
+        const double w = 1.0 - hz;
+        const double cr = w + (((1.0 - w) - hz) + (z[i] * z[i]) * pc[i]);
+        const bool swap = (q[i] & 1) != 0;
+        const double sv = swap ? cr : sr;
+        const double cv = swap ? sr : cr;
+        s[i] = (((q[i] & 2) != 0) != signbit(x[i])) ? -sv : sv;
+        c[i] = ((q[i] + 1) & 2) ? -cv : cv;
+    }
+    if (slow) {
+        PP_UNROLL
+        for (int i = 0; i < N; ++i)
+            if (!(fabs(x[i]) < 1.0e5)) {
+#ifdef __CUDACC__
+                sincos(x[i], &s[i], &c[i]);
+#else
+                s[i] = sin(x[i]);
+                c[i] = cos(x[i]);
+#endif
+            }
+    }
+}
+
+PP_MATH_FN void pp_sincos1(double x, double *s, double *c) {
+    const double xi[1] = {x};
+    double so[1], co[1];
+    pp_sincos_n<1>(xi, so, co);
+    *s = so[0];
+    *c = co[0];
+}
+
+// ---- atan2: a = min(|x|,|y|) / max(|x|,|y|) in [0,1], atan(a) = a + a s A(s) (degree-21 polynomial in
+// s = a^2), then the octant fix-ups pi/2 - r, pi - r and the sign of y.  Signed zeros follow C99
+// (atan2(+-0, -x) = +-pi, atan2(+-0, +x) = +-0); NaN propagates; (0, 0) gives +-0 or +-pi like glibc.
+template <int N>
+PP_MATH_FN void pp_atan2_n(const double (&y)[N], const double (&x)[N], double (&out)[N]) {
+    double a[N], s[N], p[N];
+    bool swp[N];
+    PP_UNROLL
+    for (int i = 0; i < N; ++i) {
+        const double ax = fabs(x[i]), ay = fabs(y[i]);
+        // one compare orders the pair (and is reused for the octant fix-up); a NaN operand makes the
+        // compare false and then reaches the quotient, so NaN propagates; inf/inf gives NaN (libm: pi/4 ...),
+        // which only happens for non-finite poses whose cost is not finite either
+        swp[i] = ay > ax;
+        const double mx = swp[i] ? ay : ax, mn = swp[i] ? ax : ay;
+        a[i] = mn / (mx + 0x1p-1000);  // (0, 0) -> 0; leaves every mx > 1e-285 unchanged; NaN propagates
+        s[i] = a[i] * a[i];
+        p[i] = pp_atan_c[21];
+    }
+    PP_UNROLL
+    for (int j = 20; j >= 0; --j) {
+        PP_UNROLL
+        for (int i = 0; i < N; ++i) p[i] = fma(p[i], s[i], pp_atan_c[j]);
+    }
+    PP_UNROLL
+    for (int i = 0; i < N; ++i) {
+        double r = fma(a[i] * s[i], p[i], a[i]);
+        if (swp[i]) r = (PP_PIO2 - r) + PP_PIO2_LO;
+        if (signbit(x[i])) r = (PP_PI_HI - r) + PP_PI_LO;
+        out[i] = copysign(r, y[i]);
+    }
+}
+
+PP_MATH_FN double pp_atan2(double y, double x) {
+    const double yi[1] = {y}, xi[1] = {x};
+    double o[1];
+    pp_atan2_n<1>(yi, xi, o);
+    return o[0];
+}
+
+// the argument pair that turns acos(v), |v| <= 1, into an atan2: acos(v) = atan2(sqrt((1-v)(1+v)), v)
+PP_MATH_FN void pp_acos_as_atan2(double v, double *y, double *x) {
+    *y = sqrt((1.0 - v) * (1.0 + v));
+    *x = v;
+}
+PP_MATH_FN double pp_acos(double v) {
+    double y, x;
+    pp_acos_as_atan2(v, &y, &x);
+    return pp_atan2(y, x);
+}
