@@ -341,7 +341,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
     ok = torch.empty(m, dtype=torch.uint8, device=dev)
     ref_idx = None
     for name, nnf, cf, kname in [("extend_scan", 0, 0, "nn_scan"), ("extend_scan_plain_f64", 1, 0, "nn_scan_f64"),
-                                 ("extend_grid", 2, 2, "nn_grid")]:
+                                 ("extend_scan_unsorted", 4, 0, "nn_scan_unsorted"), ("extend_grid", 2, 2, "nn_grid")]:
         ctx.timing_enable(True)
         fn = lambda: ctx.rrt_extend_dev(m, qx, qy, idx, yaw, ok, nn_flags=nnf, collide_flags=cf)  # noqa: E731
         fn()
@@ -406,6 +406,58 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
         "plan_kernel_ms": p_ms / max(p_n, 1), "verify_kernel_ms": v_ms / max(v_n, 1),
         "config": {"workload": f"c5 slice: {e} Dubins edges/GPU (2^22 over 8 GPUs), step 0.05, radius 1.0, vs {C5_RINGS} rings",
                    "free_fraction_rank0": float(ok5.float().mean().item())},
+    }
+    # same edges against the no-hit ring set: no early exit, every sample segment is generated and tested
+    _, rings6 = pp.synth.circle_world(C5_RINGS, rmin=0.5, rmax=1.5, shift=5000.0)
+    bx = np.array([-100.0, -100.0, 1100.0, 1100.0, -100.0])
+    ctx.obstacles_upload((bx, np.array([-100.0, 1100.0, 1100.0, -100.0, -100.0])), rings6)
+    ctx.timing_enable(True)
+    fn()
+    torch.cuda.synchronize()
+    ctx.timing_reset()
+    ms, _, _ = time_steps(torch, dist, fn, steps, 0, world)
+    v_ms, v_n = ctx.timing_get("collide_dubins")
+    ctx.timing_enable(False)
+    out["dubins_rrt_nohit"] = {
+        "metric": "dubins_edges_verified_per_s", "value": world * e * steps / (ms * 1e-3), "unit": "edges/s",
+        "ms_per_step": ms / steps, "verify_kernel_ms": v_ms / max(v_n, 1),
+        "config": {"workload": "c5 slice against rings translated outside the (enlarged) bounds: every sample is tested",
+                   "free_fraction_rank0": float(ok5.float().mean().item())},
+    }
+    # ---- sample materialisation (config-1 style paths in bulk): count -> prefix sum -> fill
+    ns = 1 << 16
+    se = [torch.from_numpy(a).to(dev) for a in pp.synth.dubins_edges(ns, first=rank * ns)]
+    counts = torch.empty(ns, dtype=torch.int32, device=dev)
+    plan = torch.empty(ns * 112, dtype=torch.uint8, device=dev)
+    offsets = torch.empty(ns, dtype=torch.int64, device=dev)
+    total_d = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.dubins_sample_count_dev(ns, *se, 1.0, 0.05, counts, plan)
+    ctx.exclusive_scan_u32_dev(ns, counts, offsets, total_d)
+    torch.cuda.synchronize()
+    total = int(total_d.item())
+    samples = torch.empty(total * 3, dtype=torch.float64, device=dev)
+
+    def fill_step():
+        ctx.dubins_sample_count_dev(ns, *se, 1.0, 0.05, counts, plan)
+        ctx.exclusive_scan_u32_dev(ns, counts, offsets, total_d)
+        ctx.dubins_sample_fill_dev(ns, plan, offsets, total, samples)
+
+    ctx.timing_enable(True)
+    fill_step()
+    torch.cuda.synchronize()
+    ctx.timing_reset()
+    l0 = ctx.launch_count
+    ms, _, _ = time_steps(torch, dist, fill_step, steps, 0, world)
+    f_ms, f_n = ctx.timing_get("dubins_fill")
+    ctx.timing_enable(False)
+    f_s = f_ms / max(f_n, 1) * 1e-3
+    out["dubins_sample"] = {
+        "metric": "dubins_samples_per_s", "value": world * total * steps / (ms * 1e-3), "unit": "samples/s",
+        "ms_per_step": ms / steps, "fill_kernel_ms": f_ms / max(f_n, 1), "gpu_launches": ctx.launch_count - l0,
+        "config": {"workload": f"{ns} Dubins paths/GPU (c5 edge distribution), step 0.05: count + scan + fill of {total} samples"},
+        "roofline": {"kernel": "pp_dubins_fill_kernel", "bound": "hbm", "achieved": total * 24.0 / f_s / 1e9, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": total * 24.0 / f_s / 1e9 / hbm_peak, "traffic": None,
+                     "per_unit": "24 B written per sample (+112 B plan record per path)"},
     }
     return out
 

@@ -62,9 +62,10 @@ enum pp_collide_flags {
 
 /* flags for pp_nn */
 enum pp_nn_flags {
-    PP_NN_DEFAULT = 0,   /* tiled brute-force scan with exact fp32 pre-rejection */
+    PP_NN_DEFAULT = 0,   /* tiled brute-force scan, queries binned by x, warp-wide exact fp32 pre-rejection */
     PP_NN_PLAIN_F64 = 1, /* tiled brute-force scan, every pair in f64 (the yard-stick kernel) */
-    PP_NN_GRID = 2       /* exact uniform-grid search (same argmin and tie-break) */
+    PP_NN_GRID = 2,      /* exact uniform-grid search (same argmin and tie-break) */
+    PP_NN_UNSORTED = 4   /* tiled scan with per-thread fp32 pre-rejection, queries in the caller's order */
 };
 
 /* bytes of the opaque per-path plan record produced by pp_dubins_sample_count */

@@ -13,13 +13,13 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpathplanning_b200.so")
+LIB_PATH = os.environ.get("PP_B200_LIB") or os.path.join(_PKG, "libpathplanning_b200.so")  # env: A/B builds
 
 PP_OK, PP_ERR_INVALID, PP_ERR_NO_DEVICE, PP_ERR_CUDA, PP_ERR_NOMEM, PP_ERR_STATE, PP_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5, -6
 WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
 WORD_NONE = 0xFF
 COLLIDE_DEFAULT, COLLIDE_NO_CULL, COLLIDE_USE_GRID = 0, 1, 2
-NN_DEFAULT, NN_PLAIN_F64, NN_GRID = 0, 1, 2
+NN_DEFAULT, NN_PLAIN_F64, NN_GRID, NN_UNSORTED = 0, 1, 2, 4
 PLAN_BYTES = 112
 
 if not os.path.exists(LIB_PATH):

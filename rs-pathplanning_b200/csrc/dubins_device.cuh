@@ -193,7 +193,8 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve_libm(double alpha, doub
 
 
 // N-way mod2pi (bit-exact like pp_mod2pi): the N reductions are interleaved and share ONE guard branch.
-template <int N>
+// BOUNDED: the caller guarantees |x| < 1e5 (or NaN), so the large-quotient guard is not needed.
+template <int N, bool BOUNDED = false>
 __device__ __forceinline__ void pp_mod2pi_n(double (&x)[N]) {
     double k[N];
     bool slow = false;
@@ -202,7 +203,8 @@ __device__ __forceinline__ void pp_mod2pi_n(double (&x)[N]) {
         const double q = x[i] * PP_INV_TWO_PI;
         k[i] = floor(q);
         const double f = q - k[i];
-        slow |= !(fabs(f - 0.5) < 0.5 - 1e-9) || !(fabs(q) < 1e5);
+        slow |= !(fabs(f - 0.5) < 0.5 - 1e-9);
+        if (!BOUNDED) slow |= !(fabs(q) < 1e5);
     }
     if (slow) {
 #pragma unroll
@@ -290,11 +292,11 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double be
     m[7] = beta - at[3];                       // RSL q
     m[8] = (alpha - at[1]) + pc_rlr * 0.5;     // RLR t
     m[9] = (-alpha + at[0]) + pc_lrl * 0.5;    // LRL t   (atan2(ca-cb, d+sa-sb) = -at[0])
-    pp_mod2pi_n<10>(m);
+    pp_mod2pi_n<10, true>(m);  // sums of a few angles in [-2pi, 2pi]
     double m2[2];
     m2[0] = ((alpha - beta) - m[8]) + pc_rlr;  // RLR q
     m2[1] = ((mbeta - alpha) - m[9]) + pc_lrl; // LRL q
-    pp_mod2pi_n<2>(m2);
+    pp_mod2pi_n<2, true>(m2);
 
     pp_dubins_sol best;
     best.cost = CUDART_INF;

@@ -279,6 +279,240 @@ __global__ void __launch_bounds__(128)
     if (d2_out) d2_out[j] = best;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bucketed scan (default for many queries).  The queries are binned by x (counting sort: histogram,
+// single-block scan, scatter) so that the 128 queries of a warp lie within a narrow x-band.  The warp
+// then keeps ONE outward-rounded float interval [wlo, whi] = union of its threads' rejection intervals
+// and tests 128 nodes per step: lane l compares fl32(x) of nodes 4l..4l+3 (one LDS.128) with the warp
+// interval, a ballot yields the (rare) candidate nodes, and only those go through the per-thread fp32 test and the
+// exact f64 evaluation.  Every node is still visited for every query (brute force, no index structure on
+// the tree), nodes are met in increasing index order and the comparison is strict, so the result is the
+// same bit-exact argmin with lowest-index tie-break.  Only the 4-byte fl32(x) stream goes through shared
+// memory (16 KB TMA tiles); x and y of a candidate are fetched from L2 (one broadcast load per warp).
+// ---------------------------------------------------------------------------------------------
+#define PP_NNS_TILE 4096
+#define PP_NNS_STAGES 3
+#define PP_NNS_THREADS 128
+#define PP_NNS_QPT 4
+#define PP_NNS_SMEM_BYTES (PP_NNS_STAGES * PP_NNS_TILE * 4 + PP_NNS_STAGES * 8)
+
+__device__ __forceinline__ unsigned long long pp_f64_key(double v) {  // order-preserving u64 key
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double pp_key_f64(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// mm[0] = min key, mm[1] = max key over the non-NaN query x (mm preset to {~0, 0})
+__global__ void __launch_bounds__(256)
+    pp_nn_qrange_kernel(const double *__restrict__ qx, size_t m, unsigned long long *__restrict__ mm) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (size_t)gridDim.x * 256) {
+        const double v = qx[i];
+        if (v == v) {
+            const unsigned long long k = pp_f64_key(v);
+            lo = min(lo, k);
+            hi = max(hi, k);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_down_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_down_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], lo);
+        atomicMax(&mm[1], hi);
+    }
+}
+
+__device__ __forceinline__ uint32_t pp_nn_bucket_of(double v, const unsigned long long *mm, uint32_t nb) {
+    const double lo = pp_key_f64(mm[0]), hi = pp_key_f64(mm[1]);
+    const double span = hi - lo;
+    if (!(v == v) || !(span > 0.0)) return 0;
+    const double f = (v - lo) * ((double)nb / span);
+    if (!(f > 0.0)) return 0;
+    return (f >= (double)nb) ? nb - 1 : (uint32_t)f;
+}
+
+__global__ void __launch_bounds__(256)
+    pp_nn_bucket_count_kernel(const double *__restrict__ qx, size_t m, const unsigned long long *__restrict__ mm,
+                              uint32_t nb, uint32_t *__restrict__ hist) {
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < m) atomicAdd(&hist[pp_nn_bucket_of(qx[i], mm, nb)], 1u);
+}
+
+// single block: exclusive scan of hist[nb] into cursor[nb] (nb <= 16384)
+__global__ void __launch_bounds__(1024) pp_nn_bucket_scan_kernel(const uint32_t *__restrict__ hist, uint32_t nb,
+                                                                 uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = (i < nb) ? hist[i] : 0;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane], winc = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sums[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sums[warp] + inc - v;
+        if (i < nb) cursor[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    pp_nn_bucket_scatter_kernel(const double *__restrict__ qx, size_t m, const unsigned long long *__restrict__ mm,
+                                uint32_t nb, uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm) {
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < m) perm[atomicAdd(&cursor[pp_nn_bucket_of(qx[i], mm, nb)], 1u)] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(PP_NNS_THREADS)
+    pp_nn_bucketed_kernel(const double *__restrict__ nx, const double *__restrict__ ny, const float *__restrict__ nx32,
+                          uint32_t n_tiles, const double *__restrict__ qx, const double *__restrict__ qy,
+                          const uint32_t *__restrict__ perm, size_t m, uint32_t *__restrict__ idx_out,
+                          double *__restrict__ d2_out) {
+    extern __shared__ __align__(128) unsigned char pp_nns_smem[];
+    float *tiles = reinterpret_cast<float *>(pp_nns_smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(pp_nns_smem + PP_NNS_STAGES * PP_NNS_TILE * 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // the q-th query of this thread: consecutive positions of the x-sorted order within the warp
+    const size_t warp_base = ((size_t)blockIdx.x * (PP_NNS_THREADS / 32) + warp) * (32 * PP_NNS_QPT);
+    uint32_t qi[PP_NNS_QPT];
+    double x[PP_NNS_QPT], y[PP_NNS_QPT], best[PP_NNS_QPT];
+    float lo[PP_NNS_QPT], hi[PP_NNS_QPT];
+    uint32_t bi[PP_NNS_QPT];
+#pragma unroll
+    for (int q = 0; q < PP_NNS_QPT; ++q) {
+        const size_t pos = warp_base + (size_t)q * 32 + lane;
+        const bool live = pos < m;
+        qi[q] = live ? perm[pos] : 0xFFFFFFFFu;
+        x[q] = live ? qx[qi[q]] : 0.0;
+        y[q] = live ? qy[qi[q]] : 0.0;
+        best[q] = CUDART_INF;
+        bi[q] = 0xFFFFFFFFu;
+        // dead slots get an empty interval so that they never widen the warp's
+        lo[q] = live ? -CUDART_INF_F : CUDART_INF_F;
+        hi[q] = live ? CUDART_INF_F : -CUDART_INF_F;
+    }
+
+    if (tid == 0) {
+        for (int s = 0; s < PP_NNS_STAGES; ++s) pp_mbar_init(&full[s], 1);
+        pp_fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (uint32_t t = 0; t < PP_NNS_STAGES && t < n_tiles; ++t) {
+            pp_mbar_expect_tx(&full[t], PP_NNS_TILE * 4);
+            pp_bulk_g2s(tiles + (size_t)t * PP_NNS_TILE, nx32 + (size_t)t * PP_NNS_TILE, PP_NNS_TILE * 4, &full[t]);
+        }
+    }
+
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const int s = t % PP_NNS_STAGES;
+        pp_mbar_wait(&full[s], (t / PP_NNS_STAGES) & 1u);
+        const uint32_t tile_addr = pp_smem_u32(tiles + (size_t)s * PP_NNS_TILE) + (uint32_t)lane * 16u;
+        const uint32_t base = t * PP_NNS_TILE;
+        float wlo = CUDART_INF_F, whi = -CUDART_INF_F;
+        // 128 nodes per step: lane l holds nodes 4l .. 4l+3 of the chunk (one LDS.128), so the candidate
+        // order (lane, then k) is the node index order
+#pragma unroll 2
+        for (int c = 0; c < PP_NNS_TILE / 128; ++c) {
+            if ((c & 3) == 0) {  // refresh the warp interval every 512 nodes (a stale one is only wider)
+                wlo = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
+                whi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    wlo = fminf(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+                    whi = fmaxf(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+                }
+            }
+            float4 xq;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(xq.x), "=f"(xq.y), "=f"(xq.z), "=f"(xq.w)
+                         : "r"(tile_addr + (uint32_t)c * 512u));
+            const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
+            // common case: no lane holds a candidate -> eight compares, one vote, one branch
+            const bool in0 = !((xv[0] > whi) || (xv[0] < wlo)), in1 = !((xv[1] > whi) || (xv[1] < wlo));
+            const bool in2 = !((xv[2] > whi) || (xv[2] < wlo)), in3 = !((xv[3] > whi) || (xv[3] < wlo));
+            unsigned mask = __ballot_sync(0xffffffffu, in0 || in1 || in2 || in3);
+            if (mask == 0u) continue;
+            const unsigned nib = (in0 ? 1u : 0u) | (in1 ? 2u : 0u) | (in2 ? 4u : 0u) | (in3 ? 8u : 0u);
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                unsigned nj = __shfl_sync(0xffffffffu, nib, j);
+                const float x0 = __shfl_sync(0xffffffffu, xv[0], j), x1 = __shfl_sync(0xffffffffu, xv[1], j);
+                const float x2 = __shfl_sync(0xffffffffu, xv[2], j), x3 = __shfl_sync(0xffffffffu, xv[3], j);
+                const float xs4[4] = {x0, x1, x2, x3};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!(nj & (1u << k))) continue;
+                    const float xs = xs4[k];
+                    bool surv[PP_NNS_QPT];
+                    bool any = false;
+#pragma unroll
+                    for (int q = 0; q < PP_NNS_QPT; ++q) {
+                        surv[q] = !((xs > hi[q]) || (xs < lo[q]));
+                        any |= surv[q];
+                    }
+                    if (any) {
+                        const uint32_t node = base + c * 128 + j * 4 + k;
+                        const double nxv = __ldg(nx + node), nyv = __ldg(ny + node);
+#pragma unroll
+                        for (int q = 0; q < PP_NNS_QPT; ++q) {
+                            if (surv[q]) {
+                                const double dx = nxv - x[q], dy = nyv - y[q];
+                                const double v = dx * dx + dy * dy;
+                                if (v < best[q]) {
+                                    best[q] = v;
+                                    bi[q] = node;
+                                    const double r = __dsqrt_ru(v);
+                                    hi[q] = __double2float_ru(__dadd_ru(x[q], r));
+                                    lo[q] = __double2float_rd(__dadd_rd(x[q], -r));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + PP_NNS_STAGES < n_tiles) {
+            pp_mbar_expect_tx(&full[s], PP_NNS_TILE * 4);
+            pp_bulk_g2s(tiles + (size_t)s * PP_NNS_TILE, nx32 + (size_t)(t + PP_NNS_STAGES) * PP_NNS_TILE,
+                        PP_NNS_TILE * 4, &full[s]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PP_NNS_QPT; ++q) {
+        if (qi[q] != 0xFFFFFFFFu) {
+            idx_out[qi[q]] = bi[q];
+            if (d2_out) d2_out[qi[q]] = best[q];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -287,10 +521,12 @@ int pp_nn_configure(pp_ctx *ctx) {
                                       (int)PP_NN_SMEM_BYTES));
     PP_CUDA(ctx, cudaFuncSetAttribute(pp_nn_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)PP_NN_SMEM_BYTES));
+    PP_CUDA(ctx, cudaFuncSetAttribute(pp_nn_bucketed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)PP_NNS_SMEM_BYTES));
     return PP_OK;
 }
 
-size_t pp_nn_tile_nodes() { return PP_NN_TILE; }
+size_t pp_nn_tile_nodes() { return PP_NNS_TILE; }  // padding granule: a multiple of both tile sizes
 
 int pp_launch_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *d2, int flags,
                  cudaStream_t stream) {
@@ -330,10 +566,39 @@ int pp_launch_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint
         pp_launch_scope scope(ctx, "nn_scan_f64");
         pp_nn_scan_kernel<false><<<grid, PP_NN_THREADS, PP_NN_SMEM_BYTES, stream>>>(t.x, t.y, t.x32, n_tiles, qx, qy, m,
                                                                                      idx, d2);
-    } else {
-        pp_launch_scope scope(ctx, "nn_scan");
+    } else if (flags & PP_NN_UNSORTED) {
+        pp_launch_scope scope(ctx, "nn_scan_unsorted");
         pp_nn_scan_kernel<true><<<grid, PP_NN_THREADS, PP_NN_SMEM_BYTES, stream>>>(t.x, t.y, t.x32, n_tiles, qx, qy, m,
                                                                                     idx, d2);
+    } else {
+        // bin the queries by x, then the bucketed scan
+        if (m >= 0xFFFFFFF0ull) return pp_fail(ctx, PP_ERR_INVALID, "too many queries for one call");
+        uint32_t nb = (uint32_t)(m / 64);
+        nb = nb < 1 ? 1 : (nb > 16384 ? 16384 : nb);
+        const size_t need = 64 + (size_t)nb * 8 + m * 4;
+        int rc = pp_scratch_reserve(ctx, need);
+        if (rc) return rc;
+        unsigned long long *mm = (unsigned long long *)ctx->scratch;
+        uint32_t *hist = (uint32_t *)((char *)ctx->scratch + 64);
+        uint32_t *cursor = hist + nb;
+        uint32_t *perm = cursor + nb;
+        {
+            pp_launch_scope scope(ctx, "nn_bucket", 4);
+            const unsigned long long init[2] = {~0ull, 0ull};
+            PP_CUDA(ctx, cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, stream));
+            PP_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4, stream));
+            unsigned g1 = (unsigned)((m + 255) / 256);
+            unsigned gr = g1 < (unsigned)ctx->sm_count * 8 ? g1 : (unsigned)ctx->sm_count * 8;
+            pp_nn_qrange_kernel<<<gr, 256, 0, stream>>>(qx, m, mm);
+            pp_nn_bucket_count_kernel<<<g1, 256, 0, stream>>>(qx, m, mm, nb, hist);
+            pp_nn_bucket_scan_kernel<<<1, 1024, 0, stream>>>(hist, nb, cursor);
+            pp_nn_bucket_scatter_kernel<<<g1, 256, 0, stream>>>(qx, m, mm, nb, cursor, perm);
+        }
+        const uint32_t n_tiles_s = (uint32_t)((t.n + PP_NNS_TILE - 1) / PP_NNS_TILE);
+        const unsigned grid_s = (unsigned)((m + PP_NNS_THREADS * PP_NNS_QPT - 1) / (PP_NNS_THREADS * PP_NNS_QPT));
+        pp_launch_scope scope(ctx, "nn_scan");
+        pp_nn_bucketed_kernel<<<grid_s, PP_NNS_THREADS, PP_NNS_SMEM_BYTES, stream>>>(t.x, t.y, t.x32, n_tiles_s, qx, qy,
+                                                                                       perm, m, idx, d2);
     }
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;

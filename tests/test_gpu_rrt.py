@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-NN_DEFAULT, NN_PLAIN, NN_GRID = 0, 1, 2
+NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED = 0, 1, 2, 4
 DEFAULT, NO_CULL, USE_GRID = 0, 1, 2
 
 
@@ -21,8 +21,9 @@ def _bench_world(pp):
     return bounds, rings
 
 
-@pytest.mark.parametrize("n_nodes,m", [(1, 10), (7, 300), (1000, 5000), (1024, 2048), (50_000, 20_000), (3000, 3)])
-@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID])
+@pytest.mark.parametrize("n_nodes,m", [(1, 10), (7, 300), (1000, 5000), (1024, 2048), (4096, 129), (4097, 70_001),
+                                        (50_000, 20_000), (3000, 3)])
+@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED])
 def test_nn_bit_exact(ctx, O, pp, n_nodes, m, flags):
     qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(m, n_nodes, world=1000.0)
     ctx.tree_upload(nx, ny, nyaw)
@@ -32,7 +33,7 @@ def test_nn_bit_exact(ctx, O, pp, n_nodes, m, flags):
     assert np.array_equal(d2, od2)  # same non-fused arithmetic -> same bits
 
 
-@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID])
+@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED])
 def test_nn_ties_lowest_index(ctx, O, flags):
     # lattice nodes duplicated 3x: every query has exact ties, some at equal distance to 4 lattice points
     g = np.arange(0, 20, dtype=np.float64)
@@ -70,7 +71,9 @@ def test_nn_nonfinite(ctx, O):
     qx = np.array([0.9, np.nan, 100.0])
     qy = np.array([0.9, 0.0, 100.0])
     ctx.tree_upload(nx, ny)
-    for flags in (NN_DEFAULT, NN_PLAIN, NN_GRID):
+    for flags in (NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED):
+        idx = ctx.nn(np.tile(qx, 40), np.tile(qy, 40), flags=flags, want_d2=False)  # > 64 queries: scan kernels
+        assert np.array_equal(idx, np.tile(O.nn_brute(nx, ny, qx, qy)[0], 40)), flags
         idx = ctx.nn(qx, qy, flags=flags, want_d2=False)
         assert np.array_equal(idx, O.nn_brute(nx, ny, qx, qy)[0]), flags
 
