@@ -219,9 +219,12 @@ struct pp_points_dubins {
 };
 
 #define PP_POLY_THREADS 128
+#ifndef PP_POLY_MIN_BLOCKS
+#define PP_POLY_MIN_BLOCKS 8  // 64 registers (some spills): measured faster than 80 / 96 / 109 registers on the C5 slice
+#endif
 
 template <bool CULL, bool DUBINS>
-__global__ void __launch_bounds__(PP_POLY_THREADS)
+__global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
     pp_verify_polylines_kernel(pp_world_view w, size_t n_lines, pp_points_csr csr, pp_points_dubins dub,
                                uint8_t *__restrict__ ok) {
     const int lane = threadIdx.x & 31;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(PP_POLY_THREADS)
             } else {
                 nsamp = pl.count;
                 pp_segment_origins(pl, o, &gx_unused);
-                sincos(pl.syaw, &ss, &cs);
+                pp_sincos1(pl.syaw, &ss, &cs);
             }
             np = nsamp + 1;
         } else {

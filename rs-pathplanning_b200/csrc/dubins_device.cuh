@@ -42,6 +42,28 @@ __device__ __forceinline__ double pp_mod2pi_unit(double x) { return (x == PP_TWO
 // src/dubins.rs:22-24 ; Rust % == fmod
 __device__ __forceinline__ double pp_pi_2_pi(double a) { return fmod(a + PP_PI, PP_TWO_PI) - PP_PI; }
 
+// Same value, bit for bit, without the library fmod: fmod's result is exactly representable, so ONE fma
+// reproduces it when the integer quotient is right, and a quotient that is off by one (product rounding next
+// to a multiple of 2pi) is repaired by redoing the fma with the neighbouring integer.
+__device__ __forceinline__ double pp_pi_2_pi_fast(double a) {
+    const double b = a + PP_PI;
+    const double ab = fabs(b);
+    double r = ab;
+    if (ab >= PP_TWO_PI) {
+        if (!(ab < 1e15)) return fmod(b, PP_TWO_PI) - PP_PI;  // huge or infinite
+        double k = floor(ab * PP_INV_TWO_PI);
+        r = fma(-k, PP_TWO_PI, ab);
+        if (r < 0.0) {
+            k -= 1.0;
+            r = fma(-k, PP_TWO_PI, ab);
+        } else if (r >= PP_TWO_PI) {
+            k += 1.0;
+            r = fma(-k, PP_TWO_PI, ab);
+        }
+    }
+    return copysign(r, b) - PP_PI;
+}
+
 struct pp_dubins_sol {
     double t, p, q, cost;
     int word;  // pp_word or PP_WORD_NONE
@@ -350,7 +372,11 @@ __device__ __forceinline__ void pp_interpolate(int mode, double len, double ox, 
         *yaw = oyaw;
     } else {
         double sl, cl;
+#ifdef PP_INTERP_LIBM
         sincos(len, &sl, &cl);
+#else
+        pp_sincos1(len, &sl, &cl);
+#endif
         double ldx = sl * rinv;
         double ldy = (1.0 - cl) * rinv;
         if (mode == PP_MODE_R) ldy = -ldy;
@@ -398,7 +424,7 @@ __device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_
             o[i + 1].ox = x;
             o[i + 1].oy = y;
             o[i + 1].oyaw = yaw;
-            sincos(yaw, &o[i + 1].so, &o[i + 1].co);
+            pp_sincos1(yaw, &o[i + 1].so, &o[i + 1].co);
         } else {
             *gx = x;
         }
@@ -408,6 +434,8 @@ __device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_
 // local-frame sample of output slot k (1 <= k <= n0+n1+n2)
 __device__ __forceinline__ void pp_plan_sample_local(const pp_dubins_plan &pl, const pp_seg_origin o[3], uint32_t k,
                                                      double *x, double *y, double *yaw) {
+    // the run-time `seg` index puts pl / o in local memory (L1-resident); measured faster than a select
+    // tree, which costs ~30 instructions per sample and spills in the verify kernel
     uint32_t j = k - 1;
     int seg = 0;
     if (j >= pl.n[0]) {
@@ -418,8 +446,8 @@ __device__ __forceinline__ void pp_plan_sample_local(const pp_dubins_plan &pl, c
             seg = 2;
         }
     }
-    double d = (pl.len[seg] > 0.0) ? pl.step : -pl.step;
-    double pd = pl.pd0[seg] + (double)j * d;  // reference accumulates; differs by <= j ulp (Q10)
+    const double d = (pl.len[seg] > 0.0) ? pl.step : -pl.step;
+    const double pd = pl.pd0[seg] + (double)j * d;  // reference accumulates; differs by <= j ulp (Q10)
     pp_interpolate(pp_word_mode(pl.word, seg), pd, o[seg].ox, o[seg].oy, o[seg].oyaw, o[seg].so, o[seg].co, pl.rinv, x,
                    y, yaw);
 }
