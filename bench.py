@@ -345,7 +345,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
     ok = torch.empty(m, dtype=torch.uint8, device=dev)
     ref_idx = None
     for name, nnf, cf, kname in [("extend_scan", 0, 0, "nn_scan"), ("extend_scan_plain_f64", 1, 0, "nn_scan_f64"),
-                                 ("extend_scan_unsorted", 4, 0, "nn_scan_unsorted"), ("extend_grid", 2, 2, "nn_grid")]:
+                                 ("extend_scan_unsorted", 4, 4, "nn_scan_unsorted"), ("extend_grid", 2, 2, "nn_grid")]:
         ctx.timing_enable(True)
         fn = lambda: ctx.rrt_extend_dev(m, qx, qy, idx, yaw, ok, nn_flags=nnf, collide_flags=cf)  # noqa: E731
         fn()
@@ -354,7 +354,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
         l0 = ctx.launch_count
         ms, _, _ = time_steps(torch, dist, fn, steps, 0, world)
         nn_ms, nn_n = ctx.timing_get(kname)
-        c_ms, c_n = ctx.timing_get("collide_segments_grid" if cf == 2 else "collide_segments")
+        c_ms, c_n = ctx.timing_get({0: "collide_segments", 2: "collide_segments_grid", 4: "collide_segments_unsorted"}[cf])
         ctx.timing_enable(False)
         if ref_idx is None:
             ref_idx, ref_ok = idx.clone(), ok.clone()

@@ -57,7 +57,8 @@ enum pp_mode { PP_MODE_L = 0, PP_MODE_S = 1, PP_MODE_R = 2 };
 enum pp_collide_flags {
     PP_COLLIDE_DEFAULT = 0,
     PP_COLLIDE_NO_CULL = 1, /* exhaustive segment-pair loop exactly as geo's, no AABB rejection */
-    PP_COLLIDE_USE_GRID = 2 /* broad phase through the uniform obstacle grid instead of the tiled AABB scan */
+    PP_COLLIDE_USE_GRID = 2, /* broad phase through the uniform obstacle grid instead of the tiled AABB scan */
+    PP_COLLIDE_UNSORTED = 4  /* tiled AABB scan with one edge per thread in the caller's order (no binning) */
 };
 
 /* flags for pp_nn */

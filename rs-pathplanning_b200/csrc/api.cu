@@ -24,6 +24,7 @@ int pp_nn_configure(pp_ctx *);
 int pp_dubins_tu_init(pp_ctx *);
 int pp_collide_tu_init(pp_ctx *);
 size_t pp_nn_tile_nodes();
+size_t pp_nn_xy32_floats(size_t cap);
 int pp_launch_nn(pp_ctx *, size_t, const double *, const double *, uint32_t *, double *, int, cudaStream_t);
 int pp_launch_tree_finish(pp_ctx *, size_t, size_t, size_t, cudaStream_t);
 int pp_launch_collide_segments(pp_ctx *, size_t, const double *, const double *, const double *, const double *,
@@ -558,7 +559,7 @@ static int pp_tree_reserve(pp_ctx *ctx, size_t n_total, bool keep) {
     float *x32 = nullptr;
     bool ok = cudaMalloc(&x, cap * 8) == cudaSuccess && cudaMalloc(&y, cap * 8) == cudaSuccess &&
               cudaMalloc(&yaw, cap * 8) == cudaSuccess && cudaMalloc(&parent, cap * 4) == cudaSuccess &&
-              cudaMalloc(&x32, cap * 4) == cudaSuccess;
+              cudaMalloc(&x32, pp_nn_xy32_floats(cap) * 4) == cudaSuccess;
     if (!ok) {
         cudaFree(x);
         cudaFree(y);
@@ -574,7 +575,7 @@ static int pp_tree_reserve(pp_ctx *ctx, size_t n_total, bool keep) {
         PP_CUDA(ctx, cudaMemcpyAsync(y, t.y, t.n * 8, cudaMemcpyDeviceToDevice, s));
         PP_CUDA(ctx, cudaMemcpyAsync(yaw, t.yaw, t.n * 8, cudaMemcpyDeviceToDevice, s));
         PP_CUDA(ctx, cudaMemcpyAsync(parent, t.parent, t.n * 4, cudaMemcpyDeviceToDevice, s));
-        PP_CUDA(ctx, cudaMemcpyAsync(x32, t.x32, t.n * 4, cudaMemcpyDeviceToDevice, s));
+        PP_CUDA(ctx, cudaMemcpyAsync(x32, t.x32, pp_nn_xy32_floats(t.cap) * 4, cudaMemcpyDeviceToDevice, s));  // blocked layout
         PP_CUDA(ctx, cudaStreamSynchronize(s));
     }
     cudaFree(t.x);

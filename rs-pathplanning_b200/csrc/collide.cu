@@ -24,6 +24,8 @@
 #include "pp_common.cuh"
 
 pp_world_view pp_make_world_view(const pp_world_dev &w);  // api.cu
+int pp_build_bucket_perm(pp_ctx *ctx, size_t m, const double *kx, const double *ky, uint32_t **perm_out,
+                         cudaStream_t stream);  // nn.cu
 
 #define PP_AABB_TILE 1024  // ring boxes per shared-memory tile (16 KB)
 
@@ -201,6 +203,134 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// kernel 3a' (default for straight edges): the same tiled scan over ALL ring boxes, but the edges are
+// first binned by their start point (the counting sort of the NN scan, nn.cu), each thread owns 4 edges
+// and the warp keeps the union box of its 128 undecided edges.  Per step the 32 lanes test 32 different
+// ring boxes (one LDS.128 each) against the warp box; a ballot yields the rare candidate rings, whose box
+// is then broadcast by shuffle and tested per edge (fp32), and only overlapping (edge, ring) pairs take
+// the exact f64 predicates.  Exactness is that of the per-edge scan (the warp box only pre-filters).
+// ------------------------------------------------------------------------------------------------
+#define PP_SEGB_EPT 4
+
+__global__ void __launch_bounds__(PP_SEG_THREADS)
+    pp_collide_segments_bucketed_kernel(pp_world_view w, size_t m, const double *__restrict__ ax,
+                                        const double *__restrict__ ay, const double *__restrict__ bx,
+                                        const double *__restrict__ by, const uint32_t *__restrict__ gather_idx,
+                                        const double *__restrict__ node_x, const double *__restrict__ node_y,
+                                        double *__restrict__ yaw_out, const uint32_t *__restrict__ perm,
+                                        uint8_t *__restrict__ ok) {
+    __shared__ __align__(128) float4 tiles[2][PP_AABB_TILE];
+    __shared__ uint64_t full[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t warp_base = ((size_t)blockIdx.x * (PP_SEG_THREADS / 32) + warp) * (32 * PP_SEGB_EPT);
+    uint32_t ei[PP_SEGB_EPT];
+    double x0[PP_SEGB_EPT], y0[PP_SEGB_EPT], x1[PP_SEGB_EPT], y1[PP_SEGB_EPT];
+    float eminx[PP_SEGB_EPT], emaxx[PP_SEGB_EPT], eminy[PP_SEGB_EPT], emaxy[PP_SEGB_EPT];
+    bool good[PP_SEGB_EPT], hit[PP_SEGB_EPT];
+#pragma unroll
+    for (int e = 0; e < PP_SEGB_EPT; ++e) {
+        const size_t pos = warp_base + (size_t)e * 32 + lane;
+        const bool live = pos < m;
+        ei[e] = live ? perm[pos] : 0xFFFFFFFFu;
+        x0[e] = y0[e] = x1[e] = y1[e] = 0.0;
+        if (live) {
+            const uint32_t i = ei[e];
+            x0[e] = ax[i];
+            y0[e] = ay[i];
+            if (gather_idx) {  // extend step: b = tree node nearest to the sample a (src/rrt.rs:406-411)
+                const uint32_t g = gather_idx[i];
+                x1[e] = node_x[g];
+                y1[e] = node_y[g];
+                if (yaw_out) yaw_out[i] = atan2(y1[e] - y0[e], x1[e] - x0[e]);  // compute_yaw, src/rrt.rs:267-271
+            } else {
+                x1[e] = bx[i];
+                y1[e] = by[i];
+            }
+        }
+        // bounds.contains(line): both points strictly inside (src/rrt.rs:125)
+        good[e] = live && pp_bounds_contains(w, x0[e], y0[e]) && pp_bounds_contains(w, x1[e], y1[e]);
+        hit[e] = false;
+        eminx[e] = __double2float_rd(fmin(x0[e], x1[e]));
+        emaxx[e] = __double2float_ru(fmax(x0[e], x1[e]));
+        eminy[e] = __double2float_rd(fmin(y0[e], y1[e]));
+        emaxy[e] = __double2float_ru(fmax(y0[e], y1[e]));
+    }
+    if (tid == 0) {
+        pp_mbar_init(&full[0], 1);
+        pp_mbar_init(&full[1], 1);
+        pp_fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (uint32_t t = 0; t < 2 && t < w.n_aabb_tiles; ++t) {
+            pp_mbar_expect_tx(&full[t], PP_AABB_TILE * 16);
+            pp_bulk_g2s(tiles[t], w.aabb32 + (size_t)t * PP_AABB_TILE, PP_AABB_TILE * 16, &full[t]);
+        }
+    }
+    for (uint32_t t = 0; t < w.n_aabb_tiles; ++t) {
+        const int s = t & 1;
+        pp_mbar_wait(&full[s], (t >> 1) & 1u);
+        // union box of this warp's undecided edges (an edge that left the bounds or already hit is decided)
+        float wminx = CUDART_INF_F, wmaxx = -CUDART_INF_F, wminy = CUDART_INF_F, wmaxy = -CUDART_INF_F;
+#pragma unroll
+        for (int e = 0; e < PP_SEGB_EPT; ++e) {
+            if (good[e] && !hit[e]) {
+                // NaN coordinates never pass pp_bounds_contains, so the boxes here are ordered
+                wminx = fminf(wminx, eminx[e]);
+                wmaxx = fmaxf(wmaxx, emaxx[e]);
+                wminy = fminf(wminy, eminy[e]);
+                wmaxy = fmaxf(wmaxy, emaxy[e]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wminx = fminf(wminx, __shfl_xor_sync(0xffffffffu, wminx, o));
+            wmaxx = fmaxf(wmaxx, __shfl_xor_sync(0xffffffffu, wmaxx, o));
+            wminy = fminf(wminy, __shfl_xor_sync(0xffffffffu, wminy, o));
+            wmaxy = fmaxf(wmaxy, __shfl_xor_sync(0xffffffffu, wmaxy, o));
+        }
+        if (wminx <= wmaxx) {  // some edge still undecided (warp-uniform)
+            const float4 *T = tiles[s];
+#pragma unroll 2
+            for (int c = 0; c < PP_AABB_TILE / 32; ++c) {
+                const float4 bb = T[c * 32 + lane];
+                unsigned mask = __ballot_sync(0xffffffffu, !(wmaxx < bb.x || wminx > bb.z || wmaxy < bb.y || wminy > bb.w));
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float rminx = __shfl_sync(0xffffffffu, bb.x, j), rminy = __shfl_sync(0xffffffffu, bb.y, j);
+                    const float rmaxx = __shfl_sync(0xffffffffu, bb.z, j), rmaxy = __shfl_sync(0xffffffffu, bb.w, j);
+                    const uint32_t ring = t * PP_AABB_TILE + c * 32 + j;
+                    if (ring >= w.n_rings) continue;  // padding boxes are empty and never get here; belt and braces
+#pragma unroll
+                    for (int e = 0; e < PP_SEGB_EPT; ++e) {
+                        if (good[e] && !hit[e] &&
+                            !(emaxx[e] < rminx || eminx[e] > rmaxx || emaxy[e] < rminy || eminy[e] > rmaxy)) {
+                            const pp_ring_meta mt = w.meta[ring];
+                            const double *rx = w.ox + mt.first, *ry = w.oy + mt.first;
+                            if (pp_ring_hits_segment(rx, ry, mt.count, x0[e], y0[e], x1[e], y1[e]) ||
+                                (!pp_outside_padded(mt, x0[e], y0[e]) &&
+                                 pp_point_position(rx, ry, mt.count, x0[e], y0[e]) == 1) ||
+                                (!pp_outside_padded(mt, x1[e], y1[e]) &&
+                                 pp_point_position(rx, ry, mt.count, x1[e], y1[e]) == 1))
+                                hit[e] = true;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + 2 < w.n_aabb_tiles) {
+            pp_mbar_expect_tx(&full[s], PP_AABB_TILE * 16);
+            pp_bulk_g2s(tiles[s], w.aabb32 + (size_t)(t + 2) * PP_AABB_TILE, PP_AABB_TILE * 16, &full[s]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < PP_SEGB_EPT; ++e)
+        if (ei[e] != 0xFFFFFFFFu) ok[ei[e]] = (good[e] && !hit[e]) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel 3b: polylines, one warp per polyline.  Points come either from memory (CSR polylines,
 // pp_verify_polylines) or are generated on the fly from a Dubins plan record (pp_collide_dubins):
 // samples are consumed in registers and never written (config 5 would materialise ~100 GB).
@@ -319,10 +449,18 @@ int pp_launch_collide_segments(pp_ctx *ctx, size_t m, const double *ax, const do
         pp_launch_scope scope(ctx, "collide_segments_grid");
         pp_collide_segments_kernel<2><<<grid, PP_SEG_THREADS, 0, stream>>>(w, m, ax, ay, bx, by, gather_idx, nx, ny,
                                                                            yaw_out, ok);
-    } else {
-        pp_launch_scope scope(ctx, "collide_segments");
+    } else if (flags & PP_COLLIDE_UNSORTED) {
+        pp_launch_scope scope(ctx, "collide_segments_unsorted");
         pp_collide_segments_kernel<0><<<grid, PP_SEG_THREADS, 0, stream>>>(w, m, ax, ay, bx, by, gather_idx, nx, ny,
                                                                            yaw_out, ok);
+    } else {
+        uint32_t *perm = nullptr;
+        int rc = pp_build_bucket_perm(ctx, m, ax, ay, &perm, stream);
+        if (rc) return rc;
+        const unsigned grid_b = (unsigned)((m + PP_SEG_THREADS * PP_SEGB_EPT - 1) / (PP_SEG_THREADS * PP_SEGB_EPT));
+        pp_launch_scope scope(ctx, "collide_segments");
+        pp_collide_segments_bucketed_kernel<<<grid_b, PP_SEG_THREADS, 0, stream>>>(w, m, ax, ay, bx, by, gather_idx, nx,
+                                                                                   ny, yaw_out, perm, ok);
     }
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;

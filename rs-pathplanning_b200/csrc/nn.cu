@@ -23,6 +23,13 @@
 #define PP_NN_THREADS 128
 #define PP_NN_QPT 4
 
+// fp32 copies of the node coordinates live in ONE array, blocked so that a bucketed-scan tile is a single
+// contiguous 16 KB TMA copy: block b = nodes [2048 b, 2048 b + 2048) stored as 2048 x-values then 2048 y-values
+#define PP_XY32_BLOCK 2048
+__host__ __device__ __forceinline__ size_t pp_xy32_index(size_t node) {  // index of fl32(x); fl32(y) is +2048
+    return (node / PP_XY32_BLOCK) * (2 * PP_XY32_BLOCK) + (node % PP_XY32_BLOCK);
+}
+
 struct __align__(128) pp_nn_stage {
     double x[PP_NN_TILE];
     double y[PP_NN_TILE];
@@ -37,7 +44,7 @@ __device__ __forceinline__ void pp_nn_issue_tile(pp_nn_stage *st, uint64_t *bar,
     pp_mbar_expect_tx(bar, PP_NN_STAGE_BYTES);
     pp_bulk_g2s(st->x, nx + base, PP_NN_TILE * 8, bar);
     pp_bulk_g2s(st->y, ny + base, PP_NN_TILE * 8, bar);
-    pp_bulk_g2s(st->x32, nx32 + base, PP_NN_TILE * 4, bar);
+    pp_bulk_g2s(st->x32, nx32 + pp_xy32_index(base), PP_NN_TILE * 4, bar);
 }
 
 template <bool PREFILTER>
@@ -281,21 +288,24 @@ __global__ void __launch_bounds__(128)
 
 
 // ---------------------------------------------------------------------------------------------
-// Bucketed scan (default for many queries).  The queries are binned by x (counting sort: histogram,
-// single-block scan, scatter) so that the 128 queries of a warp lie within a narrow x-band.  The warp
-// then keeps ONE outward-rounded float interval [wlo, whi] = union of its threads' rejection intervals
-// and tests 128 nodes per step: lane l compares fl32(x) of nodes 4l..4l+3 (one LDS.128) with the warp
-// interval, a ballot yields the (rare) candidate nodes, and only those go through the per-thread fp32 test and the
-// exact f64 evaluation.  Every node is still visited for every query (brute force, no index structure on
-// the tree), nodes are met in increasing index order and the comparison is strict, so the result is the
-// same bit-exact argmin with lowest-index tie-break.  Only the 4-byte fl32(x) stream goes through shared
-// memory (16 KB TMA tiles); x and y of a candidate are fetched from L2 (one broadcast load per warp).
+// Bucketed scan (default for many queries).  The queries are binned into the cells of a G x G grid over
+// their bounding box (counting sort: histogram, single-block scan, scatter -> a permutation), so the 128
+// queries of a warp lie in a small box.  The warp keeps ONE outward-rounded float box = union of its
+// threads' rejection boxes [q - r, q + r] (r = sqrt_ru(best)) and tests 128 nodes per step: lane l compares
+// fl32(x), fl32(y) of nodes 4l..4l+3 (two LDS.128) with the warp box, a ballot yields the (rare) candidate
+// nodes, and only those go through the per-thread fp32 test and the exact f64 evaluation.  A node outside a
+// thread's box has |dx| >= r or |dy| >= r, hence d2 >= best: skipping it is exact.  Every node is still
+// visited for every query (brute force, no index structure on the tree), in increasing index order with a
+// strict comparison, so the result is the same bit-exact argmin with lowest-index tie-break.  Only the fp32
+// copies stream through shared memory (16 KB TMA tiles of 2048 nodes); x and y of a candidate are fetched
+// from L2 (one broadcast load per warp).
 // ---------------------------------------------------------------------------------------------
-#define PP_NNS_TILE 4096
+#define PP_NNS_TILE PP_XY32_BLOCK
 #define PP_NNS_STAGES 3
 #define PP_NNS_THREADS 128
 #define PP_NNS_QPT 4
-#define PP_NNS_SMEM_BYTES (PP_NNS_STAGES * PP_NNS_TILE * 4 + PP_NNS_STAGES * 8)
+#define PP_NNS_TILE_BYTES (PP_NNS_TILE * 8)
+#define PP_NNS_SMEM_BYTES (PP_NNS_STAGES * PP_NNS_TILE_BYTES + PP_NNS_STAGES * 8)
 
 __device__ __forceinline__ unsigned long long pp_f64_key(double v) {  // order-preserving u64 key
     unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -306,42 +316,54 @@ __device__ __forceinline__ double pp_key_f64(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-// mm[0] = min key, mm[1] = max key over the non-NaN query x (mm preset to {~0, 0})
+// mm[0..1] = min / max key of the non-NaN query x, mm[2..3] of y (preset to {~0, 0, ~0, 0})
 __global__ void __launch_bounds__(256)
-    pp_nn_qrange_kernel(const double *__restrict__ qx, size_t m, unsigned long long *__restrict__ mm) {
-    unsigned long long lo = ~0ull, hi = 0ull;
+    pp_nn_qrange_kernel(const double *__restrict__ qx, const double *__restrict__ qy, size_t m,
+                        unsigned long long *__restrict__ mm) {
+    unsigned long long lo[2] = {~0ull, ~0ull}, hi[2] = {0ull, 0ull};
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (size_t)gridDim.x * 256) {
-        const double v = qx[i];
-        if (v == v) {
-            const unsigned long long k = pp_f64_key(v);
-            lo = min(lo, k);
-            hi = max(hi, k);
+        const double v[2] = {qx[i], qy[i]};
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+            if (v[a] == v[a]) {
+                const unsigned long long k = pp_f64_key(v[a]);
+                lo[a] = min(lo[a], k);
+                hi[a] = max(hi[a], k);
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_down_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_down_sync(0xffffffffu, hi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&mm[2 * a], lo[a]);
+            atomicMax(&mm[2 * a + 1], hi[a]);
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_down_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_down_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&mm[0], lo);
-        atomicMax(&mm[1], hi);
-    }
 }
 
-__device__ __forceinline__ uint32_t pp_nn_bucket_of(double v, const unsigned long long *mm, uint32_t nb) {
-    const double lo = pp_key_f64(mm[0]), hi = pp_key_f64(mm[1]);
+__device__ __forceinline__ uint32_t pp_nn_axis_cell(double v, unsigned long long klo, unsigned long long khi,
+                                                    uint32_t g) {
+    const double lo = pp_key_f64(klo), hi = pp_key_f64(khi);
     const double span = hi - lo;
     if (!(v == v) || !(span > 0.0)) return 0;
-    const double f = (v - lo) * ((double)nb / span);
+    const double f = (v - lo) * ((double)g / span);
     if (!(f > 0.0)) return 0;
-    return (f >= (double)nb) ? nb - 1 : (uint32_t)f;
+    return (f >= (double)g) ? g - 1 : (uint32_t)f;
+}
+// row-major cell of the g x g grid; consecutive buckets are x-neighbours, so a warp that spans two
+// buckets still covers a compact box
+__device__ __forceinline__ uint32_t pp_nn_bucket_of(double x, double y, const unsigned long long *mm, uint32_t g) {
+    return pp_nn_axis_cell(y, mm[2], mm[3], g) * g + pp_nn_axis_cell(x, mm[0], mm[1], g);
 }
 
 __global__ void __launch_bounds__(256)
-    pp_nn_bucket_count_kernel(const double *__restrict__ qx, size_t m, const unsigned long long *__restrict__ mm,
-                              uint32_t nb, uint32_t *__restrict__ hist) {
+    pp_nn_bucket_count_kernel(const double *__restrict__ qx, const double *__restrict__ qy, size_t m,
+                              const unsigned long long *__restrict__ mm, uint32_t g, uint32_t *__restrict__ hist) {
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < m) atomicAdd(&hist[pp_nn_bucket_of(qx[i], mm, nb)], 1u);
+    if (i < m) atomicAdd(&hist[pp_nn_bucket_of(qx[i], qy[i], mm, g)], 1u);
 }
 
 // single block: exclusive scan of hist[nb] into cursor[nb] (nb <= 16384)
@@ -380,27 +402,28 @@ __global__ void __launch_bounds__(1024) pp_nn_bucket_scan_kernel(const uint32_t 
 }
 
 __global__ void __launch_bounds__(256)
-    pp_nn_bucket_scatter_kernel(const double *__restrict__ qx, size_t m, const unsigned long long *__restrict__ mm,
-                                uint32_t nb, uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm) {
+    pp_nn_bucket_scatter_kernel(const double *__restrict__ qx, const double *__restrict__ qy, size_t m,
+                                const unsigned long long *__restrict__ mm, uint32_t g, uint32_t *__restrict__ cursor,
+                                uint32_t *__restrict__ perm) {
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < m) perm[atomicAdd(&cursor[pp_nn_bucket_of(qx[i], mm, nb)], 1u)] = (uint32_t)i;
+    if (i < m) perm[atomicAdd(&cursor[pp_nn_bucket_of(qx[i], qy[i], mm, g)], 1u)] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(PP_NNS_THREADS)
-    pp_nn_bucketed_kernel(const double *__restrict__ nx, const double *__restrict__ ny, const float *__restrict__ nx32,
+    pp_nn_bucketed_kernel(const double *__restrict__ nx, const double *__restrict__ ny, const float *__restrict__ nxy32,
                           uint32_t n_tiles, const double *__restrict__ qx, const double *__restrict__ qy,
                           const uint32_t *__restrict__ perm, size_t m, uint32_t *__restrict__ idx_out,
                           double *__restrict__ d2_out) {
     extern __shared__ __align__(128) unsigned char pp_nns_smem[];
     float *tiles = reinterpret_cast<float *>(pp_nns_smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(pp_nns_smem + PP_NNS_STAGES * PP_NNS_TILE * 4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(pp_nns_smem + PP_NNS_STAGES * PP_NNS_TILE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // the q-th query of this thread: consecutive positions of the x-sorted order within the warp
+    // the q-th query of this thread: consecutive positions of the bucket order within the warp
     const size_t warp_base = ((size_t)blockIdx.x * (PP_NNS_THREADS / 32) + warp) * (32 * PP_NNS_QPT);
     uint32_t qi[PP_NNS_QPT];
     double x[PP_NNS_QPT], y[PP_NNS_QPT], best[PP_NNS_QPT];
-    float lo[PP_NNS_QPT], hi[PP_NNS_QPT];
+    float xlo[PP_NNS_QPT], xhi[PP_NNS_QPT], ylo[PP_NNS_QPT], yhi[PP_NNS_QPT];
     uint32_t bi[PP_NNS_QPT];
 #pragma unroll
     for (int q = 0; q < PP_NNS_QPT; ++q) {
@@ -411,9 +434,9 @@ __global__ void __launch_bounds__(PP_NNS_THREADS)
         y[q] = live ? qy[qi[q]] : 0.0;
         best[q] = CUDART_INF;
         bi[q] = 0xFFFFFFFFu;
-        // dead slots get an empty interval so that they never widen the warp's
-        lo[q] = live ? -CUDART_INF_F : CUDART_INF_F;
-        hi[q] = live ? CUDART_INF_F : -CUDART_INF_F;
+        // dead slots get an empty box so that they never widen the warp's
+        xlo[q] = ylo[q] = live ? -CUDART_INF_F : CUDART_INF_F;
+        xhi[q] = yhi[q] = live ? CUDART_INF_F : -CUDART_INF_F;
     }
 
     if (tid == 0) {
@@ -423,57 +446,64 @@ __global__ void __launch_bounds__(PP_NNS_THREADS)
     __syncthreads();
     if (tid == 0) {
         for (uint32_t t = 0; t < PP_NNS_STAGES && t < n_tiles; ++t) {
-            pp_mbar_expect_tx(&full[t], PP_NNS_TILE * 4);
-            pp_bulk_g2s(tiles + (size_t)t * PP_NNS_TILE, nx32 + (size_t)t * PP_NNS_TILE, PP_NNS_TILE * 4, &full[t]);
+            pp_mbar_expect_tx(&full[t], PP_NNS_TILE_BYTES);
+            pp_bulk_g2s(tiles + (size_t)t * (2 * PP_NNS_TILE), nxy32 + (size_t)t * (2 * PP_NNS_TILE), PP_NNS_TILE_BYTES,
+                        &full[t]);
         }
     }
 
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const int s = t % PP_NNS_STAGES;
         pp_mbar_wait(&full[s], (t / PP_NNS_STAGES) & 1u);
-        const uint32_t tile_addr = pp_smem_u32(tiles + (size_t)s * PP_NNS_TILE) + (uint32_t)lane * 16u;
+        const uint32_t tile_addr = pp_smem_u32(tiles + (size_t)s * (2 * PP_NNS_TILE)) + (uint32_t)lane * 16u;
         const uint32_t base = t * PP_NNS_TILE;
-        float wlo = CUDART_INF_F, whi = -CUDART_INF_F;
-        // 128 nodes per step: lane l holds nodes 4l .. 4l+3 of the chunk (one LDS.128), so the candidate
-        // order (lane, then k) is the node index order
+        float wxlo = CUDART_INF_F, wxhi = -CUDART_INF_F, wylo = CUDART_INF_F, wyhi = -CUDART_INF_F;
+        // 128 nodes per step: lane l holds nodes 4l .. 4l+3 of the chunk, so the candidate order (lane, then k)
+        // is the node index order
 #pragma unroll 2
         for (int c = 0; c < PP_NNS_TILE / 128; ++c) {
-            if ((c & 3) == 0) {  // refresh the warp interval every 512 nodes (a stale one is only wider)
-                wlo = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
-                whi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+            if ((c & 3) == 0) {  // refresh the warp box every 512 nodes (a stale one is only larger)
+                wxlo = fminf(fminf(xlo[0], xlo[1]), fminf(xlo[2], xlo[3]));
+                wxhi = fmaxf(fmaxf(xhi[0], xhi[1]), fmaxf(xhi[2], xhi[3]));
+                wylo = fminf(fminf(ylo[0], ylo[1]), fminf(ylo[2], ylo[3]));
+                wyhi = fmaxf(fmaxf(yhi[0], yhi[1]), fmaxf(yhi[2], yhi[3]));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    wlo = fminf(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
-                    whi = fmaxf(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+                    wxlo = fminf(wxlo, __shfl_xor_sync(0xffffffffu, wxlo, o));
+                    wxhi = fmaxf(wxhi, __shfl_xor_sync(0xffffffffu, wxhi, o));
+                    wylo = fminf(wylo, __shfl_xor_sync(0xffffffffu, wylo, o));
+                    wyhi = fmaxf(wyhi, __shfl_xor_sync(0xffffffffu, wyhi, o));
                 }
             }
-            float4 xq;
+            float4 xq, yq;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(xq.x), "=f"(xq.y), "=f"(xq.z), "=f"(xq.w)
                          : "r"(tile_addr + (uint32_t)c * 512u));
-            const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
-            // common case: no lane holds a candidate -> eight compares, one vote, one branch
-            const bool in0 = !((xv[0] > whi) || (xv[0] < wlo)), in1 = !((xv[1] > whi) || (xv[1] < wlo));
-            const bool in2 = !((xv[2] > whi) || (xv[2] < wlo)), in3 = !((xv[3] > whi) || (xv[3] < wlo));
-            unsigned mask = __ballot_sync(0xffffffffu, in0 || in1 || in2 || in3);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(yq.x), "=f"(yq.y), "=f"(yq.z), "=f"(yq.w)
+                         : "r"(tile_addr + (uint32_t)(PP_NNS_TILE * 4) + (uint32_t)c * 512u));
+            const float xv[4] = {xq.x, xq.y, xq.z, xq.w}, yv[4] = {yq.x, yq.y, yq.z, yq.w};
+            // common case: no lane holds a candidate -> sixteen compares, one vote, one branch
+            bool in[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                in[k] = !((xv[k] > wxhi) || (xv[k] < wxlo)) && !((yv[k] > wyhi) || (yv[k] < wylo));
+            unsigned mask = __ballot_sync(0xffffffffu, in[0] || in[1] || in[2] || in[3]);
             if (mask == 0u) continue;
-            const unsigned nib = (in0 ? 1u : 0u) | (in1 ? 2u : 0u) | (in2 ? 4u : 0u) | (in3 ? 8u : 0u);
+            const unsigned nib = (in[0] ? 1u : 0u) | (in[1] ? 2u : 0u) | (in[2] ? 4u : 0u) | (in[3] ? 8u : 0u);
             while (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                unsigned nj = __shfl_sync(0xffffffffu, nib, j);
-                const float x0 = __shfl_sync(0xffffffffu, xv[0], j), x1 = __shfl_sync(0xffffffffu, xv[1], j);
-                const float x2 = __shfl_sync(0xffffffffu, xv[2], j), x3 = __shfl_sync(0xffffffffu, xv[3], j);
-                const float xs4[4] = {x0, x1, x2, x3};
+                const unsigned nj = __shfl_sync(0xffffffffu, nib, j);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (!(nj & (1u << k))) continue;
-                    const float xs = xs4[k];
+                    if (!(nj & (1u << k))) continue;  // warp-uniform
+                    const float xs = __shfl_sync(0xffffffffu, xv[k], j), ys = __shfl_sync(0xffffffffu, yv[k], j);
                     bool surv[PP_NNS_QPT];
                     bool any = false;
 #pragma unroll
                     for (int q = 0; q < PP_NNS_QPT; ++q) {
-                        surv[q] = !((xs > hi[q]) || (xs < lo[q]));
+                        surv[q] = !((xs > xhi[q]) || (xs < xlo[q])) && !((ys > yhi[q]) || (ys < ylo[q]));
                         any |= surv[q];
                     }
                     if (any) {
@@ -487,9 +517,12 @@ __global__ void __launch_bounds__(PP_NNS_THREADS)
                                 if (v < best[q]) {
                                     best[q] = v;
                                     bi[q] = node;
+                                    // |nx - qx| >= r or |ny - qy| >= r  =>  d2 >= best
                                     const double r = __dsqrt_ru(v);
-                                    hi[q] = __double2float_ru(__dadd_ru(x[q], r));
-                                    lo[q] = __double2float_rd(__dadd_rd(x[q], -r));
+                                    xhi[q] = __double2float_ru(__dadd_ru(x[q], r));
+                                    xlo[q] = __double2float_rd(__dadd_rd(x[q], -r));
+                                    yhi[q] = __double2float_ru(__dadd_ru(y[q], r));
+                                    ylo[q] = __double2float_rd(__dadd_rd(y[q], -r));
                                 }
                             }
                         }
@@ -499,9 +532,9 @@ __global__ void __launch_bounds__(PP_NNS_THREADS)
         }
         __syncthreads();
         if (tid == 0 && t + PP_NNS_STAGES < n_tiles) {
-            pp_mbar_expect_tx(&full[s], PP_NNS_TILE * 4);
-            pp_bulk_g2s(tiles + (size_t)s * PP_NNS_TILE, nx32 + (size_t)(t + PP_NNS_STAGES) * PP_NNS_TILE,
-                        PP_NNS_TILE * 4, &full[s]);
+            pp_mbar_expect_tx(&full[s], PP_NNS_TILE_BYTES);
+            pp_bulk_g2s(tiles + (size_t)s * (2 * PP_NNS_TILE), nxy32 + (size_t)(t + PP_NNS_STAGES) * (2 * PP_NNS_TILE),
+                        PP_NNS_TILE_BYTES, &full[s]);
         }
     }
 #pragma unroll
@@ -526,7 +559,39 @@ int pp_nn_configure(pp_ctx *ctx) {
     return PP_OK;
 }
 
-size_t pp_nn_tile_nodes() { return PP_NNS_TILE; }  // padding granule: a multiple of both tile sizes
+size_t pp_nn_tile_nodes() { return 4096; }  // padding granule: a multiple of every tile size used here
+size_t pp_nn_xy32_floats(size_t cap) { return 2 * cap; }  // cap is a multiple of the granule
+
+// Counting sort of m points into the cells of a g x g grid over their bounding box (~64 points per cell):
+// *perm_out (in the ctx scratch, valid until the next call that uses the scratch) lists the point indices
+// cell by cell.  Shared by the bucketed NN scan and the bucketed straight-edge verify (collide.cu).
+int pp_build_bucket_perm(pp_ctx *ctx, size_t m, const double *kx, const double *ky, uint32_t **perm_out,
+                         cudaStream_t stream) {
+    if (m >= 0xFFFFFFF0ull) return pp_fail(ctx, PP_ERR_INVALID, "too many items for one call");
+    uint32_t g = (uint32_t)sqrt((double)m / 64.0);
+    g = g < 1 ? 1 : (g > 128 ? 128 : g);
+    const uint32_t nb = g * g;
+    const size_t need = 64 + (size_t)nb * 8 + m * 4;
+    int rc = pp_scratch_reserve(ctx, need);
+    if (rc) return rc;
+    unsigned long long *mm = (unsigned long long *)ctx->scratch;
+    uint32_t *hist = (uint32_t *)((char *)ctx->scratch + 64);
+    uint32_t *cursor = hist + nb;
+    uint32_t *perm = cursor + nb;
+    pp_launch_scope scope(ctx, "bucket_sort", 4);
+    const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
+    PP_CUDA(ctx, cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, stream));
+    PP_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4, stream));
+    const unsigned g1 = (unsigned)((m + 255) / 256);
+    const unsigned gr = g1 < (unsigned)ctx->sm_count * 8 ? g1 : (unsigned)ctx->sm_count * 8;
+    pp_nn_qrange_kernel<<<gr, 256, 0, stream>>>(kx, ky, m, mm);
+    pp_nn_bucket_count_kernel<<<g1, 256, 0, stream>>>(kx, ky, m, mm, g, hist);
+    pp_nn_bucket_scan_kernel<<<1, 1024, 0, stream>>>(hist, nb, cursor);
+    pp_nn_bucket_scatter_kernel<<<g1, 256, 0, stream>>>(kx, ky, m, mm, g, cursor, perm);
+    PP_CUDA(ctx, cudaGetLastError());
+    *perm_out = perm;
+    return PP_OK;
+}
 
 int pp_launch_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *d2, int flags,
                  cudaStream_t stream) {
@@ -571,29 +636,10 @@ int pp_launch_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint
         pp_nn_scan_kernel<true><<<grid, PP_NN_THREADS, PP_NN_SMEM_BYTES, stream>>>(t.x, t.y, t.x32, n_tiles, qx, qy, m,
                                                                                     idx, d2);
     } else {
-        // bin the queries by x, then the bucketed scan
-        if (m >= 0xFFFFFFF0ull) return pp_fail(ctx, PP_ERR_INVALID, "too many queries for one call");
-        uint32_t nb = (uint32_t)(m / 64);
-        nb = nb < 1 ? 1 : (nb > 16384 ? 16384 : nb);
-        const size_t need = 64 + (size_t)nb * 8 + m * 4;
-        int rc = pp_scratch_reserve(ctx, need);
+        // bin the queries into grid cells, then the bucketed scan
+        uint32_t *perm = nullptr;
+        int rc = pp_build_bucket_perm(ctx, m, qx, qy, &perm, stream);
         if (rc) return rc;
-        unsigned long long *mm = (unsigned long long *)ctx->scratch;
-        uint32_t *hist = (uint32_t *)((char *)ctx->scratch + 64);
-        uint32_t *cursor = hist + nb;
-        uint32_t *perm = cursor + nb;
-        {
-            pp_launch_scope scope(ctx, "nn_bucket", 4);
-            const unsigned long long init[2] = {~0ull, 0ull};
-            PP_CUDA(ctx, cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, stream));
-            PP_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4, stream));
-            unsigned g1 = (unsigned)((m + 255) / 256);
-            unsigned gr = g1 < (unsigned)ctx->sm_count * 8 ? g1 : (unsigned)ctx->sm_count * 8;
-            pp_nn_qrange_kernel<<<gr, 256, 0, stream>>>(qx, m, mm);
-            pp_nn_bucket_count_kernel<<<g1, 256, 0, stream>>>(qx, m, mm, nb, hist);
-            pp_nn_bucket_scan_kernel<<<1, 1024, 0, stream>>>(hist, nb, cursor);
-            pp_nn_bucket_scatter_kernel<<<g1, 256, 0, stream>>>(qx, m, mm, nb, cursor, perm);
-        }
         const uint32_t n_tiles_s = (uint32_t)((t.n + PP_NNS_TILE - 1) / PP_NNS_TILE);
         const unsigned grid_s = (unsigned)((m + PP_NNS_THREADS * PP_NNS_QPT - 1) / (PP_NNS_THREADS * PP_NNS_QPT));
         pp_launch_scope scope(ctx, "nn_scan");
@@ -604,17 +650,24 @@ int pp_launch_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint
     return PP_OK;
 }
 
-// fl32 copy of x (+inf sentinel padding is written by the uploader)
-__global__ void pp_tree_x32_kernel(const double *__restrict__ x, float *__restrict__ x32, size_t first, size_t n) {
+// fl32 copies of x and y in the blocked layout (+inf sentinel padding up to the granule)
+__global__ void pp_tree_x32_kernel(const double *__restrict__ x, const double *__restrict__ y, float *__restrict__ xy32,
+                                   size_t first, size_t n) {
     size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x32[i] = __double2float_rn(x[i]);
+    if (i < n) {
+        const size_t k = pp_xy32_index(i);
+        xy32[k] = __double2float_rn(x[i]);
+        xy32[k + PP_XY32_BLOCK] = __double2float_rn(y[i]);
+    }
 }
-__global__ void pp_tree_pad_kernel(double *x, double *y, float *x32, size_t first, size_t end) {
+__global__ void pp_tree_pad_kernel(double *x, double *y, float *xy32, size_t first, size_t end) {
     size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < end) {
         x[i] = CUDART_INF;
         y[i] = CUDART_INF;
-        x32[i] = CUDART_INF_F;
+        const size_t k = pp_xy32_index(i);
+        xy32[k] = CUDART_INF_F;
+        xy32[k + PP_XY32_BLOCK] = CUDART_INF_F;
     }
 }
 
@@ -622,7 +675,7 @@ int pp_launch_tree_finish(pp_ctx *ctx, size_t first, size_t n, size_t padded_end
     pp_tree_dev &t = ctx->tree;
     pp_launch_scope scope(ctx, "tree_finish", 2);
     if (n > first)
-        pp_tree_x32_kernel<<<(unsigned)((n - first + 255) / 256), 256, 0, stream>>>(t.x, t.x32, first, n);
+        pp_tree_x32_kernel<<<(unsigned)((n - first + 255) / 256), 256, 0, stream>>>(t.x, t.y, t.x32, first, n);
     if (padded_end > n)
         pp_tree_pad_kernel<<<(unsigned)((padded_end - n + 255) / 256), 256, 0, stream>>>(t.x, t.y, t.x32, n, padded_end);
     PP_CUDA(ctx, cudaGetLastError());

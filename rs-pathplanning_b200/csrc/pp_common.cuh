@@ -21,7 +21,7 @@ struct pp_tree_dev {
     size_t n = 0, cap = 0;
     double *x = nullptr, *y = nullptr, *yaw = nullptr;
     int32_t *parent = nullptr;
-    float *x32 = nullptr;  // fl32(x), for the exact fp32 pre-rejection of the NN scan
+    float *x32 = nullptr;  // fl32(x), fl32(y) in 2048-node blocks (nn.cu: pp_xy32_index) for the exact fp32 pre-rejection
     // uniform grid over the nodes (PP_NN_GRID), rebuilt lazily when `grid_n != n`
     size_t grid_n = (size_t)-1;
     int gx = 0, gy = 0;

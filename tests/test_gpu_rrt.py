@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED = 0, 1, 2, 4
-DEFAULT, NO_CULL, USE_GRID = 0, 1, 2
+DEFAULT, NO_CULL, USE_GRID, UNSORTED = 0, 1, 2, 4
 
 
 def _bench_world(pp):
@@ -78,7 +78,7 @@ def test_nn_nonfinite(ctx, O):
         assert np.array_equal(idx, O.nn_brute(nx, ny, qx, qy)[0]), flags
 
 
-@pytest.mark.parametrize("flags", [DEFAULT, NO_CULL, USE_GRID])
+@pytest.mark.parametrize("flags", [DEFAULT, NO_CULL, USE_GRID, UNSORTED])
 def test_collide_segments_random_world(ctx, O, pp, flags):
     bounds, rings = pp.synth.circle_world(300, world=100.0, rmin=1.0, rmax=3.0)
     ctx.obstacles_upload(bounds, rings)
@@ -104,7 +104,7 @@ def test_collide_segments_bench_world_and_boundary_cases(ctx, O, pp):
     ay = np.array([-5.0, 0.0, 0.0, ry[0], ry[2], 6.0, 6.0, -5.0, 14.0, 3.9, 15.0, 0.0, 6.0])
     bx = np.array([-4.0, -5.0, 14.0, rx[0], rx[3], 3.1, 12.0, -5.0, 14.5, 5.0, 0.0, 0.0, 3.0 + 1e-13])
     by = np.array([-4.0, 0.0, 0.0, ry[0], ry[3], 6.1, 6.0, -5.0, 14.5, 4.1, 14.0, 0.0, 6.0])
-    for flags in (DEFAULT, NO_CULL, USE_GRID):
+    for flags in (DEFAULT, NO_CULL, USE_GRID, UNSORTED):
         ok = ctx.collide_segments(ax, ay, bx, by, flags=flags)
         assert np.array_equal(ok, W.verify_segments(ax, ay, bx, by)), flags
     # degenerate segments (a == b) and points exactly on the bounds ring are not contained
@@ -129,7 +129,7 @@ def test_collide_transit_fixture(ctx, O):
     ln = rng.choice([0.1, 3.0, 30.0], m)
     bx, by = ax + ln * np.cos(th), ay + ln * np.sin(th)
     want = W.verify_segments(ax, ay, bx, by)
-    for flags in (DEFAULT, USE_GRID):
+    for flags in (DEFAULT, USE_GRID, UNSORTED):
         assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=flags), want), flags
     assert 0 < want.sum() < m
     # start -> goal as one straight line, and as the reference's start/goal poses
