@@ -424,17 +424,40 @@ class RRT {  // src/rrt.rs:325-619
         return std::nullopt;
     }
     std::optional<NodePtr> optimize(const NodePtr &node, size_t i) const {  // src/rrt.rs:463-487
+        // Same candidates, same (root-first) order and same verdicts as the reference's loop, but all shortcut
+        // candidates of a level are verified in ONE fused launch: verify(line_to_origin(new)) =
+        // verify(edge new -> to_node) AND verify(chain of to_node), the latter a suffix-AND over the chain's edges.
         if (i >= RECURSION_LIMIT) return std::nullopt;
-        std::vector<NodePtr> nodes_vec;
+        std::vector<NodePtr> chain;  // node, parent, ..., root
         NodeIter it(node);
-        while (NodePtr n = it.next()) nodes_vec.push_back(n);
-        for (auto rit = nodes_vec.rbegin(); rit != nodes_vec.rend(); ++rit) {
-            const NodePtr &to_node = *rit;
-            NodePtr new_node = std::make_shared<Node>(node->get_coord(), to_node);
-            if (verify_node(new_node)) {
-                auto deeper = optimize(to_node, i + 1);
+        while (NodePtr n = it.next()) chain.push_back(n);
+        const size_t n = chain.size();
+        std::vector<NodePtr> cands(n);
+        detail_rrt::Edges e;
+        auto push = [&e](const Node &a, const Node &b) {
+            e.sx.push_back(a.get_point().x);
+            e.sy.push_back(a.get_point().y);
+            e.syaw.push_back(a.get_yaw());
+            e.ex.push_back(b.get_point().x);
+            e.ey.push_back(b.get_point().y);
+            e.eyaw.push_back(b.get_yaw());
+        };
+        for (size_t k = 0; k < n; ++k) {
+            cands[k] = std::make_shared<Node>(node->get_coord(), chain[k]);
+            push(*cands[k], *chain[k]);
+        }
+        for (size_t k = 0; k + 1 < n; ++k) push(*chain[k], *chain[k + 1]);
+        std::vector<uint8_t> ok(e.sx.size());
+        detail::check(pp_collide_dubins(detail::ctx(), ok.size(), e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
+                                        e.ey.data(), e.eyaw.data(), space_->get_steer(), step_size_, ok.data(), 0),
+                      "collide_dubins");
+        std::vector<uint8_t> chain_ok(n, 1);
+        for (size_t k = n - 1; k-- > 0;) chain_ok[k] = (uint8_t)(chain_ok[k + 1] && ok[n + k]);
+        for (size_t k = n; k-- > 0;) {  // .rev(): root first
+            if (ok[k] && chain_ok[k]) {
+                auto deeper = optimize(chain[k], i + 1);
                 if (deeper) return std::make_shared<Node>(node->get_coord(), *deeper);
-                return new_node;
+                return cands[k];
             }
         }
         return std::nullopt;

@@ -178,6 +178,7 @@ class RRT:  # src/rrt.rs:325-619
         self.ctx = space.ctx
         root = Node.new_root(start, start_yaw)
         self.nodes: List[Node] = [root]  # index i <-> device tree slot i (replaces the RTree, :345-346)
+        self._slot = {id(root): 0}
         self.ctx.tree_upload([root.point[0]], [root.point[1]], [root.yaw], [-1])
 
     # -- src/rrt.rs:378-391
@@ -201,7 +202,8 @@ class RRT:  # src/rrt.rs:325-619
 
     def _insert(self, node: Node):  # src/rrt.rs:586-589
         self.nodes.append(node)
-        par = self.nodes.index(node.parent) if node.parent is not None else -1
+        self._slot[id(node)] = len(self.nodes) - 1
+        par = self._slot[id(node.parent)] if node.parent is not None else -1
         self.ctx.tree_append([node.point[0]], [node.point[1]], [node.yaw], [par])
 
     # -- src/rrt.rs:428-438
@@ -210,17 +212,38 @@ class RRT:  # src/rrt.rs:325-619
         line = self.finalize(goal_node)
         return line if self.space.verify(line) else None
 
-    # -- src/rrt.rs:463-487
+    # -- src/rrt.rs:463-487.  Same candidates in the same (root-first) order and the same verdicts as the
+    # reference's loop, but ALL shortcut candidates of a level are verified in ONE fused launch:
+    # verify(line_to_origin(new_node)) = verify(edge new_node -> to_node) AND verify(chain of to_node), and the
+    # chain verdicts are prefix-ANDs over the ancestors' own edges, so 2*depth edges replace depth^2.
     def optimize(self, node: Node, i: int) -> Optional[Node]:
         if i >= RECURSION_LIMIT:
             return None
-        nodes_vec = list(NodeIter(node))
-        for to_node in reversed(nodes_vec):
-            new_node = Node(node.get_coord(), to_node)
-            if self.verify_node(new_node):
-                deeper = self.optimize(to_node, i + 1)
-                return Node(node.get_coord(), deeper) if deeper is not None else new_node
+        nodes_vec = list(NodeIter(node))  # node, parent, ..., root
+        cands = [Node(node.get_coord(), to_node) for to_node in nodes_vec]
+        valid = self._verify_shortcuts(nodes_vec, cands)
+        for k in range(len(nodes_vec) - 1, -1, -1):  # .rev(): root first
+            if valid[k]:
+                deeper = self.optimize(nodes_vec[k], i + 1)
+                return Node(node.get_coord(), deeper) if deeper is not None else cands[k]
         return None
+
+    def _verify_shortcuts(self, chain: List[Node], cands: List[Node]) -> np.ndarray:
+        """valid[k] = verify_node(cands[k]) where cands[k].parent is chain[k] (chain = node ... root)"""
+        n = len(chain)
+        sx = [c.point[0] for c in cands] + [a.point[0] for a in chain[:-1]]
+        sy = [c.point[1] for c in cands] + [a.point[1] for a in chain[:-1]]
+        syaw = [c.yaw for c in cands] + [a.yaw for a in chain[:-1]]
+        ex = [a.point[0] for a in chain] + [a.parent.point[0] for a in chain[:-1]]
+        ey = [a.point[1] for a in chain] + [a.parent.point[1] for a in chain[:-1]]
+        eyaw = [a.yaw for a in chain] + [a.parent.yaw for a in chain[:-1]]
+        ok = self.ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, self.space.get_steer(), self.step_size).astype(bool)
+        first, own = ok[:n], ok[n:]  # own[j]: edge chain[j] -> chain[j+1]
+        # chain_ok[k] = AND of own[k:]; the root's own point is the last point of every edge that ends at the root
+        chain_ok = np.ones(n, bool)
+        if n > 1:
+            chain_ok[: n - 1] = np.logical_and.accumulate(own[::-1])[::-1]
+        return first & chain_ok
 
     # -- src/rrt.rs:489-501
     def optimize_from_goal(self, goal_node: Node) -> Node:
@@ -244,6 +267,49 @@ class RRT:  # src/rrt.rs:325-619
             self._insert(rnd)
             return self.check_finish(rnd)
         return None
+
+    # -- the reference runs max_iter independent plan_one iterations on 4 racy workers that all see
+    # a slightly stale tree (src/rrt.rs:600-609).  Here a ROUND processes `batch` samples against one tree
+    # snapshot: one NN launch, one fused Dubins verify launch for the new edges (the parents' chains are already
+    # verified, that is the tree invariant), one batched append, one fused launch for the goal connections, and
+    # the shortcutting only for nodes that can reach the goal.  min_by euclidean_length stays on the host (:611-617).
+    def plan_rounds(self, batch: int = 256, max_iter: Optional[int] = None) -> Optional[Ring]:
+        budget = self.max_iter if max_iter is None else int(max_iter)
+        best, best_len = None, math.inf
+        steer = self.space.get_steer()
+        while budget > 0:
+            b = min(batch, budget)
+            budget -= b
+            pts = [self.space.rand_point() for _ in range(b)]
+            px, py = np.array([p[0] for p in pts]), np.array([p[1] for p in pts])
+            idx = self.ctx.nn(px, py, want_d2=False)
+            parents = [self.nodes[int(i)] for i in idx]
+            cand = [Node(p, par) for p, par in zip(pts, parents)]
+            ok = self.ctx.collide_dubins(px, py, [c.yaw for c in cand], [p.point[0] for p in parents],
+                                         [p.point[1] for p in parents], [p.yaw for p in parents], steer,
+                                         self.step_size).astype(bool)
+            fresh = [c for c, good in zip(cand, ok) if good]
+            if not fresh:
+                continue
+            self.ctx.tree_append([c.point[0] for c in fresh], [c.point[1] for c in fresh], [c.yaw for c in fresh],
+                                 [self._slot[id(c.parent)] for c in fresh])
+            for c in fresh:
+                self._slot[id(c)] = len(self.nodes)
+                self.nodes.append(c)
+            # goal connection goal -> node for every fresh node in one launch; finalize only the reachable ones
+            g_ok = self.ctx.collide_dubins([self.goal[0]] * len(fresh), [self.goal[1]] * len(fresh),
+                                           [self.goal_yaw] * len(fresh), [c.point[0] for c in fresh],
+                                           [c.point[1] for c in fresh], [c.yaw for c in fresh], steer,
+                                           self.step_size).astype(bool)
+            for c, reach in zip(fresh, g_ok):
+                if not reach:
+                    continue
+                line = self.check_finish(c)
+                if line is not None:
+                    length = euclidean_length(line)
+                    if length < best_len:
+                        best, best_len = line, length
+        return best
 
     # -- src/rrt.rs:599-619 (the reference's 4 racy workers become sequential iterations)
     def plan(self) -> Optional[Ring]:
