@@ -19,6 +19,8 @@ int pp_launch_mod2pi(pp_ctx *, size_t, const double *, double *, int, cudaStream
 int pp_launch_dubins_plan(pp_ctx *, size_t, const double *, const double *, const double *, const double *,
                           const double *, const double *, double, double, int, uint32_t *, void *, cudaStream_t);
 int pp_launch_dubins_fill(pp_ctx *, size_t, const void *, const uint64_t *, double *, cudaStream_t);
+int pp_launch_dubins_path(pp_ctx *, double, double, double, double, double, double, double, double, int, uint32_t, void *,
+                          double *, cudaStream_t);
 int pp_launch_exclusive_scan(pp_ctx *, size_t, const uint32_t *, uint64_t *, uint64_t *, uint64_t *, cudaStream_t);
 int pp_nn_configure(pp_ctx *);
 int pp_dubins_tu_init(pp_ctx *);
@@ -301,6 +303,8 @@ int pp_scratch_reserve(pp_ctx *ctx, size_t bytes) {
     return PP_OK;
 }
 
+static int pp_pinned_reserve(pp_ctx *ctx, size_t bytes);
+
 // stream-ordered temporary device buffer
 struct pp_tmp {
     void *p = nullptr;
@@ -489,6 +493,27 @@ int pp_exclusive_scan_u32_dev(pp_ctx *ctx, size_t n, const uint32_t *counts, uin
     return pp_launch_exclusive_scan(ctx, n, counts, offsets, total, (uint64_t *)ctx->scratch, ctx->stream);
 }
 
+// pinned, device-mapped staging buffer of the scalar calls (grown on demand)
+static int pp_pinned_reserve(pp_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return PP_OK;
+    PP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    if (cudaHostAlloc(&ctx->pinned, want, cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return pp_fail(ctx, PP_ERR_NOMEM, "pinned staging allocation failed");
+    }
+    ctx->pinned_bytes = want;
+    return PP_OK;
+}
+
+struct pp_path_header_host {  // mirrors pp_path_header in dubins.cu
+    uint32_t count, word;
+    double cost, len[3];
+};
+
 int pp_dubins_path(pp_ctx *ctx, double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
                    double step, int from_origin, double *px, double *py, double *pyaw, size_t cap, size_t *n_out,
                    int *word, double *cost) {
@@ -497,46 +522,32 @@ int pp_dubins_path(pp_ctx *ctx, double sx, double sy, double syaw, double ex, do
     pp_guard g(ctx);
     cudaStream_t s = ctx->stream;
     *n_out = 0;
-    PP_TMP(ctx, dbuf, s, 48 + 16 + PP_DUBINS_PLAN_BYTES + 64);
-    double h_in[6] = {sx, sy, syaw, ex, ey, eyaw};
-    double *d = dbuf.as<double>();
-    uint32_t *dcnt = (uint32_t *)(d + 6);
-    uint64_t *doff = (uint64_t *)(d + 7);
-    char *dplan = (char *)(d + 8);
-    PP_CUDA(ctx, cudaMemcpyAsync(d, h_in, 48, cudaMemcpyHostToDevice, s));
-    PP_CUDA(ctx, cudaMemsetAsync(doff, 0, 8, s));
-    int rc = pp_launch_dubins_plan(ctx, 1, d, d + 1, d + 2, d + 3, d + 4, d + 5, radius, step, from_origin, dcnt, dplan,
-                                   s);
+    // one launch writes the header and the samples straight into mapped pinned memory
+    const size_t cap_eff = std::min(cap, (size_t)1 << 26);
+    int rc = pp_pinned_reserve(ctx, 64 + cap_eff * 24);
     if (rc) return rc;
-    alignas(16) unsigned char h_plan[PP_DUBINS_PLAN_BYTES];
-    uint32_t h_cnt = 0;
-    PP_CUDA(ctx, cudaMemcpyAsync(&h_cnt, dcnt, 4, cudaMemcpyDeviceToHost, s));
-    PP_CUDA(ctx, cudaMemcpyAsync(h_plan, dplan, PP_DUBINS_PLAN_BYTES, cudaMemcpyDeviceToHost, s));
+    pp_path_header_host *hdr = (pp_path_header_host *)ctx->pinned;
+    double *samples = (double *)((char *)ctx->pinned + 64);
+    rc = pp_launch_dubins_path(ctx, sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin, (uint32_t)cap_eff, hdr, samples,
+                               s);
+    if (rc) return rc;
     PP_CUDA(ctx, cudaStreamSynchronize(s));
-    // plan layout (dubins_device.cuh): len[3] @0, ..., word @104
-    double h_len[3];
-    memcpy(h_len, h_plan, 24);
-    int w = h_plan[104];
+    const int w = (int)hdr->word;
     if (word) *word = w;
-    if (cost) *cost = (w == PP_WORD_NONE) ? INFINITY : (std::fabs(h_len[0]) + std::fabs(h_len[1])) + std::fabs(h_len[2]);
+    if (cost) *cost = hdr->cost;
     if (w == PP_WORD_NONE) return PP_OK;  // reference: None
+    const uint32_t h_cnt = hdr->count;
     if (h_cnt == 0xFFFFFFFFu) return pp_fail(ctx, PP_ERR_OVERFLOW, "path too long for the sample replay");
-    if (h_cnt > cap) {
+    if (h_cnt > cap_eff) {
         *n_out = h_cnt;
         return pp_fail(ctx, PP_ERR_OVERFLOW, "sample capacity too small");
     }
     if (h_cnt == 0) return PP_OK;
     if (!px || !py) return PP_ERR_INVALID;
-    PP_TMP(ctx, dout, s, (size_t)h_cnt * 24);
-    rc = pp_launch_dubins_fill(ctx, 1, dplan, doff, dout.as<double>(), s);
-    if (rc) return rc;
-    std::vector<double> h((size_t)h_cnt * 3);
-    PP_CUDA(ctx, cudaMemcpyAsync(h.data(), dout.p, (size_t)h_cnt * 24, cudaMemcpyDeviceToHost, s));
-    PP_CUDA(ctx, cudaStreamSynchronize(s));
     for (uint32_t k = 0; k < h_cnt; ++k) {
-        px[k] = h[3 * k];
-        py[k] = h[3 * k + 1];
-        if (pyaw) pyaw[k] = h[3 * k + 2];
+        px[k] = samples[3 * k];
+        py[k] = samples[3 * k + 1];
+        if (pyaw) pyaw[k] = samples[3 * k + 2];
     }
     *n_out = h_cnt;
     return PP_OK;
@@ -1024,6 +1035,23 @@ int pp_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *i
     int rc = pp_nn_prepare(ctx, flags);
     if (rc) return rc;
     cudaStream_t s = ctx->stream;
+    if (m <= 64) {
+        // the scalar get_nearest_node call: queries and answers live in mapped pinned memory, so the whole
+        // call is one kernel launch and one stream synchronisation (no allocation, no explicit copy)
+        rc = pp_pinned_reserve(ctx, 4096);
+        if (rc) return rc;
+        double *q = (double *)ctx->pinned;          // [0, 1024): qx, qy
+        double *od2 = q + 128;                       // [1024, 1536)
+        uint32_t *oidx = (uint32_t *)(q + 192);      // [1536, 1792)
+        memcpy(q, qx, m * 8);
+        memcpy(q + 64, qy, m * 8);
+        rc = pp_launch_nn(ctx, m, q, q + 64, oidx, d2 ? od2 : nullptr, flags, s);
+        if (rc) return rc;
+        PP_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(idx, oidx, m * 4);
+        if (d2) memcpy(d2, od2, m * 8);
+        return PP_OK;
+    }
     PP_TMP(ctx, dq, s, m * 16);
     PP_TMP(ctx, di, s, m * 4);
     PP_TMP(ctx, dd, s, m * 8);
@@ -1122,6 +1150,21 @@ int pp_collide_dubins(pp_ctx *ctx, size_t m, const double *sx, const double *sy,
     pp_guard g(ctx);
     if (!ctx->world.valid) return pp_fail(ctx, PP_ERR_STATE, "obstacles not uploaded");
     cudaStream_t s = ctx->stream;
+    if (m <= 1024) {
+        // verify_node on a chain of a few edges: poses in, flags out through mapped pinned memory
+        int rc0 = pp_pinned_reserve(ctx, 64 + 1024 * 56);
+        if (rc0) return rc0;
+        double *d = (double *)ctx->pinned;
+        uint8_t *pok = (uint8_t *)(d + 6 * m);
+        const double *in[6] = {sx, sy, syaw, ex, ey, eyaw};
+        for (int k = 0; k < 6; ++k) memcpy(d + k * m, in[k], m * 8);
+        rc0 = pp_collide_dubins_impl(ctx, m, d, d + m, d + 2 * m, d + 3 * m, d + 4 * m, d + 5 * m, radius, step, pok,
+                                     flags, s);
+        if (rc0) return rc0;
+        PP_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(ok, pok, m);
+        return PP_OK;
+    }
     PP_TMP(ctx, din, s, m * 48);
     PP_TMP(ctx, dok, s, m);
     double *d = din.as<double>();

@@ -104,25 +104,21 @@ int pp_launch_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi
 // ------------------------------------------------------------------------------------------------
 #define PP_PLAN_MAX_ITERS (1u << 26)
 
-__global__ void __launch_bounds__(128)
-    pp_dubins_plan_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
-                          const double *__restrict__ syaw, const double *__restrict__ ex,
-                          const double *__restrict__ ey, const double *__restrict__ eyaw, double radius, double step,
-                          int from_origin, uint32_t *__restrict__ counts, pp_dubins_plan *__restrict__ plans) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// one path: evaluate + replay; (sx, sy, syaw) are ignored when from_origin
+__device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, double syaw, double ex, double ey,
+                                                       double eyaw, double radius, double step, int from_origin) {
     pp_dubins_plan pl;
     double lex, ley, leyaw, ss, cs;
     if (from_origin) {
-        lex = ex[i];
-        ley = ey[i];
-        leyaw = eyaw[i];
+        lex = ex;
+        ley = ey;
+        leyaw = eyaw;
         pl.sx = pl.sy = pl.syaw = 0.0;
     } else {
-        pl.sx = sx[i];
-        pl.sy = sy[i];
-        pl.syaw = syaw[i];
-        pp_dubins_to_local(pl.sx, pl.sy, pl.syaw, ex[i], ey[i], eyaw[i], &lex, &ley, &leyaw, &ss, &cs);
+        pl.sx = sx;
+        pl.sy = sy;
+        pl.syaw = syaw;
+        pp_dubins_to_local(pl.sx, pl.sy, pl.syaw, ex, ey, eyaw, &lex, &ley, &leyaw, &ss, &cs);
     }
     double c = 1.0 / radius;
     pp_dubins_frame f = pp_dubins_frame_from_local(lex, ley, leyaw, c);
@@ -183,8 +179,101 @@ __global__ void __launch_bounds__(128)
             pl.count = cntout;
         }
     }
+    return pl;
+}
+
+__global__ void __launch_bounds__(128)
+    pp_dubins_plan_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
+                          const double *__restrict__ syaw, const double *__restrict__ ex,
+                          const double *__restrict__ ey, const double *__restrict__ eyaw, double radius, double step,
+                          int from_origin, uint32_t *__restrict__ counts, pp_dubins_plan *__restrict__ plans) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const pp_dubins_plan pl = from_origin
+                                  ? pp_make_plan(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, 1)
+                                  : pp_make_plan(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0);
     counts[i] = pl.count;
     if (plans) plans[i] = pl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar call (dubins_path_planning(&conf) of the reference, a batch of one): ONE launch, arguments by
+// value, plan by thread 0, samples by the whole CTA straight into mapped pinned host memory -- no
+// allocation, no explicit copy, one stream synchronisation on the host side.
+// ------------------------------------------------------------------------------------------------
+struct pp_path_header {
+    uint32_t count, word;
+    double cost, len[3];
+};
+
+__global__ void __launch_bounds__(128)
+    pp_dubins_path_kernel(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
+                          double step, int from_origin, uint32_t cap, pp_path_header *__restrict__ hdr,
+                          double *__restrict__ out) {
+    __shared__ pp_dubins_plan spl;
+    if (threadIdx.x == 0) {
+        spl = pp_make_plan(sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin);
+        hdr->count = spl.count;
+        hdr->word = spl.word;
+        hdr->len[0] = spl.len[0];
+        hdr->len[1] = spl.len[1];
+        hdr->len[2] = spl.len[2];
+        hdr->cost = (spl.word == PP_WORD_NONE) ? CUDART_INF : (fabs(spl.len[0]) + fabs(spl.len[1])) + fabs(spl.len[2]);
+    }
+    __syncthreads();
+    const pp_dubins_plan pl = spl;
+    if (pl.word == PP_WORD_NONE || pl.count == 0 || pl.count == 0xFFFFFFFFu || pl.count > cap) return;
+    double ss = 0.0, cs = 1.0;
+    if (!pl.from_origin) pp_sincos1(pl.syaw, &ss, &cs);
+    if (threadIdx.x == 0) {
+        out[0] = pl.from_origin ? 0.0 : (cs * 0.0 + (-ss) * 0.0) + pl.sx;
+        out[1] = pl.from_origin ? 0.0 : (ss * 0.0 + cs * 0.0) + pl.sy;
+        out[2] = pl.from_origin ? 0.0 : pp_pi_2_pi_fast(0.0 + pl.syaw);
+    }
+    double ox = 0.0, oy = 0.0, oyaw = 0.0, so = 0.0, co = 1.0;
+    uint32_t base = 1;
+#pragma unroll
+    for (int seg = 0; seg < 3; ++seg) {
+        const int mode = pp_word_mode(pl.word, seg);
+        const double len = pl.len[seg], pd0 = pl.pd0[seg];
+        const double d = (len > 0.0) ? pl.step : -pl.step;
+        const uint32_t ns = pl.n[seg];
+        for (uint32_t j = threadIdx.x; j < ns; j += blockDim.x) {
+            const uint32_t k = base + j;
+            if (k >= pl.count) break;
+            double x, y, yaw;
+            pp_interpolate(mode, pd0 + (double)j * d, ox, oy, oyaw, so, co, pl.rinv, &x, &y, &yaw);
+            if (!pl.from_origin) {
+                const double xw = (cs * x + (-ss) * y) + pl.sx;
+                const double yw = (ss * x + cs * y) + pl.sy;
+                x = xw;
+                y = yw;
+                yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
+            }
+            out[3 * (size_t)k + 0] = x;
+            out[3 * (size_t)k + 1] = y;
+            out[3 * (size_t)k + 2] = yaw;
+        }
+        base += ns;
+        if (seg < 2) {
+            double ex_, ey_, eyaw_;
+            pp_interpolate(mode, len, ox, oy, oyaw, so, co, pl.rinv, &ex_, &ey_, &eyaw_);
+            ox = ex_;
+            oy = ey_;
+            oyaw = eyaw_;
+            pp_sincos1(oyaw, &so, &co);
+        }
+    }
+}
+
+int pp_launch_dubins_path(pp_ctx *ctx, double sx, double sy, double syaw, double ex, double ey, double eyaw,
+                          double radius, double step, int from_origin, uint32_t cap, void *hdr, double *out,
+                          cudaStream_t stream) {
+    pp_launch_scope scope(ctx, "dubins_path");
+    pp_dubins_path_kernel<<<1, 128, 0, stream>>>(sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin, cap,
+                                                 (pp_path_header *)hdr, out);
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
 }
 
 int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
