@@ -408,6 +408,24 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
                          "hbm_view": {"achieved": 36.0 * 2 ** 20 / nn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                       "per_unit": "36 MiB algorithmic bytes per launch"}},
         }
+    # the same step with the reference's real edge geometry: Dubins curve new node -> nearest node, sampled at 0.1
+    fn = lambda: ctx.rrt_extend_dubins_dev(m, qx, qy, 0.8, 0.1, idx, yaw, ok)  # noqa: E731
+    ctx.timing_enable(True)
+    fn()
+    torch.cuda.synchronize()
+    ctx.timing_reset()
+    l0 = ctx.launch_count
+    ms, _, _ = time_steps(torch, dist, fn, steps, 0, world)
+    parts = {k: ctx.timing_get(k) for k in ("nn_scan", "dubins_plan", "collide_dubins")}
+    ctx.timing_enable(False)
+    out["extend_dubins"] = {
+        "metric": "rrt_extend_steps_per_s", "value": world * m * steps / (ms * 1e-3), "unit": "steps/s",
+        "ms_per_step": ms / steps, "steps": steps, "gpu_launches": ctx.launch_count - l0,
+        "kernel_ms": {k: v[0] / max(v[1], 1) for k, v in parts.items()},
+        "config": {"workload": f"c4 with Dubins edges: {m} samples/GPU vs {C4_NODES}-node tree, NN + Node::new yaw + fused "
+                               f"sample-and-verify of the Dubins edge (turn radius 0.8, step 0.1) vs {C4_RINGS} rings",
+                   "free_fraction_rank0": float(ok.float().mean().item())},
+    }
     # no-hit obstacle set: same rings translated outside the world, so early exit cannot flatter the number
     bounds2, rings2 = pp.synth.circle_world(C4_RINGS, shift=5000.0)
     ctx.obstacles_upload(bounds2, rings2)

@@ -192,6 +192,15 @@ int pp_rrt_extend(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uin
 int pp_rrt_extend_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *yaw,
                       uint8_t *ok, int nn_flags, int collide_flags);
 
+/* the same step with the reference's real edge geometry (src/rrt.rs:406-426, 291-321): idx = nearest node,
+ * yaw = heading from q_j toward it, ok = Space::verify of the Dubins curve (q_j, yaw) -> (node, node yaw)
+ * sampled at `step` (polyline = samples ++ [node point]).  For a tree whose nodes were inserted through
+ * verify_node (every chain already verified) this is verify_node of the new node. */
+int pp_rrt_extend_dubins(pp_ctx *ctx, size_t m, const double *qx, const double *qy, double radius, double step,
+                         uint32_t *idx, double *yaw, uint8_t *ok, int nn_flags, int collide_flags);
+int pp_rrt_extend_dubins_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy, double radius, double step,
+                             uint32_t *idx, double *yaw, uint8_t *ok, int nn_flags, int collide_flags);
+
 /* ------------------------------------------------------------------ measurement helpers */
 /* FP64 pipe peak micro-benchmark: runs `iters` dependent DFMA chains of
  * length `chain` on every SM and returns DFMA thread-instructions per second. */

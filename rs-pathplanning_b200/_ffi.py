@@ -79,6 +79,8 @@ SIGNATURES = {
     "pp_collide_dubins_dev": (_i, [_vp, _sz] + [_vp] * 6 + [_d, _d, _vp, _i]),
     "pp_rrt_extend": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "pp_rrt_extend_dev": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "pp_rrt_extend_dubins": (_i, [_vp, _sz, _vp, _vp, _d, _d, _vp, _vp, _vp, _i, _i]),
+    "pp_rrt_extend_dubins_dev": (_i, [_vp, _sz, _vp, _vp, _d, _d, _vp, _vp, _vp, _i, _i]),
     "pp_measure_fp64_peak": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_d)]),
     "pp_timing_enable": (_i, [_vp, _i]),
     "pp_timing_reset": (_i, [_vp]),
@@ -380,3 +382,18 @@ class Context:
     def rrt_extend_dev(self, m, qx, qy, idx, yaw, ok, nn_flags=NN_DEFAULT, collide_flags=COLLIDE_DEFAULT):
         self._ck(lib.pp_rrt_extend_dev(self._h, int(m), _ptr(qx), _ptr(qy), _ptr(idx), _ptr(yaw), _ptr(ok),
                                        int(nn_flags), int(collide_flags)), "rrt_extend_dev")
+
+    def rrt_extend_dubins(self, qx, qy, radius, step, nn_flags=NN_DEFAULT, collide_flags=COLLIDE_DEFAULT):
+        """nearest node, new node's yaw and verify of the Dubins edge new -> nearest, per sample point"""
+        qx, qy = _np(np.atleast_1d(qx), np.float64), _np(np.atleast_1d(qy), np.float64)
+        m = qx.size
+        idx, yaw, ok = np.empty(m, np.uint32), np.empty(m, np.float64), np.empty(m, np.uint8)
+        self._ck(lib.pp_rrt_extend_dubins(self._h, m, _ptr(qx), _ptr(qy), float(radius), float(step), _ptr(idx),
+                                          _ptr(yaw), _ptr(ok), int(nn_flags), int(collide_flags)), "rrt_extend_dubins")
+        return idx, yaw, ok
+
+    def rrt_extend_dubins_dev(self, m, qx, qy, radius, step, idx, yaw, ok, nn_flags=NN_DEFAULT,
+                              collide_flags=COLLIDE_DEFAULT):
+        self._ck(lib.pp_rrt_extend_dubins_dev(self._h, int(m), _ptr(qx), _ptr(qy), float(radius), float(step), _ptr(idx),
+                                              _ptr(yaw), _ptr(ok), int(nn_flags), int(collide_flags)),
+                 "rrt_extend_dubins_dev")

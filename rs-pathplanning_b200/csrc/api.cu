@@ -36,6 +36,8 @@ int pp_launch_verify_polylines(pp_ctx *, size_t, const double *, const double *,
 int pp_launch_collide_dubins(pp_ctx *, size_t, const void *, const double *, const double *, uint8_t *, int,
                              cudaStream_t);
 int pp_launch_fp64_peak(pp_ctx *, int, double *, cudaStream_t, unsigned *, unsigned *);
+int pp_launch_extend_gather(pp_ctx *, size_t, const double *, const double *, const uint32_t *, double *, double *,
+                            double *, double *, cudaStream_t);
 
 #define PP_AABB_TILE 1024
 #define PP_BOUNDS_GRID 256
@@ -1213,6 +1215,59 @@ int pp_rrt_extend(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uin
     if (rc) return rc;
     rc = pp_launch_collide_segments(ctx, m, q, q + m, nullptr, nullptr, di.as<uint32_t>(), dy.as<double>(),
                                     dok.as<uint8_t>(), collide_flags, s);
+    if (rc) return rc;
+    PP_CUDA(ctx, cudaMemcpyAsync(idx, di.p, m * 4, cudaMemcpyDeviceToHost, s));
+    if (yaw) PP_CUDA(ctx, cudaMemcpyAsync(yaw, dy.p, m * 8, cudaMemcpyDeviceToHost, s));
+    PP_CUDA(ctx, cudaMemcpyAsync(ok, dok.p, m, cudaMemcpyDeviceToHost, s));
+    PP_CUDA(ctx, cudaStreamSynchronize(s));
+    return PP_OK;
+}
+
+static int pp_extend_dubins_impl(pp_ctx *ctx, size_t m, const double *qx, const double *qy, double radius, double step,
+                                 uint32_t *idx, double *yaw, uint8_t *ok, int nn_flags, int collide_flags,
+                                 cudaStream_t s) {
+    int rc = pp_launch_nn(ctx, m, qx, qy, idx, nullptr, nn_flags, s);
+    if (rc) return rc;
+    PP_TMP(ctx, de, s, m * 24);  // ex, ey, eyaw of the nearest nodes
+    double *e = de.as<double>();
+    rc = pp_launch_extend_gather(ctx, m, qx, qy, idx, yaw, e, e + m, e + 2 * m, s);
+    if (rc) return rc;
+    return pp_collide_dubins_impl(ctx, m, qx, qy, yaw, e, e + m, e + 2 * m, radius, step, ok, collide_flags, s);
+}
+
+int pp_rrt_extend_dubins_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy, double radius, double step,
+                             uint32_t *idx, double *yaw, uint8_t *ok, int nn_flags, int collide_flags) {
+    if (!ctx || (m && (!qx || !qy || !idx || !yaw || !ok))) return PP_ERR_INVALID;
+    if (!pp_pos_finite(radius) || !pp_pos_finite(step)) return PP_ERR_INVALID;
+    if (m == 0) return PP_OK;
+    pp_guard g(ctx);
+    if (!ctx->world.valid) return pp_fail(ctx, PP_ERR_STATE, "obstacles not uploaded");
+    if (ctx->tree.n == 0) return pp_fail(ctx, PP_ERR_STATE, "tree is empty");
+    int rc = pp_nn_prepare(ctx, nn_flags);
+    if (rc) return rc;
+    return pp_extend_dubins_impl(ctx, m, qx, qy, radius, step, idx, yaw, ok, nn_flags, collide_flags, ctx->stream);
+}
+
+int pp_rrt_extend_dubins(pp_ctx *ctx, size_t m, const double *qx, const double *qy, double radius, double step,
+                         uint32_t *idx, double *yaw, uint8_t *ok, int nn_flags, int collide_flags) {
+    if (!ctx || (m && (!qx || !qy || !idx || !ok))) return PP_ERR_INVALID;
+    if (!pp_pos_finite(radius) || !pp_pos_finite(step)) return PP_ERR_INVALID;
+    if (m == 0) return PP_OK;
+    pp_guard g(ctx);
+    if (!ctx->world.valid) return pp_fail(ctx, PP_ERR_STATE, "obstacles not uploaded");
+    if (ctx->tree.n == 0) return pp_fail(ctx, PP_ERR_STATE, "tree is empty");
+    int rc = pp_nn_prepare(ctx, nn_flags);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    PP_TMP(ctx, dq, s, m * 16);
+    PP_TMP(ctx, di, s, m * 4);
+    PP_TMP(ctx, dy, s, m * 8);
+    PP_TMP(ctx, dok, s, m);
+    double *q = dq.as<double>();
+    PP_CUDA(ctx, cudaMemcpyAsync(q, qx, m * 8, cudaMemcpyHostToDevice, s));
+    PP_CUDA(ctx, cudaMemcpyAsync(q + m, qy, m * 8, cudaMemcpyHostToDevice, s));
+    rc = pp_extend_dubins_impl(ctx, m, q, q + m, radius, step, di.as<uint32_t>(), dy.as<double>(), dok.as<uint8_t>(),
+                               nn_flags, collide_flags, s);
     if (rc) return rc;
     PP_CUDA(ctx, cudaMemcpyAsync(idx, di.p, m * 4, cudaMemcpyDeviceToHost, s));
     if (yaw) PP_CUDA(ctx, cudaMemcpyAsync(yaw, dy.p, m * 8, cudaMemcpyDeviceToHost, s));

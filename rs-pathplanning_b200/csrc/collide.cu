@@ -511,3 +511,33 @@ int pp_collide_tu_init(pp_ctx *ctx) {
     PP_CUDA(ctx, pp_math_upload_tables());
     return PP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// extend step with Dubins edges: Node::new for every sample (src/rrt.rs:169-175, 267-271) -- the new
+// node's yaw aims at its nearest node, which becomes the goal pose of the edge
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    pp_extend_gather_kernel(size_t m, const double *__restrict__ qx, const double *__restrict__ qy,
+                            const uint32_t *__restrict__ idx, const double *__restrict__ node_x,
+                            const double *__restrict__ node_y, const double *__restrict__ node_yaw,
+                            double *__restrict__ syaw, double *__restrict__ ex, double *__restrict__ ey,
+                            double *__restrict__ eyaw) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t p = idx[i];
+    const double px = node_x[p], py = node_y[p];
+    ex[i] = px;
+    ey[i] = py;
+    eyaw[i] = node_yaw[p];
+    syaw[i] = atan2(py - qy[i], px - qx[i]);  // compute_yaw(from = the new point, to = its parent)
+}
+
+int pp_launch_extend_gather(pp_ctx *ctx, size_t m, const double *qx, const double *qy, const uint32_t *idx,
+                            double *syaw, double *ex, double *ey, double *eyaw, cudaStream_t stream) {
+    if (m == 0) return PP_OK;
+    pp_launch_scope scope(ctx, "extend_gather");
+    pp_extend_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(m, qx, qy, idx, ctx->tree.x, ctx->tree.y,
+                                                                            ctx->tree.yaw, syaw, ex, ey, eyaw);
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}

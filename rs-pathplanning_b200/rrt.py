@@ -282,13 +282,11 @@ class RRT:  # src/rrt.rs:325-619
             budget -= b
             pts = [self.space.rand_point() for _ in range(b)]
             px, py = np.array([p[0] for p in pts]), np.array([p[1] for p in pts])
-            idx = self.ctx.nn(px, py, want_d2=False)
+            # one call: NN -> Node::new yaw -> fused Dubins sample-and-verify of the new edges
+            idx, _, ok = self.ctx.rrt_extend_dubins(px, py, steer, self.step_size)
             parents = [self.nodes[int(i)] for i in idx]
             cand = [Node(p, par) for p, par in zip(pts, parents)]
-            ok = self.ctx.collide_dubins(px, py, [c.yaw for c in cand], [p.point[0] for p in parents],
-                                         [p.point[1] for p in parents], [p.yaw for p in parents], steer,
-                                         self.step_size).astype(bool)
-            fresh = [c for c, good in zip(cand, ok) if good]
+            fresh = [c for c, good in zip(cand, ok.astype(bool)) if good]
             if not fresh:
                 continue
             self.ctx.tree_append([c.point[0] for c in fresh], [c.point[1] for c in fresh], [c.yaw for c in fresh],

@@ -62,6 +62,9 @@ extern "C" {
                              radius: c_double, step: c_double, ok: *mut u8, flags: c_int) -> c_int;
     pub fn pp_rrt_extend(ctx: *mut pp_ctx, m: usize, qx: *const c_double, qy: *const c_double, idx: *mut u32,
                          yaw: *mut c_double, ok: *mut u8, nn_flags: c_int, collide_flags: c_int) -> c_int;
+    pub fn pp_rrt_extend_dubins(ctx: *mut pp_ctx, m: usize, qx: *const c_double, qy: *const c_double,
+                                radius: c_double, step: c_double, idx: *mut u32, yaw: *mut c_double, ok: *mut u8,
+                                nn_flags: c_int, collide_flags: c_int) -> c_int;
 }
 
 /// one context per process; pp_ctx is internally synchronised, so `&Ctx` may be shared by rayon workers

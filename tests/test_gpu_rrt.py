@@ -268,3 +268,23 @@ def test_plan_rounds_keeps_the_tree_invariant(pp, ctx, O):
     if path is not None:
         assert W.verify(path[0], path[1])
         assert abs(path[0][-1] - 6.0) < 0.2 and abs(path[1][-1] - 10.0) < 0.2  # ends next to the goal (Q6)
+
+
+def test_extend_step_with_dubins_edges(ctx, O, pp):
+    """pp_rrt_extend_dubins = get_random_node + verify of the Dubins edge new -> nearest (src/rrt.rs:406-426)"""
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(6000, 4000, world=120.0)
+    bounds, rings = pp.synth.circle_world(150, world=120.0, rmin=0.5, rmax=2.0)
+    ctx.tree_upload(nx, ny, nyaw)
+    ctx.obstacles_upload(bounds, rings)
+    oidx, _ = O.nn_brute(nx, ny, qx, qy)
+    wyaw = np.array([O.compute_yaw(qx[i], qy[i], nx[oidx[i]], ny[oidx[i]]) for i in range(qx.size)])
+    W = O.OracleWorld(bounds, rings)
+    want = W.verify_dubins_edges(qx, qy, wyaw, nx[oidx], ny[oidx], nyaw[oidx], 0.8, 0.1)
+    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, DEFAULT)]:
+        idx, yaw, ok = ctx.rrt_extend_dubins(qx, qy, 0.8, 0.1, nn_flags=nnf, collide_flags=cf)
+        assert np.array_equal(idx, oidx)
+        assert np.abs(yaw - wyaw).max() < 1e-12
+        assert (ok != want).sum() <= 2  # sample coordinates agree to 1e-9: only grazing samples can differ
+    assert 0 < want.sum() < want.size
+    one = ctx.rrt_extend_dubins([qx[0]], [qy[0]], 0.8, 0.1)  # scalar use
+    assert one[0][0] == oidx[0] and one[2][0] == want[0]
