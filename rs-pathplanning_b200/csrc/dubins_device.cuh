@@ -81,7 +81,7 @@ __device__ __forceinline__ pp_dubins_frame pp_dubins_frame_from_local(double lex
     f.d = hypot(lex, ley) * c;
     double a = atan2(ley, lex);  // [-pi, pi]
 #else
-    f.d = sqrt(fma(lex, lex, ley * ley)) * c;  // world-scale coordinates: no overflow guard needed (<= 1 ulp)
+    f.d = pp_sqrt_pos(fma(lex, lex, ley * ley)) * c;  // world-scale coordinates: no overflow guard needed (<= 1 ulp)
     double a = pp_atan2(ley, lex);
 #endif
     // theta = mod2pi(a): floor(a/2pi) is -1 for a < 0, else 0 (and -0 -> +0)
@@ -218,22 +218,24 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve_libm(double alpha, doub
 // BOUNDED: the caller guarantees |x| < 1e5 (or NaN), so the large-quotient guard is not needed.
 template <int N, bool BOUNDED = false>
 __device__ __forceinline__ void pp_mod2pi_n(double (&x)[N]) {
-    double k[N];
+    // The guard looks at the RESULT: with the right floor the value is bit-identical to the reference form and
+    // lies in [0, 2pi]; a floor that is off by one (quotient rounding next to an integer) puts it outside, and a
+    // result within 1e-9 of either end is re-derived with the IEEE division as well.
+    double r[N];
     bool slow = false;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const double q = x[i] * PP_INV_TWO_PI;
-        k[i] = floor(q);
-        const double f = q - k[i];
-        slow |= !(fabs(f - 0.5) < 0.5 - 1e-9);
+        r[i] = x[i] - PP_TWO_PI * floor(q);
+        slow |= !(r[i] > 1e-9 && r[i] < PP_TWO_PI - 1e-9);
         if (!BOUNDED) slow |= !(fabs(q) < 1e5);
     }
     if (slow) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) k[i] = floor(x[i] / PP_TWO_PI);
+        for (int i = 0; i < N; ++i) r[i] = x[i] - PP_TWO_PI * floor(x[i] / PP_TWO_PI);
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = x[i] - PP_TWO_PI * k[i];
+    for (int i = 0; i < N; ++i) x[i] = r[i];
 }
 
 // The six words + selection, written for the FP64 pipe (default).  Differences from the libm version:
@@ -276,8 +278,8 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double be
     // send sqrt(0) and 0/x down the IEEE slow paths of sqrt and division in nearly every warp
     const double v_rlr = f_rlr ? tmp_rlr : 0.5, v_lrl = f_lrl ? tmp_lrl : 0.5;
 
-    const double p_lsl = sqrt(f_lsl ? psq_lsl : 1.0), p_rsr = sqrt(f_rsr ? psq_rsr : 1.0);
-    const double p_lsr = sqrt(f_lsr ? psq_lsr : 1.0), p_rsl = sqrt(f_rsl ? psq_rsl : 1.0);
+    const double p_lsl = pp_sqrt_pos(f_lsl ? psq_lsl : 1.0), p_rsr = pp_sqrt_pos(f_rsr ? psq_rsr : 1.0);
+    const double p_lsr = pp_sqrt_pos(f_lsr ? psq_lsr : 1.0), p_rsl = pp_sqrt_pos(f_rsl ? psq_rsl : 1.0);
 
     // ---- six atan2 in one batch
     double ay[6], ax[6], at[6];

@@ -111,6 +111,40 @@ PP_MATH_FN void pp_sincos1(double x, double *s, double *c) {
     *c = co[0];
 }
 
+// quotient n / d for 0 <= n <= d, d a positive normal number: hardware reciprocal seed (MUFU.RCP64H), two Newton
+// steps and one residual correction (<= 1 ulp); the IEEE division's range checks and slow-path call are not
+// needed for these operands.  The host build (accuracy harness) uses the plain division.
+PP_MATH_FN double pp_div_01(double n, double d) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    const double q = n * r;
+    return fma(fma(-d, q, n), r, q);
+#else
+    return n / d;
+#endif
+}
+
+// sqrt(x) for finite x >= 0: hardware reciprocal-square-root seed (MUFU.RSQ64H, ~2^-22), one coupled Newton
+// step on (g ~ sqrt x, h ~ 1/(2 sqrt x)) and one residual correction (<= 1 ulp, exact for 0); no range checks.
+PP_MATH_FN double pp_sqrt_pos(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x + 0x1p-1000));  // keeps the seed finite for x = 0
+    double g = x * y, h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    return fma(fma(-g, g, x), h, g);
+#else
+    return sqrt(x);
+#endif
+}
+
 // ---- atan2: a = min(|x|,|y|) / max(|x|,|y|) in [0,1], atan(a) = a + a s A(s) (degree-21 polynomial in
 // s = a^2), then the octant fix-ups pi/2 - r, pi - r and the sign of y.  Signed zeros follow C99
 // (atan2(+-0, -x) = +-pi, atan2(+-0, +x) = +-0); NaN propagates; (0, 0) gives +-0 or +-pi like glibc.
@@ -126,7 +160,7 @@ PP_MATH_FN void pp_atan2_n(const double (&y)[N], const double (&x)[N], double (&
         // which only happens for non-finite poses whose cost is not finite either
         swp[i] = ay > ax;
         const double mx = swp[i] ? ay : ax, mn = swp[i] ? ax : ay;
-        a[i] = mn / (mx + 0x1p-1000);  // (0, 0) -> 0; leaves every mx > 1e-285 unchanged; NaN propagates
+        a[i] = pp_div_01(mn, mx + 0x1p-1000);  // (0, 0) -> 0; leaves every mx > 1e-285 unchanged; NaN propagates
         s[i] = a[i] * a[i];
         p[i] = pp_atan_c[21];
     }
@@ -153,7 +187,7 @@ PP_MATH_FN double pp_atan2(double y, double x) {
 
 // the argument pair that turns acos(v), |v| <= 1, into an atan2: acos(v) = atan2(sqrt((1-v)(1+v)), v)
 PP_MATH_FN void pp_acos_as_atan2(double v, double *y, double *x) {
-    *y = sqrt((1.0 - v) * (1.0 + v));
+    *y = pp_sqrt_pos((1.0 - v) * (1.0 + v));
     *x = v;
 }
 PP_MATH_FN double pp_acos(double v) {
