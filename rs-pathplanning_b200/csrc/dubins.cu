@@ -13,7 +13,7 @@
 #define PP_EVAL_THREADS 128
 
 #ifndef PP_EVAL_MIN_BLOCKS
-#define PP_EVAL_MIN_BLOCKS 7  // 72 registers; measured 0.789 ms vs 0.809 (5 CTAs, 96 regs) per 2^24 pairs
+#define PP_EVAL_MIN_BLOCKS 6  // 80 registers; measured per 2^24 pairs: 0.658 ms (6), 0.661 (5), 0.665 (7), 0.692 (8)
 #endif
 template <bool HAS_RADIUS_ARR, bool WANT_TPQ>
 __global__ void __launch_bounds__(PP_EVAL_THREADS, PP_EVAL_MIN_BLOCKS)

@@ -243,8 +243,8 @@ __device__ __forceinline__ void pp_mod2pi_n(double (&x)[N]) {
 //     angle-difference identity (3 DP instructions instead of a third trig call)
 //   * LSR / RSL: atan2(y1,x1) - atan2(y2,x2) is folded into ONE atan2(y1 x2 - x1 y2, x1 x2 + y1 y2); the
 //     result differs by a multiple of 2 pi, which the following mod2pi removes
-//   * acos(v) = atan2(sqrt((1-v)(1+v)), v): the two CCC words join the same batch
-//   * the six atan2 and the twelve mod2pi run as interleaved batches (coefficients fetched once, 6-12
+//   * the two acos of the CCC words as one 2-way batch of the direct asin-polynomial kernel (no division)
+//   * the four atan2 and the twelve mod2pi run as interleaved batches (coefficients fetched once, 4-10
 //     independent dependency chains in flight)
 // All of it stays inside the 1e-9 contract; t/q agree with the reference to a few ulp away from the wrap.
 template <bool WANT_ALL>
@@ -281,8 +281,8 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double be
     const double p_lsl = pp_sqrt_pos(f_lsl ? psq_lsl : 1.0), p_rsr = pp_sqrt_pos(f_rsr ? psq_rsr : 1.0);
     const double p_lsr = pp_sqrt_pos(f_lsr ? psq_lsr : 1.0), p_rsl = pp_sqrt_pos(f_rsl ? psq_rsl : 1.0);
 
-    // ---- six atan2 in one batch
-    double ay[6], ax[6], at[6];
+    // ---- four atan2 in one batch, the two acos of the CCC words in another
+    double ay[4], ax[4], at[4];
     ay[0] = cb - ca;  // LSL (and LRL, negated)
     ax[0] = (d + sa) - sb;
     ay[1] = ca - cb;  // RSR (and RLR)
@@ -297,12 +297,15 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double be
         ay[3] = fma(y1, p_rsl, -2.0 * x1);
         ax[3] = fma(x1, p_rsl, 2.0 * y1);
     }
-    pp_acos_as_atan2(v_rlr, &ay[4], &ax[4]);
-    pp_acos_as_atan2(v_lrl, &ay[5], &ax[5]);
-    pp_atan2_n<6>(ay, ax, at);
+    pp_atan2_n<4>(ay, ax, at);
+    double ac[2];
+    {
+        const double vv[2] = {v_rlr, v_lrl};
+        pp_acos_n<2>(vv, ac);
+    }
 
-    const double pc_rlr = pp_mod2pi_unit(PP_TWO_PI - at[4]);  // p of RLR, in [pi, 2pi] -> only 2pi wraps
-    const double pc_lrl = pp_mod2pi_unit(PP_TWO_PI - at[5]);
+    const double pc_rlr = pp_mod2pi_unit(PP_TWO_PI - ac[0]);  // p of RLR, in [pi, 2pi] -> only 2pi wraps
+    const double pc_lrl = pp_mod2pi_unit(PP_TWO_PI - ac[1]);
 
     // ---- twelve mod2pi in two batches (q of the CCC words needs their t)
     double m[10];

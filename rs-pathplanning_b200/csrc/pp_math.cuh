@@ -34,17 +34,21 @@
 static __constant__ __attribute__((aligned(16))) double pp_sin_c[6];
 static __constant__ __attribute__((aligned(16))) double pp_cos_c[6];
 static __constant__ __attribute__((aligned(16))) double pp_atan_c[22];
+static __constant__ __attribute__((aligned(16))) double pp_asin_c[14];  // 13 used
 static inline cudaError_t pp_math_upload_tables() {
     static const double h_sin[6] = PP_SIN_COEF, h_cos[6] = PP_COS_COEF, h_atan[22] = PP_ATAN_COEF;
+    static const double h_asin[14] = PP_ASIN_COEF;
     cudaError_t e = cudaMemcpyToSymbol(pp_sin_c, h_sin, sizeof h_sin);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(pp_cos_c, h_cos, sizeof h_cos);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(pp_atan_c, h_atan, sizeof h_atan);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(pp_asin_c, h_asin, sizeof h_asin);
     return e;
 }
 #else
 PP_MATH_TABLE pp_sin_c[6] = PP_SIN_COEF;
 PP_MATH_TABLE pp_cos_c[6] = PP_COS_COEF;
 PP_MATH_TABLE pp_atan_c[22] = PP_ATAN_COEF;
+PP_MATH_TABLE pp_asin_c[14] = PP_ASIN_COEF;
 #endif
 
 // ---- sincos: Cody-Waite reduction by pi/2 with three FMAs (pi/2 = P1 + P2 + P3 to ~160 bits), then the
@@ -185,13 +189,50 @@ PP_MATH_FN double pp_atan2(double y, double x) {
     return o[0];
 }
 
-// the argument pair that turns acos(v), |v| <= 1, into an atan2: acos(v) = atan2(sqrt((1-v)(1+v)), v)
-PP_MATH_FN void pp_acos_as_atan2(double v, double *y, double *x) {
-    *y = pp_sqrt_pos((1.0 - v) * (1.0 + v));
-    *x = v;
+// ---- acos, direct: asin(r) = r + r z Q(z) on z = r^2 <= 1/4 (13 coefficients), with the usual two ranges
+//   |v| <= 1/2 : acos(v) = pi/2 - asin(v)
+//   |v| >  1/2 : r = sqrt((1 - |v|) / 2) (exact subtraction), acos(|v|) = 2 asin(r), acos(-|v|) = pi - 2 asin(r)
+// |v| > 1 gives NaN (the square root of a negative number), NaN propagates.  About 30 FP64 instructions per
+// value against ~47 for the atan2 form, and no division.
+template <int N>
+PP_MATH_FN void pp_acos_n(const double (&v)[N], double (&out)[N]) {
+    double s[N], z[N], p[N];
+    bool big[N];
+    PP_UNROLL
+    for (int i = 0; i < N; ++i) {
+        const double av = fabs(v[i]);
+        big[i] = av > 0.5;
+        z[i] = big[i] ? (1.0 - av) * 0.5 : av * av;
+        p[i] = pp_asin_c[12];
+    }
+    PP_UNROLL
+    for (int i = 0; i < N; ++i) {
+#ifdef __CUDA_ARCH__
+        const double rt = pp_sqrt_pos(z[i]);
+#else
+        const double rt = sqrt(z[i]);
+#endif
+        s[i] = big[i] ? rt : v[i];
+    }
+    PP_UNROLL
+    for (int j = 11; j >= 0; --j) {
+        PP_UNROLL
+        for (int i = 0; i < N; ++i) p[i] = fma(p[i], z[i], pp_asin_c[j]);
+    }
+    PP_UNROLL
+    for (int i = 0; i < N; ++i) {
+        const double corr = (s[i] * z[i]) * p[i];  // asin(s) - s
+        if (big[i]) {
+            const double r2 = 2.0 * (s[i] + corr);
+            out[i] = signbit(v[i]) ? (PP_PI_HI - r2) + PP_PI_LO : r2;
+        } else {
+            out[i] = PP_PIO2 - (s[i] - (PP_PIO2_LO - corr));
+        }
+    }
 }
 PP_MATH_FN double pp_acos(double v) {
-    double y, x;
-    pp_acos_as_atan2(v, &y, &x);
-    return pp_atan2(y, x);
+    const double vi[1] = {v};
+    double o[1];
+    pp_acos_n<1>(vi, o);
+    return o[0];
 }
