@@ -15,20 +15,13 @@
 #ifndef PP_EVAL_MIN_BLOCKS
 #define PP_EVAL_MIN_BLOCKS 6  // 80 registers; measured per 2^24 pairs: 0.658 ms (6), 0.661 (5), 0.665 (7), 0.692 (8)
 #endif
-template <bool HAS_RADIUS_ARR, bool WANT_TPQ>
-__global__ void __launch_bounds__(PP_EVAL_THREADS, PP_EVAL_MIN_BLOCKS)
-    pp_dubins_eval_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
-                          const double *__restrict__ syaw, const double *__restrict__ ex,
-                          const double *__restrict__ ey, const double *__restrict__ eyaw,
-                          const double *__restrict__ radius_arr, double radius, double *__restrict__ cost,
-                          uint8_t *__restrict__ word, double *__restrict__ tpq) {
-    size_t i = (size_t)blockIdx.x * PP_EVAL_THREADS + threadIdx.x;
-    if (i >= n) return;
+// one pose pair: to_local + frame + six words + selection (src/dubins.rs:401-408, 333-363); c = 1 / turn_radius
+template <bool WANT_TPQ>
+__device__ __forceinline__ void pp_eval_one(double sx, double sy, double syaw, double ex, double ey, double eyaw,
+                                            double c, size_t i, double *__restrict__ cost,
+                                            uint8_t *__restrict__ word, double *__restrict__ tpq) {
     double lex, ley, leyaw, ss, cs;
-    pp_dubins_to_local(__ldg(sx + i), __ldg(sy + i), __ldg(syaw + i), __ldg(ex + i), __ldg(ey + i), __ldg(eyaw + i),
-                       &lex, &ley, &leyaw, &ss, &cs);
-    double r = HAS_RADIUS_ARR ? __ldg(radius_arr + i) : radius;
-    double c = 1.0 / r;  // src/dubins.rs:404
+    pp_dubins_to_local(sx, sy, syaw, ex, ey, eyaw, &lex, &ley, &leyaw, &ss, &cs);
     pp_dubins_frame f = pp_dubins_frame_from_local(lex, ley, leyaw, c);
     pp_dubins_sol s = pp_dubins_solve<false>(f.alpha, f.beta, f.d, nullptr, nullptr);
     cost[i] = s.cost;
@@ -40,15 +33,36 @@ __global__ void __launch_bounds__(PP_EVAL_THREADS, PP_EVAL_MIN_BLOCKS)
     }
 }
 
+// One thread per pair.  A persistent variant (per-warp two-stage ring in shared memory fed by 1-D bulk copies,
+// 148 x 6 CTAs) was measured and dropped: 0.785 ms against 0.651 ms per 2^24 pairs -- inside a loop ptxas hoists
+// the coefficient loads, runs out of uniform registers and executes 1 160 instead of ~950 instructions per pair,
+// and even behind a call the ring bookkeeping costs more than the 10 % of load-scoreboard stalls it removes
+// (profiles/r01_summary.md).
+template <bool HAS_RADIUS_ARR, bool WANT_TPQ>
+__global__ void __launch_bounds__(PP_EVAL_THREADS, PP_EVAL_MIN_BLOCKS)
+    pp_dubins_eval_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
+                          const double *__restrict__ syaw, const double *__restrict__ ex,
+                          const double *__restrict__ ey, const double *__restrict__ eyaw,
+                          const double *__restrict__ radius_arr, double inv_radius, double *__restrict__ cost,
+                          uint8_t *__restrict__ word, double *__restrict__ tpq) {
+    size_t i = (size_t)blockIdx.x * PP_EVAL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    // src/dubins.rs:404 `c = 1 / turn_radius`: for a scalar radius the host passes the quotient (same IEEE division)
+    const double c = HAS_RADIUS_ARR ? 1.0 / __ldg(radius_arr + i) : inv_radius;
+    pp_eval_one<WANT_TPQ>(__ldg(sx + i), __ldg(sy + i), __ldg(syaw + i), __ldg(ex + i), __ldg(ey + i), __ldg(eyaw + i),
+                          c, i, cost, word, tpq);
+}
+
 int pp_launch_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
                           const double *ex, const double *ey, const double *eyaw, const double *radius_arr,
                           double radius, double *cost, uint8_t *word, double *tpq, cudaStream_t stream) {
     if (n == 0) return PP_OK;
-    unsigned grid = (unsigned)((n + PP_EVAL_THREADS - 1) / PP_EVAL_THREADS);
     pp_launch_scope scope(ctx, "dubins_eval");
+    const double inv_radius = 1.0 / radius;
+    const unsigned grid = (unsigned)((n + PP_EVAL_THREADS - 1) / PP_EVAL_THREADS);
 #define PP_GO(RA, TPQ)                                                                                          \
     pp_dubins_eval_kernel<RA, TPQ><<<grid, PP_EVAL_THREADS, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius_arr, \
-                                                                         radius, cost, word, tpq)
+                                                                         inv_radius, cost, word, tpq)
     if (radius_arr) {
         if (tpq) PP_GO(true, true); else PP_GO(true, false);
     } else {

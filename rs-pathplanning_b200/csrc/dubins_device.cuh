@@ -37,7 +37,8 @@ __device__ __forceinline__ double pp_mod2pi(double x) {
     return x - PP_TWO_PI * k;
 }
 // mod2pi for x already known to lie in [0, 2pi]: only x == 2pi wraps (to 0)
-__device__ __forceinline__ double pp_mod2pi_unit(double x) { return (x == PP_TWO_PI) ? 0.0 : x; }
+// (bit-pattern compare, integer pipe: 2 pi = 0x401921FB54442D18)
+__device__ __forceinline__ double pp_mod2pi_unit(double x) { return (pp_bits(x) == 0x401921FB54442D18LL) ? 0.0 : x; }
 
 // src/dubins.rs:22-24 ; Rust % == fmod
 __device__ __forceinline__ double pp_pi_2_pi(double a) { return fmod(a + PP_PI, PP_TWO_PI) - PP_PI; }
@@ -227,8 +228,10 @@ __device__ __forceinline__ void pp_mod2pi_n(double (&x)[N]) {
     for (int i = 0; i < N; ++i) {
         const double q = x[i] * PP_INV_TWO_PI;
         r[i] = x[i] - PP_TWO_PI * floor(q);
-        slow |= !(r[i] > 1e-9 && r[i] < PP_TWO_PI - 1e-9);
-        if (!BOUNDED) slow |= !(fabs(q) < 1e5);
+        // 1e-9 < r < 2pi - 1.3e-6, tested on the high word with integer instructions (pp_math.cuh: the FP64
+        // pipe is the bound); negative values and NaN fall outside the unsigned window as well
+        slow |= !((pp_hi32(r[i]) - 0x3E112E0Cu) < (0x401921FBu - 0x3E112E0Cu));
+        if (!BOUNDED) slow |= !pp_abs_below_pow2(q, 16);
     }
     if (slow) {
 #pragma unroll
@@ -339,7 +342,9 @@ __device__ __forceinline__ pp_dubins_sol pp_dubins_solve(double alpha, double be
             all_tpq[3 * W + 1] = _f ? (P) : CUDART_NAN;   \
             all_tpq[3 * W + 2] = _f ? (Q) : CUDART_NAN;   \
         }                                                 \
-        if (_f && _c < best.cost) {                       \
+        /* costs are sums of |.|: non-negative or NaN, so the unsigned bit patterns order like the */ \
+        /* values (NaN above +inf, never selected) and the compare stays off the FP64 pipe */          \
+        if (_f && (unsigned long long)pp_bits(_c) < (unsigned long long)pp_bits(best.cost)) { \
             best.cost = _c;                               \
             best.word = W;                                \
             best.t = (T);                                 \

@@ -8,10 +8,11 @@
 // and the N independent dependency chains give the FP64 pipe its ILP.
 //
 // Accuracy (tests/test_math_host.py, 10^6 samples per function against glibc): sincos <= 1.5 ulp for
-// |x| < 1e5, atan2 <= 2 ulp, acos <= 2 ulp + 1e-16 absolute.  Coefficients: tools/gen_math_tables.py.
+// |x| < 2^16, atan2 <= 1.5 ulp, acos <= 1.2 ulp.  Coefficients: tools/gen_math_tables.py.
 // The header also compiles as plain C++ (g++) for that host-side accuracy test.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #include "pp_math_tables.inc"
 
@@ -51,9 +52,41 @@ PP_MATH_TABLE pp_atan_c[22] = PP_ATAN_COEF;
 PP_MATH_TABLE pp_asin_c[14] = PP_ASIN_COEF;
 #endif
 
+// Range checks that do not need the value's low word are done on the HIGH 32 bits with integer instructions:
+// the FP64 pipe is the kernels' bound (64 lanes per SM), the integer ALU is nearly idle, and a DSETP costs the
+// same FP64 issue slot as a DFMA.  For non-negative doubles the bit patterns order like the values.
+PP_MATH_FN unsigned pp_hi32(double x) {
+#ifdef __CUDA_ARCH__
+    return (unsigned)__double2hiint(x);
+#else
+    unsigned long long u;
+    memcpy(&u, &x, 8);
+    return (unsigned)(u >> 32);
+#endif
+}
+PP_MATH_FN long long pp_bits(double x) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(x);
+#else
+    long long u;
+    memcpy(&u, &x, 8);
+    return u;
+#endif
+}
+// |x| < 2^k for a finite x (false for NaN / inf): exponent-field compare
+PP_MATH_FN bool pp_abs_below_pow2(double x, int k) { return (pp_hi32(x) & 0x7fffffffu) < (unsigned)(1023 + k) << 20; }
+// x with its sign flipped when neg (integer XOR on the high word)
+PP_MATH_FN double pp_negate_if(double x, bool neg) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) ^ (neg ? (int)0x80000000u : 0), __double2loint(x));
+#else
+    return neg ? -x : x;
+#endif
+}
+
 // ---- sincos: Cody-Waite reduction by pi/2 with three FMAs (pi/2 = P1 + P2 + P3 to ~160 bits), then the
 // two kernels sin(r) = r + r z S(z), cos(r) = 1 - z/2 + z^2 C(z) on |r| <= pi/4, swapped / negated by quadrant.
-// Valid for |x| < 1e5; larger or non-finite arguments take the library routine (rare branch).
+// Used for |x| < 2^16; larger or non-finite arguments take the library routine (rare branch).
 template <int N>
 PP_MATH_FN void pp_sincos_n(const double (&x)[N], double (&s)[N], double (&c)[N]) {
     double r[N], z[N], ps[N], pc[N];
@@ -63,7 +96,7 @@ PP_MATH_FN void pp_sincos_n(const double (&x)[N], double (&s)[N], double (&c)[N]
     for (int i = 0; i < N; ++i) {
         // sin is odd, cos even: reduce |x| and put the sign back at the end (keeps sin(-0.0) = -0.0)
         const double xa = fabs(x[i]);
-        slow |= !(xa < 1.0e5);
+        slow |= !pp_abs_below_pow2(x[i], 16);
         const double kf = rint(xa * PP_TWO_OVER_PI);
         q[i] = (int)kf;
         double t = fma(-kf, PP_PIO2_1, xa);
@@ -96,7 +129,7 @@ PP_MATH_FN void pp_sincos_n(const double (&x)[N], double (&s)[N], double (&c)[N]
     if (slow) {
         PP_UNROLL
         for (int i = 0; i < N; ++i)
-            if (!(fabs(x[i]) < 1.0e5)) {
+            if (!pp_abs_below_pow2(x[i], 16)) {
 #ifdef __CUDACC__
                 sincos(x[i], &s[i], &c[i]);
 #else
@@ -162,7 +195,8 @@ PP_MATH_FN void pp_atan2_n(const double (&y)[N], const double (&x)[N], double (&
         // one compare orders the pair (and is reused for the octant fix-up); a NaN operand makes the
         // compare false and then reaches the quotient, so NaN propagates; inf/inf gives NaN (libm: pi/4 ...),
         // which only happens for non-finite poses whose cost is not finite either
-        swp[i] = ay > ax;
+        // (integer compare of the two non-negative bit patterns: same order, NaN sorts above infinity)
+        swp[i] = pp_bits(ay) > pp_bits(ax);
         const double mx = swp[i] ? ay : ax, mn = swp[i] ? ax : ay;
         a[i] = pp_div_01(mn, mx + 0x1p-1000);  // (0, 0) -> 0; leaves every mx > 1e-285 unchanged; NaN propagates
         s[i] = a[i] * a[i];
@@ -175,10 +209,13 @@ PP_MATH_FN void pp_atan2_n(const double (&y)[N], const double (&x)[N], double (&
     }
     PP_UNROLL
     for (int i = 0; i < N; ++i) {
-        double r = fma(a[i] * s[i], p[i], a[i]);
-        if (swp[i]) r = (PP_PIO2 - r) + PP_PIO2_LO;
-        if (signbit(x[i])) r = (PP_PI_HI - r) + PP_PI_LO;
-        out[i] = copysign(r, y[i]);
+        // octants in one step: (B + sgn r) with B = 0, pi/2, pi, pi/2 and sgn = +,-,-,+ for
+        // (swap, x<0) = (0,0), (1,0), (0,1), (1,1); base and sign are picked with integer selects
+        const double r = fma(a[i] * s[i], p[i], a[i]);
+        const bool xneg = signbit(x[i]);
+        const double bh = swp[i] ? PP_PIO2 : (xneg ? PP_PI_HI : 0.0);
+        const double bl = swp[i] ? PP_PIO2_LO : (xneg ? PP_PI_LO : 0.0);
+        out[i] = copysign((bh + pp_negate_if(r, swp[i] != xneg)) + bl, y[i]);
     }
 }
 
@@ -201,7 +238,7 @@ PP_MATH_FN void pp_acos_n(const double (&v)[N], double (&out)[N]) {
     PP_UNROLL
     for (int i = 0; i < N; ++i) {
         const double av = fabs(v[i]);
-        big[i] = av > 0.5;
+        big[i] = (pp_hi32(av) >= 0x3fe00000u);  // av >= 0.5 (both branches are valid at 0.5)
         z[i] = big[i] ? (1.0 - av) * 0.5 : av * av;
         p[i] = pp_asin_c[12];
     }
