@@ -55,19 +55,26 @@ enum pp_mode { PP_MODE_L = 0, PP_MODE_S = 1, PP_MODE_R = 2 };
 
 /* flags for the collision entry points */
 enum pp_collide_flags {
-    PP_COLLIDE_DEFAULT = 0,
-    PP_COLLIDE_NO_CULL = 1, /* exhaustive segment-pair loop exactly as geo's, no AABB rejection */
-    PP_COLLIDE_USE_GRID = 2, /* broad phase through the uniform obstacle grid instead of the tiled AABB scan */
-    PP_COLLIDE_UNSORTED = 4  /* tiled AABB scan with one edge per thread in the caller's order (no binning) */
+    PP_COLLIDE_DEFAULT = 0,  /* straight edges: broad phase through the uniform obstacle grid (fastest; same flags) */
+    PP_COLLIDE_NO_CULL = 1,  /* exhaustive segment-pair loop exactly as geo's, no AABB rejection */
+    PP_COLLIDE_USE_GRID = 2, /* the obstacle grid, explicitly */
+    PP_COLLIDE_UNSORTED = 4, /* tiled AABB scan with one edge per thread in the caller's order (no binning) */
+    PP_COLLIDE_SCAN = 8      /* tiled scan of ALL ring boxes through shared memory (TMA tiles), edges binned by start
+                                point, 32 boxes per instruction against the warp's union box, hit flags by ballot */
 };
 
 /* flags for pp_nn */
+/* Every method returns the same bit-exact argmin of dx*dx + dy*dy with the lowest index on ties. */
 enum pp_nn_flags {
-    PP_NN_DEFAULT = 0,   /* tiled brute-force scan, queries binned by x, warp-wide exact fp32 pre-rejection */
+    PP_NN_DEFAULT = 0,   /* automatic: the grid search for trees of >= PP_NN_GRID_MIN_NODES nodes when there are more
+                            than 64 queries or the node grid is current; otherwise the brute-force scans */
     PP_NN_PLAIN_F64 = 1, /* tiled brute-force scan, every pair in f64 (the yard-stick kernel) */
-    PP_NN_GRID = 2,      /* exact uniform-grid search (same argmin and tie-break) */
-    PP_NN_UNSORTED = 4   /* tiled scan with per-thread fp32 pre-rejection, queries in the caller's order */
+    PP_NN_GRID = 2,      /* exact uniform-grid search; the grid is (re)built on the device after the tree changed */
+    PP_NN_UNSORTED = 4,  /* tiled scan with per-thread fp32 pre-rejection, queries in the caller's order */
+    PP_NN_SCAN = 8       /* tiled brute-force scan over ALL nodes, queries binned into a G x G grid, warp-wide exact
+                            fp32 pre-rejection (node-parallel variant for <= 64 queries); no index on the tree */
 };
+#define PP_NN_GRID_MIN_NODES 4096
 
 /* bytes of the opaque per-path plan record produced by pp_dubins_sample_count */
 #define PP_DUBINS_PLAN_BYTES 112

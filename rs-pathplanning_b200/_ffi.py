@@ -18,8 +18,8 @@ LIB_PATH = os.environ.get("PP_B200_LIB") or os.path.join(_PKG, "libpathplanning_
 PP_OK, PP_ERR_INVALID, PP_ERR_NO_DEVICE, PP_ERR_CUDA, PP_ERR_NOMEM, PP_ERR_STATE, PP_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5, -6
 WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
 WORD_NONE = 0xFF
-COLLIDE_DEFAULT, COLLIDE_NO_CULL, COLLIDE_USE_GRID, COLLIDE_UNSORTED = 0, 1, 2, 4
-NN_DEFAULT, NN_PLAIN_F64, NN_GRID, NN_UNSORTED = 0, 1, 2, 4
+COLLIDE_DEFAULT, COLLIDE_NO_CULL, COLLIDE_USE_GRID, COLLIDE_UNSORTED, COLLIDE_SCAN = 0, 1, 2, 4, 8
+NN_DEFAULT, NN_PLAIN_F64, NN_GRID, NN_UNSORTED, NN_SCAN = 0, 1, 2, 4, 8
 PLAN_BYTES = 112
 
 if not os.path.exists(LIB_PATH):

@@ -29,6 +29,7 @@ size_t pp_nn_tile_nodes();
 size_t pp_nn_xy32_floats(size_t cap);
 int pp_launch_nn(pp_ctx *, size_t, const double *, const double *, uint32_t *, double *, int, cudaStream_t);
 int pp_launch_tree_finish(pp_ctx *, size_t, size_t, size_t, cudaStream_t);
+int pp_tree_build_grid(pp_ctx *, cudaStream_t);  // nn.cu: device-side counting sort of the nodes by cell
 int pp_launch_collide_segments(pp_ctx *, size_t, const double *, const double *, const double *, const double *,
                                const uint32_t *, double *, uint8_t *, int, cudaStream_t);
 int pp_launch_verify_polylines(pp_ctx *, size_t, const double *, const double *, const uint32_t *, uint8_t *, int,
@@ -661,83 +662,6 @@ int pp_tree_append(pp_ctx *ctx, size_t k, const double *x, const double *y, cons
 }
 size_t pp_tree_size(pp_ctx *ctx) { return ctx ? ctx->tree.n : 0; }
 
-// uniform grid over the nodes for PP_NN_GRID: built on the host from a copy of the device arrays
-static int pp_tree_build_grid(pp_ctx *ctx) {
-    pp_tree_dev &t = ctx->tree;
-    if (t.grid_n == t.n) return PP_OK;
-    const size_t n = t.n;
-    cudaStream_t s = ctx->stream;
-    std::vector<double> x(n), y(n);
-    if (n) {
-        PP_CUDA(ctx, cudaMemcpyAsync(x.data(), t.x, n * 8, cudaMemcpyDeviceToHost, s));
-        PP_CUDA(ctx, cudaMemcpyAsync(y.data(), t.y, n * 8, cudaMemcpyDeviceToHost, s));
-    }
-    PP_CUDA(ctx, cudaStreamSynchronize(s));
-    double minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
-    for (size_t i = 0; i < n; ++i) {
-        if (std::isfinite(x[i]) && std::isfinite(y[i])) {
-            minx = std::min(minx, x[i]);
-            maxx = std::max(maxx, x[i]);
-            miny = std::min(miny, y[i]);
-            maxy = std::max(maxy, y[i]);
-        }
-    }
-    if (!(minx <= maxx)) minx = maxx = miny = maxy = 0.0;
-    double w = maxx - minx, h = maxy - miny;
-    long g = (long)std::floor(std::sqrt((double)std::max<size_t>(n, 1) / 2.0));
-    g = std::max(1L, std::min(g, 4096L));
-    double cell = std::max(w, h) / (double)g;
-    if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
-    double inv = 1.0 / cell;
-    int gx = (int)std::min(4096.0, std::floor(w * inv) + 1.0), gy = (int)std::min(4096.0, std::floor(h * inv) + 1.0);
-    std::vector<uint32_t> start((size_t)gx * gy + 1, 0), items(std::max<size_t>(n, 1)), cellof(n);
-    auto clampi = [](double f, int gmax) {
-        if (!(f > 0.0)) return 0;
-        if (f >= (double)gmax) return gmax - 1;
-        return (int)f;
-    };
-    for (size_t i = 0; i < n; ++i) {
-        // non-finite nodes can never win (d2 is inf or NaN): park them in cell 0
-        int cx = clampi(std::floor((x[i] - minx) * inv), gx), cy = clampi(std::floor((y[i] - miny) * inv), gy);
-        cellof[i] = (uint32_t)((size_t)cy * gx + cx);
-        start[cellof[i] + 1]++;
-    }
-    for (size_t c = 0; c < (size_t)gx * gy; ++c) start[c + 1] += start[c];
-    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
-    for (size_t i = 0; i < n; ++i) items[fill[cellof[i]]++] = (uint32_t)i;
-    if (start.size() > t.cell_cap) {
-        cudaFree(t.cell_start);
-        t.cell_start = nullptr;
-        t.cell_cap = 0;
-        if (cudaMalloc(&t.cell_start, start.size() * 4) != cudaSuccess) {
-            cudaGetLastError();
-            return pp_fail(ctx, PP_ERR_NOMEM, "nn grid allocation failed");
-        }
-        t.cell_cap = start.size();
-    }
-    if (items.size() > t.item_cap) {
-        cudaFree(t.cell_items);
-        t.cell_items = nullptr;
-        t.item_cap = 0;
-        if (cudaMalloc(&t.cell_items, items.size() * 4) != cudaSuccess) {
-            cudaGetLastError();
-            return pp_fail(ctx, PP_ERR_NOMEM, "nn grid allocation failed");
-        }
-        t.item_cap = items.size();
-    }
-    PP_CUDA(ctx, cudaMemcpyAsync(t.cell_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice, s));
-    PP_CUDA(ctx, cudaMemcpyAsync(t.cell_items, items.data(), items.size() * 4, cudaMemcpyHostToDevice, s));
-    PP_CUDA(ctx, cudaStreamSynchronize(s));
-    t.gx = gx;
-    t.gy = gy;
-    t.gminx = minx;
-    t.gminy = miny;
-    t.gcell = cell;
-    t.ginv = inv;
-    t.grid_n = n;
-    return PP_OK;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // obstacles
 // ---------------------------------------------------------------------------------------------------
@@ -1017,15 +941,23 @@ pp_world_view pp_make_world_view(const pp_world_dev &w) {
 // ---------------------------------------------------------------------------------------------------
 // NN / verify / extend
 // ---------------------------------------------------------------------------------------------------
-static int pp_nn_prepare(pp_ctx *ctx, int flags) {
-    if (flags & PP_NN_GRID) return pp_tree_build_grid(ctx);
+// Resolves PP_NN_DEFAULT to a concrete method and makes the node grid current when the grid search is used.
+// Every method returns the same bit-exact argmin (lowest index on ties), so the choice is about time only:
+// the grid search costs O(1) per query but needs the O(n) device-side rebuild after the tree changed; the
+// node-parallel scan serves a handful of queries on a freshly appended tree (the scalar plan_one loop).
+static int pp_nn_prepare(pp_ctx *ctx, size_t m, int *flags) {
+    const pp_tree_dev &t = ctx->tree;
+    if (!(*flags & (PP_NN_GRID | PP_NN_SCAN | PP_NN_PLAIN_F64 | PP_NN_UNSORTED)) && t.n >= PP_NN_GRID_MIN_NODES &&
+        (m > 64 || t.grid_n == t.n))
+        *flags |= PP_NN_GRID;
+    if (*flags & PP_NN_GRID) return pp_tree_build_grid(ctx, ctx->stream);
     return PP_OK;
 }
 
 int pp_nn_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *d2, int flags) {
     if (!ctx || (m && (!qx || !qy || !idx))) return PP_ERR_INVALID;
     pp_guard g(ctx);
-    int rc = pp_nn_prepare(ctx, flags);
+    int rc = pp_nn_prepare(ctx, m, &flags);
     if (rc) return rc;
     return pp_launch_nn(ctx, m, qx, qy, idx, d2, flags, ctx->stream);
 }
@@ -1034,7 +966,7 @@ int pp_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *i
     if (!ctx || (m && (!qx || !qy || !idx))) return PP_ERR_INVALID;
     if (m == 0) return PP_OK;
     pp_guard g(ctx);
-    int rc = pp_nn_prepare(ctx, flags);
+    int rc = pp_nn_prepare(ctx, m, &flags);
     if (rc) return rc;
     cudaStream_t s = ctx->stream;
     if (m <= 64) {
@@ -1187,7 +1119,7 @@ int pp_rrt_extend_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy,
     pp_guard g(ctx);
     if (!ctx->world.valid) return pp_fail(ctx, PP_ERR_STATE, "obstacles not uploaded");
     if (ctx->tree.n == 0) return pp_fail(ctx, PP_ERR_STATE, "tree is empty");
-    int rc = pp_nn_prepare(ctx, nn_flags);
+    int rc = pp_nn_prepare(ctx, m, &nn_flags);
     if (rc) return rc;
     rc = pp_launch_nn(ctx, m, qx, qy, idx, nullptr, nn_flags, ctx->stream);
     if (rc) return rc;
@@ -1201,7 +1133,7 @@ int pp_rrt_extend(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uin
     pp_guard g(ctx);
     if (!ctx->world.valid) return pp_fail(ctx, PP_ERR_STATE, "obstacles not uploaded");
     if (ctx->tree.n == 0) return pp_fail(ctx, PP_ERR_STATE, "tree is empty");
-    int rc = pp_nn_prepare(ctx, nn_flags);
+    int rc = pp_nn_prepare(ctx, m, &nn_flags);
     if (rc) return rc;
     cudaStream_t s = ctx->stream;
     PP_TMP(ctx, dq, s, m * 16);
@@ -1243,7 +1175,7 @@ int pp_rrt_extend_dubins_dev(pp_ctx *ctx, size_t m, const double *qx, const doub
     pp_guard g(ctx);
     if (!ctx->world.valid) return pp_fail(ctx, PP_ERR_STATE, "obstacles not uploaded");
     if (ctx->tree.n == 0) return pp_fail(ctx, PP_ERR_STATE, "tree is empty");
-    int rc = pp_nn_prepare(ctx, nn_flags);
+    int rc = pp_nn_prepare(ctx, m, &nn_flags);
     if (rc) return rc;
     return pp_extend_dubins_impl(ctx, m, qx, qy, radius, step, idx, yaw, ok, nn_flags, collide_flags, ctx->stream);
 }
@@ -1256,7 +1188,7 @@ int pp_rrt_extend_dubins(pp_ctx *ctx, size_t m, const double *qx, const double *
     pp_guard g(ctx);
     if (!ctx->world.valid) return pp_fail(ctx, PP_ERR_STATE, "obstacles not uploaded");
     if (ctx->tree.n == 0) return pp_fail(ctx, PP_ERR_STATE, "tree is empty");
-    int rc = pp_nn_prepare(ctx, nn_flags);
+    int rc = pp_nn_prepare(ctx, m, &nn_flags);
     if (rc) return rc;
     cudaStream_t s = ctx->stream;
     PP_TMP(ctx, dq, s, m * 16);

@@ -650,6 +650,203 @@ int pp_launch_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint
     return PP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-side build of the uniform node grid of pp_nn_grid_kernel (counting sort of the nodes by cell):
+// range of the finite nodes -> 32 bytes to the host, which fixes the grid geometry -> histogram ->
+// single-block scan -> scatter.  The order of the ids inside a cell is whatever the atomics produce; the
+// search compares (d2, index) explicitly, so the answer does not depend on it.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    pp_nn_noderange_kernel(const double *__restrict__ x, const double *__restrict__ y, size_t n,
+                           unsigned long long *__restrict__ mm) {
+    unsigned long long lo[2] = {~0ull, ~0ull}, hi[2] = {0ull, 0ull};
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double v[2] = {x[i], y[i]};
+        if (isfinite(v[0]) && isfinite(v[1])) {  // a node with a non-finite coordinate can never be nearest
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const unsigned long long k = pp_f64_key(v[a]);
+                lo[a] = min(lo[a], k);
+                hi[a] = max(hi[a], k);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_down_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_down_sync(0xffffffffu, hi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&mm[2 * a], lo[a]);
+            atomicMax(&mm[2 * a + 1], hi[a]);
+        }
+    }
+}
+
+// the cell a node is filed under: the same expression the search uses for a query
+__device__ __forceinline__ uint32_t pp_nn_grid_cell(double x, double y, double gminx, double gminy, double ginv, int gx,
+                                                    int gy) {
+    const double fx = floor((x - gminx) * ginv), fy = floor((y - gminy) * ginv);
+    const int cx = (fx >= (double)gx) ? gx - 1 : ((fx > 0.0) ? (int)fx : 0);  // NaN -> 0
+    const int cy = (fy >= (double)gy) ? gy - 1 : ((fy > 0.0) ? (int)fy : 0);
+    return (uint32_t)cy * (uint32_t)gx + (uint32_t)cx;
+}
+
+// hist1 = cell_start + 1: after the inclusive scan cell_start[c] is the first slot of cell c
+__global__ void __launch_bounds__(256)
+    pp_nn_grid_count_kernel(const double *__restrict__ x, const double *__restrict__ y, uint32_t n, double gminx,
+                            double gminy, double ginv, int gx, int gy, uint32_t *__restrict__ hist1) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&hist1[pp_nn_grid_cell(x[i], y[i], gminx, gminy, ginv, gx, gy)], 1u);
+}
+
+// single block, in place: v[i] <- v[0] + ... + v[i]; 16 values per thread and round (16 384 per round), and a
+// copy of the exclusive prefix into cursor[] (the scatter's running slot per cell)
+#define PP_GRID_SCAN_VPT 16
+__global__ void __launch_bounds__(1024)
+    pp_nn_grid_scan_kernel(uint32_t *__restrict__ v, uint32_t nb, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nb; base += 1024 * PP_GRID_SCAN_VPT) {
+        const uint32_t first = base + threadIdx.x * PP_GRID_SCAN_VPT;
+        uint32_t a[PP_GRID_SCAN_VPT];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < PP_GRID_SCAN_VPT; ++k) {
+            a[k] = (first + k < nb) ? v[first + k] : 0u;
+            sum += a[k];
+        }
+        uint32_t inc = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = warp_sums[lane];
+            uint32_t winc = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sums[lane] = winc - w;
+        }
+        __syncthreads();
+        uint32_t run = carry + warp_sums[warp] + inc - sum;  // exclusive prefix of this thread's first value
+#pragma unroll
+        for (int k = 0; k < PP_GRID_SCAN_VPT; ++k) {
+            if (first + k < nb) {
+                cursor[first + k] = run;
+                run += a[k];
+                v[first + k] = run;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = run;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    pp_nn_grid_scatter_kernel(const double *__restrict__ x, const double *__restrict__ y, uint32_t n, double gminx,
+                              double gminy, double ginv, int gx, int gy, uint32_t *__restrict__ cursor,
+                              uint32_t *__restrict__ items) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) items[atomicAdd(&cursor[pp_nn_grid_cell(x[i], y[i], gminx, gminy, ginv, gx, gy)], 1u)] = i;
+}
+
+int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
+    pp_tree_dev &t = ctx->tree;
+    if (t.grid_n == t.n) return PP_OK;
+    const size_t n = t.n;
+    // geometry: ~2 nodes per cell, square cells over the bounding box of the finite nodes
+    long g = (long)floor(sqrt((double)(n > 1 ? n : 1) / 2.0));
+    g = g < 1 ? 1 : (g > 4096 ? 4096 : g);
+    const size_t max_cells = (size_t)(g + 1) * (size_t)(g + 1);
+    int rc = pp_scratch_reserve(ctx, 64 + max_cells * 4);
+    if (rc) return rc;
+    unsigned long long *mm = (unsigned long long *)ctx->scratch;
+    uint32_t *cursor = (uint32_t *)((char *)ctx->scratch + 64);
+    if (max_cells + 1 > t.cell_cap) {
+        PP_CUDA(ctx, cudaStreamSynchronize(stream));
+        cudaFree(t.cell_start);
+        t.cell_start = nullptr;
+        t.cell_cap = 0;
+        const size_t cap = 2 * max_cells + 1;
+        if (cudaMalloc(&t.cell_start, cap * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return pp_fail(ctx, PP_ERR_NOMEM, "nn grid allocation failed");
+        }
+        t.cell_cap = cap;
+    }
+    if ((n > 1 ? n : 1) > t.item_cap) {
+        PP_CUDA(ctx, cudaStreamSynchronize(stream));
+        cudaFree(t.cell_items);
+        t.cell_items = nullptr;
+        t.item_cap = 0;
+        const size_t cap = t.cap > n ? t.cap : (n > 1 ? n : 1);  // grows with the node arrays
+        if (cudaMalloc(&t.cell_items, cap * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return pp_fail(ctx, PP_ERR_NOMEM, "nn grid allocation failed");
+        }
+        t.item_cap = cap;
+    }
+    pp_launch_scope scope(ctx, "nn_grid_build", 4);
+    const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
+    unsigned long long got[4] = {~0ull, 0ull, ~0ull, 0ull};
+    if (n) {
+        PP_CUDA(ctx, cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, stream));
+        const unsigned g1 = (unsigned)((n + 255) / 256);
+        const unsigned gr = g1 < (unsigned)ctx->sm_count * 8 ? g1 : (unsigned)ctx->sm_count * 8;
+        pp_nn_noderange_kernel<<<gr, 256, 0, stream>>>(t.x, t.y, n, mm);
+        PP_CUDA(ctx, cudaMemcpyAsync(got, mm, sizeof got, cudaMemcpyDeviceToHost, stream));
+        PP_CUDA(ctx, cudaStreamSynchronize(stream));
+    }
+    auto unkey = [](unsigned long long k) {
+        const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+        double d;
+        memcpy(&d, &b, 8);
+        return d;
+    };
+    double minx = 0.0, maxx = 0.0, miny = 0.0, maxy = 0.0;
+    if (got[0] <= got[1]) {  // at least one finite node
+        minx = unkey(got[0]);
+        maxx = unkey(got[1]);
+        miny = unkey(got[2]);
+        maxy = unkey(got[3]);
+    }
+    const double w = maxx - minx, h = maxy - miny;
+    double cell = (w > h ? w : h) / (double)g;
+    if (!(cell > 0.0) || !isfinite(cell)) cell = 1.0;
+    const double inv = 1.0 / cell;
+    const double fgx = floor(w * inv) + 1.0, fgy = floor(h * inv) + 1.0;
+    const int gx = (int)(fgx < (double)(g + 1) ? fgx : (double)(g + 1));
+    const int gy = (int)(fgy < (double)(g + 1) ? fgy : (double)(g + 1));
+    const uint32_t ncell = (uint32_t)gx * (uint32_t)gy;
+    PP_CUDA(ctx, cudaMemsetAsync(t.cell_start, 0, ((size_t)ncell + 1) * 4, stream));
+    if (n) {
+        const unsigned g1 = (unsigned)((n + 255) / 256);
+        pp_nn_grid_count_kernel<<<g1, 256, 0, stream>>>(t.x, t.y, (uint32_t)n, minx, miny, inv, gx, gy, t.cell_start + 1);
+        pp_nn_grid_scan_kernel<<<1, 1024, 0, stream>>>(t.cell_start + 1, ncell, cursor);
+        pp_nn_grid_scatter_kernel<<<g1, 256, 0, stream>>>(t.x, t.y, (uint32_t)n, minx, miny, inv, gx, gy, cursor,
+                                                          t.cell_items);
+    }
+    PP_CUDA(ctx, cudaGetLastError());
+    t.gx = gx;
+    t.gy = gy;
+    t.gminx = minx;
+    t.gminy = miny;
+    t.gcell = cell;
+    t.ginv = inv;
+    t.grid_n = n;
+    return PP_OK;
+}
+
 // fl32 copies of x and y in the blocked layout (+inf sentinel padding up to the granule)
 __global__ void pp_tree_x32_kernel(const double *__restrict__ x, const double *__restrict__ y, float *__restrict__ xy32,
                                    size_t first, size_t n) {

@@ -55,7 +55,7 @@ def test_dev_entry_points_match_host_calls(ctx, pp, O):
     yaw = torch.empty(qx.size, dtype=torch.float64, device=dev)
     ok = torch.empty(qx.size, dtype=torch.uint8, device=dev)
     oidx, od2 = O.nn_brute(nx, ny, qx, qy)
-    for flags in (0, 1, 2, 4):
+    for flags in (0, 1, 2, 4, 8):
         idx.zero_()
         ctx.nn_dev(qx.size, dqx, dqy, idx, d2, flags=flags)
         ctx.sync()
@@ -65,7 +65,7 @@ def test_dev_entry_points_match_host_calls(ctx, pp, O):
     W = O.OracleWorld(bounds, rings)
     assert np.array_equal(ok.cpu().numpy(), W.verify_segments(qx, qy, nx[oidx], ny[oidx]))
     bxy = torch.from_numpy(np.stack([nx[oidx], ny[oidx]])).to(dev)
-    for flags in (0, 2, 4):
+    for flags in (0, 2, 4, 8):
         ok.zero_()
         ctx.collide_segments_dev(qx.size, dqx, dqy, bxy[0], bxy[1], ok, flags=flags)
         ctx.sync()

@@ -53,8 +53,8 @@ def test_c4_full_extend_step_properties(ctx, pp, O):
     bounds, rings = pp.synth.circle_world(10_000)
     ctx.tree_upload(nx, ny, nyaw)
     ctx.obstacles_upload(bounds, rings)
-    idx, yaw, ok = ctx.rrt_extend(qx, qy)                             # bucketed scans
-    idx_g, yaw_g, ok_g = ctx.rrt_extend(qx, qy, nn_flags=2, collide_flags=2)  # grid / grid: different algorithms
+    idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=8, collide_flags=8)  # tiled brute-force scans (PP_NN_SCAN, PP_COLLIDE_SCAN)
+    idx_g, yaw_g, ok_g = ctx.rrt_extend(qx, qy)  # default: device-built node grid + obstacle grid, different algorithms
     assert np.array_equal(idx, idx_g) and np.array_equal(ok, ok_g) and np.array_equal(yaw, yaw_g)
     # the reported neighbour is at least as close as 32 random nodes, and as the oracle's on a sub-sample
     d2 = (nx[idx] - qx) ** 2 + (ny[idx] - qy) ** 2

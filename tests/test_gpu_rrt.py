@@ -9,8 +9,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED = 0, 1, 2, 4
-DEFAULT, NO_CULL, USE_GRID, UNSORTED = 0, 1, 2, 4
+NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED, NN_SCAN = 0, 1, 2, 4, 8
+DEFAULT, NO_CULL, USE_GRID, UNSORTED, SCAN = 0, 1, 2, 4, 8
 
 
 def _bench_world(pp):
@@ -23,7 +23,7 @@ def _bench_world(pp):
 
 @pytest.mark.parametrize("n_nodes,m", [(1, 10), (7, 300), (1000, 5000), (1024, 2048), (4096, 129), (4097, 70_001),
                                         (50_000, 20_000), (3000, 3)])
-@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED])
+@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED, NN_SCAN])
 def test_nn_bit_exact(ctx, O, pp, n_nodes, m, flags):
     qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(m, n_nodes, world=1000.0)
     ctx.tree_upload(nx, ny, nyaw)
@@ -33,7 +33,7 @@ def test_nn_bit_exact(ctx, O, pp, n_nodes, m, flags):
     assert np.array_equal(d2, od2)  # same non-fused arithmetic -> same bits
 
 
-@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED])
+@pytest.mark.parametrize("flags", [NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED, NN_SCAN])
 def test_nn_ties_lowest_index(ctx, O, flags):
     # lattice nodes duplicated 3x: every query has exact ties, some at equal distance to 4 lattice points
     g = np.arange(0, 20, dtype=np.float64)
@@ -58,11 +58,38 @@ def test_nn_empty_tree_and_append(ctx, O, pp):
     for a, b in [(10, 11), (11, 1024), (1024, 1030), (1030, 3000)]:
         ctx.tree_append(nx[a:b], ny[a:b], nyaw[a:b], np.arange(a, b) - 1)
         assert ctx.tree_size == b
-        for flags in (NN_DEFAULT, NN_GRID):
+        for flags in (NN_DEFAULT, NN_GRID, NN_SCAN):
             idx = ctx.nn(qx, qy, flags=flags, want_d2=False)
             assert np.array_equal(idx, O.nn_brute(nx[:b], ny[:b], qx, qy)[0])
     one = ctx.nn([qx[0]], [qy[0]], want_d2=False)  # scalar call -> wide kernel
     assert one[0] == O.nn_brute(nx, ny, qx[:1], qy[:1])[0][0]
+
+
+def test_nn_grid_clustered_tree(ctx, O):
+    """device-built node grid on a hostile distribution: tight clusters (thousands of nodes per cell), exact duplicates,
+    far outliers that stretch the bounding box, a non-finite node; queries inside, between and far outside"""
+    rng = np.random.default_rng(11)
+    parts_x, parts_y = [], []
+    for cx, cy, s, k in [(10.0, 10.0, 1e-3, 6000), (-400.0, 250.0, 0.5, 3000), (10.0, 10.002, 1e-6, 2000)]:
+        parts_x.append(cx + s * rng.standard_normal(k))
+        parts_y.append(cy + s * rng.standard_normal(k))
+    parts_x += [np.array([1e6, -1e6, np.nan, 3.0]), np.full(500, 77.0)]
+    parts_y += [np.array([1e6, -1e6, 1.0, np.inf]), np.full(500, -12.5)]
+    nx, ny = np.concatenate(parts_x), np.concatenate(parts_y)
+    qx = np.concatenate([10.0 + 2e-3 * rng.standard_normal(300), rng.uniform(-500, 500, 300), [5e6, -3e5, 77.0, 0.0]])
+    qy = np.concatenate([10.0 + 2e-3 * rng.standard_normal(300), rng.uniform(-500, 500, 300), [-5e6, 1e5, -12.5, 0.0]])
+    ctx.tree_upload(nx, ny)
+    oidx, od2 = O.nn_brute(nx, ny, qx, qy)
+    for flags in (NN_DEFAULT, NN_GRID, NN_SCAN):
+        idx, d2 = ctx.nn(qx, qy, flags=flags)
+        assert np.array_equal(idx, oidx) and np.array_equal(d2, od2), flags
+    # appending invalidates the grid; the next default call rebuilds it on the device
+    ctx.tree_append(qx[:50] + 1e-4, qy[:50], np.zeros(50), np.zeros(50, dtype=np.int32))
+    nx2, ny2 = np.concatenate([nx, qx[:50] + 1e-4]), np.concatenate([ny, qy[:50]])
+    idx = ctx.nn(qx, qy, want_d2=False)
+    assert np.array_equal(idx, O.nn_brute(nx2, ny2, qx, qy)[0])
+    one = ctx.nn(qx[:3], qy[:3], want_d2=False)  # few queries on a current grid: grid path again
+    assert np.array_equal(one, idx[:3])
 
 
 def test_nn_nonfinite(ctx, O):
@@ -71,14 +98,14 @@ def test_nn_nonfinite(ctx, O):
     qx = np.array([0.9, np.nan, 100.0])
     qy = np.array([0.9, 0.0, 100.0])
     ctx.tree_upload(nx, ny)
-    for flags in (NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED):
+    for flags in (NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED, NN_SCAN):
         idx = ctx.nn(np.tile(qx, 40), np.tile(qy, 40), flags=flags, want_d2=False)  # > 64 queries: scan kernels
         assert np.array_equal(idx, np.tile(O.nn_brute(nx, ny, qx, qy)[0], 40)), flags
         idx = ctx.nn(qx, qy, flags=flags, want_d2=False)
         assert np.array_equal(idx, O.nn_brute(nx, ny, qx, qy)[0]), flags
 
 
-@pytest.mark.parametrize("flags", [DEFAULT, NO_CULL, USE_GRID, UNSORTED])
+@pytest.mark.parametrize("flags", [DEFAULT, NO_CULL, USE_GRID, UNSORTED, SCAN])
 def test_collide_segments_random_world(ctx, O, pp, flags):
     bounds, rings = pp.synth.circle_world(300, world=100.0, rmin=1.0, rmax=3.0)
     ctx.obstacles_upload(bounds, rings)
@@ -86,7 +113,7 @@ def test_collide_segments_random_world(ctx, O, pp, flags):
     m = 20_000 if flags != NO_CULL else 4000
     rng = np.random.default_rng(5)
     ax, ay = rng.uniform(-2, 102, m), rng.uniform(-2, 102, m)
-    ln = rng.choice([0.3, 2.0, 15.0], m)
+    ln = rng.choice([0.3, 2.0, 15.0, 60.0], m)  # 60: boxes that cover more grid cells than there are rings
     th = rng.uniform(-math.pi, math.pi, m)
     bx, by = ax + ln * np.cos(th), ay + ln * np.sin(th)
     ok = ctx.collide_segments(ax, ay, bx, by, flags=flags)
@@ -104,7 +131,7 @@ def test_collide_segments_bench_world_and_boundary_cases(ctx, O, pp):
     ay = np.array([-5.0, 0.0, 0.0, ry[0], ry[2], 6.0, 6.0, -5.0, 14.0, 3.9, 15.0, 0.0, 6.0])
     bx = np.array([-4.0, -5.0, 14.0, rx[0], rx[3], 3.1, 12.0, -5.0, 14.5, 5.0, 0.0, 0.0, 3.0 + 1e-13])
     by = np.array([-4.0, 0.0, 0.0, ry[0], ry[3], 6.1, 6.0, -5.0, 14.5, 4.1, 14.0, 0.0, 6.0])
-    for flags in (DEFAULT, NO_CULL, USE_GRID, UNSORTED):
+    for flags in (DEFAULT, NO_CULL, USE_GRID, UNSORTED, SCAN):
         ok = ctx.collide_segments(ax, ay, bx, by, flags=flags)
         assert np.array_equal(ok, W.verify_segments(ax, ay, bx, by)), flags
     # degenerate segments (a == b) and points exactly on the bounds ring are not contained
@@ -129,7 +156,7 @@ def test_collide_transit_fixture(ctx, O):
     ln = rng.choice([0.1, 3.0, 30.0], m)
     bx, by = ax + ln * np.cos(th), ay + ln * np.sin(th)
     want = W.verify_segments(ax, ay, bx, by)
-    for flags in (DEFAULT, USE_GRID, UNSORTED):
+    for flags in (DEFAULT, USE_GRID, UNSORTED, SCAN):
         assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=flags), want), flags
     assert 0 < want.sum() < m
     # start -> goal as one straight line, and as the reference's start/goal poses
@@ -179,7 +206,7 @@ def test_extend_step(ctx, O, pp):
     oidx, _ = O.nn_brute(nx, ny, qx, qy)
     want = W.verify_segments(qx, qy, nx[oidx], ny[oidx])
     wyaw = np.arctan2(ny[oidx] - qy, nx[oidx] - qx)
-    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_PLAIN, DEFAULT)]:
+    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_PLAIN, DEFAULT), (NN_SCAN, SCAN)]:
         idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=nnf, collide_flags=cf)
         assert np.array_equal(idx, oidx) and np.array_equal(ok, want)
         assert np.abs(yaw - wyaw).max() < 1e-12
@@ -280,7 +307,7 @@ def test_extend_step_with_dubins_edges(ctx, O, pp):
     wyaw = np.array([O.compute_yaw(qx[i], qy[i], nx[oidx[i]], ny[oidx[i]]) for i in range(qx.size)])
     W = O.OracleWorld(bounds, rings)
     want = W.verify_dubins_edges(qx, qy, wyaw, nx[oidx], ny[oidx], nyaw[oidx], 0.8, 0.1)
-    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, DEFAULT)]:
+    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, DEFAULT), (NN_SCAN, DEFAULT)]:
         idx, yaw, ok = ctx.rrt_extend_dubins(qx, qy, 0.8, 0.1, nn_flags=nnf, collide_flags=cf)
         assert np.array_equal(idx, oidx)
         assert np.abs(yaw - wyaw).max() < 1e-12
