@@ -32,8 +32,12 @@ int pp_build_bucket_perm(pp_ctx *ctx, size_t m, const double *kx, const double *
 // ---- Polygon::contains(&Point) for the bounds ring ------------------------------------------------
 __device__ __forceinline__ bool pp_bounds_contains(const pp_world_view &w, double x, double y) {
     const double fx = (x - w.bminx) * w.binvx, fy = (y - w.bminy) * w.binvy;
-    if (!(fx >= 0.0 && fx < (double)w.bgx && fy >= 0.0 && fy < (double)w.bgy)) return false;  // also NaN
-    const uint8_t cls = __ldg(w.bcls + (size_t)(int)fy * w.bgx + (int)fx);
+    // floor-convert (saturating) and range-check as integers: -0.3 -> -1, +-inf -> INT_MIN / INT_MAX all fail the
+    // unsigned compare.  NaN converts to cell (0, 0), a corner of the padded box and therefore never class 1; its
+    // class-2 exact test is false for NaN as well.
+    const int ix = __double2int_rd(fx), iy = __double2int_rd(fy);
+    if ((unsigned)ix >= (unsigned)w.bgx || (unsigned)iy >= (unsigned)w.bgy) return false;
+    const uint8_t cls = __ldg(w.bcls + (size_t)iy * w.bgx + ix);
     if (cls != 2) return cls == 1;
     return pp_point_position(w.bx, w.by, w.nb, x, y) == 1;
 }
@@ -46,10 +50,81 @@ __device__ __forceinline__ bool pp_outside_padded(const pp_ring_meta &m, double 
 }
 
 __device__ __forceinline__ int pp_cell_clamp(double f, int g) {
-    // f may be NaN/inf: comparisons first, conversion only for in-range values
-    if (!(f > 0.0)) return 0;
-    if (f >= (double)g) return g - 1;
-    return (int)f;
+    // f may be NaN / inf: the floor conversion saturates (NaN -> 0), the clamp runs on the integer pipe
+    return min(max(__double2int_rd(f), 0), g - 1);
+}
+
+// ---- warp-cooperative narrow phase: all 32 lanes call with IDENTICAL arguments, lane l takes ring segment l
+// (+32, +64, ...).  Per (ring segment, line segment) pair the arithmetic is that of geo_predicates.cuh, so the
+// answers are the same bits; what changes is that a ring's ~10-20 segments are tested in one pass instead of a
+// serial loop executed by the one lane that found the candidate.
+__device__ __forceinline__ bool pp_ring_hits_segment_warp(const double *__restrict__ rx, const double *__restrict__ ry,
+                                                          uint32_t n, double b0x, double b0y, double b1x, double b1y,
+                                                          int lane) {
+    const double b_dx = b1x - b0x, b_dy = b1y - b0y;
+    for (uint32_t base = 0; base + 1 < n; base += 32) {
+        const uint32_t i = base + lane;
+        bool hit = false;
+        if (i + 1 < n) {
+            const double a0x = rx[i], a0y = ry[i];
+            const double a_dx = rx[i + 1] - a0x, a_dy = ry[i + 1] - a0y;
+            const double u_b = b_dy * a_dx - b_dx * a_dy;
+            if (u_b != 0.0) {
+                const double ua_t = b_dx * (a0y - b0y) - b_dy * (a0x - b0x);
+                const double ub_t = a_dx * (a0y - b0y) - a_dy * (a0x - b0x);
+                const double u_a = ua_t / u_b;
+                const double u_b2 = ub_t / u_b;
+                hit = (0.0 <= u_a && u_a <= 1.0 && 0.0 <= u_b2 && u_b2 <= 1.0);
+            }
+        }
+        if (__ballot_sync(0xffffffffu, hit) != 0u) return true;
+    }
+    return false;
+}
+
+// get_position(ring, p) == Inside, cooperatively: a vertex or segment that holds the point makes it OnBoundary
+// (pp_ring_has_point), otherwise the parity of the crossing count decides (pp_point_position); the `xints` carried
+// between iterations in geo's loop is only read for segments with y0 != y1, which also write it, so every
+// segment's contribution is independent of the others.
+__device__ __forceinline__ bool pp_point_inside_ring_warp(const double *__restrict__ rx, const double *__restrict__ ry,
+                                                          uint32_t n, double px, double py, int lane) {
+    if (n < 2) return false;
+    uint32_t crossings = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        bool on = false, cross = false;
+        if (i < n) {
+            const double x0 = rx[i], y0 = ry[i];
+            on = (x0 == px && y0 == py);
+            if (i + 1 < n) {
+                const double x1 = rx[i + 1], y1 = ry[i + 1];
+                const double dx = x1 - x0, dy = y1 - y0;
+                if (dx == 0.0 && dy == 0.0) {
+                    // the vertex test above already covers it
+                } else if (dy == 0.0) {
+                    const double t = (px - x0) / dx;
+                    on = on || (py == y0 && 0.0 <= t && t <= 1.0);
+                } else if (dx == 0.0) {
+                    const double t = (py - y0) / dy;
+                    on = on || (px == x0 && 0.0 <= t && t <= 1.0);
+                } else {
+                    const double tx = (px - x0) / dx;
+                    const double ty = (py - y0) / dy;
+                    on = on || (fabs(tx - ty) <= PP_F64_EPSILON && 0.0 <= tx && tx <= 1.0);
+                }
+                const double ymin = (y0 < y1) ? y0 : y1, ymax = (y0 > y1) ? y0 : y1;
+                const double xmax = (x0 > x1) ? x0 : x1;
+                if (py > ymin && py <= ymax && px <= xmax) {
+                    // y0 != y1 here (py > ymin && py <= ymax)
+                    const double xints = (py - y0) * (x1 - x0) / (y1 - y0) + x0;
+                    cross = (x0 == x1 || px <= xints);
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, on) != 0u) return false;
+        crossings += (uint32_t)__popc(__ballot_sync(0xffffffffu, cross));
+    }
+    return (crossings & 1u) != 0u;
 }
 
 // ---- any obstacle polygon contains the point? ------------------------------------------------------
@@ -434,12 +509,118 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             const bool own_vertex = have && (lane < 31 || k + 1 == np);
             const bool own_segment = (lane < 31) && (k + 1 < np);
             bool fail = false;
-            if (own_vertex) fail = !pp_bounds_contains(w, x, y) || pp_vertex_in_obstacle<CULL>(w, x, y);
-            if (!fail && own_segment) fail = pp_segment_hits_obstacle<CULL, !DUBINS>(w, x, y, xn, yn);
+            if (!CULL) {  // exhaustive per-lane loops (PP_COLLIDE_NO_CULL)
+                if (own_vertex) fail = !pp_bounds_contains(w, x, y) || pp_vertex_in_obstacle<false>(w, x, y);
+                if (!fail && own_segment) fail = pp_segment_hits_obstacle<false>(w, x, y, xn, yn);
+                if (__ballot_sync(0xffffffffu, fail) != 0u) {
+                    bad = true;
+                    break;
+                }
+                continue;
+            }
+            if (own_vertex) fail = !pp_bounds_contains(w, x, y);
             if (__ballot_sync(0xffffffffu, fail) != 0u) {
                 bad = true;
                 break;
             }
+            // Broad phase per lane, narrow phase per warp.  A lane walks the grid cells under the box of its
+            // segment (of its vertex, for the last point) and stops at the first ring whose outward-rounded fp32
+            // box meets it; the warp then takes the pending (lane, ring) candidates one by one, broadcasts the
+            // lane's segment and runs the exact predicates with one ring segment per lane.  A ring that contains
+            // vertex k has a padded box that contains it, hence meets the segment's box: one walk serves both the
+            // vertex test and the segment test.
+            const uint32_t seg_mask = __ballot_sync(0xffffffffu, own_segment);
+            // Cell range of the box: floor is monotonic, so the cells of the box's corners are the min / max of the
+            // two end points' cells -- each lane converts its own point once (saturating floor, NaN -> 0), takes the
+            // neighbour's cell by shuffle, and everything else is integer arithmetic (f64 min / max cost ~13
+            // instructions apiece on this part: no DMNMX).
+            const int ix = __double2int_rd((x - w.gminx) * w.ginv), iy = __double2int_rd((y - w.gminy) * w.ginv);
+            const int ixn = __shfl_down_sync(0xffffffffu, ix, 1), iyn = __shfl_down_sync(0xffffffffu, iy, 1);
+            int cx0 = own_segment ? min(ix, ixn) : ix, cx1 = own_segment ? max(ix, ixn) : ix;
+            int cy = own_segment ? min(iy, iyn) : iy, cy1 = own_segment ? max(iy, iyn) : iy;
+            bool more = own_vertex && w.n_rings != 0u && !(cx1 < 0 || cy1 < 0 || cx0 >= w.gx || cy >= w.gy);
+            cx0 = max(cx0, 0);
+            cx1 = min(cx1, w.gx - 1);
+            cy = max(cy, 0);
+            cy1 = min(cy1, w.gy - 1);
+            int cx = cx0 - 1;
+            if (more) {
+                // rings registered under the box's cells, row by row (a row's cells are contiguous in the CSR
+                // array): in free space the sum is zero for every lane and the chunk is done after one vote
+                uint32_t cnt = 0;
+                for (int r = cy; r <= cy1; ++r) {
+                    const uint32_t *row = w.cell_start + (size_t)r * w.gx;
+                    cnt += __ldg(row + cx1 + 1) - __ldg(row + cx0);
+                }
+                more = cnt != 0u;
+            }
+            if (__ballot_sync(0xffffffffu, more) == 0u) continue;
+            // some lane has rings to look at: its box, rounded outward to fp32, for the per-ring overlap test
+            const double xe = own_segment ? xn : x, ye = own_segment ? yn : y;
+            const bool swx = xe < x, swy = ye < y;
+            const float q32x0 = __double2float_rd(swx ? xe : x), q32x1 = __double2float_ru(swx ? x : xe);
+            const float q32y0 = __double2float_rd(swy ? ye : y), q32y1 = __double2float_ru(swy ? y : ye);
+            uint32_t kcur = 0, kend = 0;
+            // user-supplied polylines may hold segments whose box covers more cells than there are rings: walk
+            // the ring list instead (bounds the cost per segment by O(rings)); Dubins samples are a step apart
+            bool linear = false;
+            if (!DUBINS && more &&
+                (unsigned long long)(cx1 - cx0 + 1) * (unsigned long long)(cy1 - cy + 1) > (unsigned long long)w.n_rings + 64ull) {
+                linear = true;
+                kend = w.n_rings;
+                cx = cx1;
+                cy = cy1;
+            }
+            for (;;) {
+                uint32_t ring = 0xFFFFFFFFu;
+                while (more) {
+                    if (kcur < kend) {
+                        const uint32_t r = linear ? kcur : __ldg(w.cell_items + kcur);
+                        ++kcur;
+                        const float4 bb = __ldg(w.aabb32 + r);
+                        if (!(q32x1 < bb.x || q32x0 > bb.z || q32y1 < bb.y || q32y0 > bb.w)) {
+                            ring = r;
+                            break;
+                        }
+                    } else {
+                        if (++cx > cx1) {
+                            cx = cx0;
+                            ++cy;
+                        }
+                        if (cy > cy1) {
+                            more = false;
+                            break;
+                        }
+                        const size_t c = (size_t)cy * w.gx + cx;
+                        kcur = __ldg(w.cell_start + c);
+                        kend = __ldg(w.cell_start + c + 1);
+                    }
+                }
+                uint32_t pend = __ballot_sync(0xffffffffu, ring != 0xFFFFFFFFu);
+                if (pend == 0u) break;
+                do {
+                    const int src = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    const uint32_t rr = __shfl_sync(0xffffffffu, ring, src);
+                    const double ax0 = __shfl_sync(0xffffffffu, x, src), ay0 = __shfl_sync(0xffffffffu, y, src);
+                    const pp_ring_meta mt = w.meta[rr];
+                    const double *rx = w.ox + mt.first, *ry = w.oy + mt.first;
+                    bool hit = false;
+                    if ((seg_mask >> src) & 1u) {
+                        const double ax1 = __shfl_sync(0xffffffffu, xn, src), ay1 = __shfl_sync(0xffffffffu, yn, src);
+                        // the f64 padded-box rule of the per-lane path decides whether the pair is tested at all
+                        const bool sx = ax1 < ax0, sy = ay1 < ay0;
+                        if (!((sx ? ax0 : ax1) < mt.minx - mt.pad || (sx ? ax1 : ax0) > mt.maxx + mt.pad ||
+                              (sy ? ay0 : ay1) < mt.miny - mt.pad || (sy ? ay1 : ay0) > mt.maxy + mt.pad))
+                            hit = pp_ring_hits_segment_warp(rx, ry, mt.count, ax0, ay0, ax1, ay1, lane);
+                    }
+                    if (!hit && !pp_outside_padded(mt, ax0, ay0))
+                        hit = pp_point_inside_ring_warp(rx, ry, mt.count, ax0, ay0, lane);
+                    if (hit) bad = true;
+                } while (pend != 0u && !bad);
+                if (bad) break;
+            }
+            if (bad) break;
         }
         if (lane == 0) ok[line] = bad ? 0 : 1;
     }
