@@ -72,9 +72,7 @@ __device__ __forceinline__ bool pp_ring_hits_segment_warp(const double *__restri
             if (u_b != 0.0) {
                 const double ua_t = b_dx * (a0y - b0y) - b_dy * (a0x - b0x);
                 const double ub_t = a_dx * (a0y - b0y) - a_dy * (a0x - b0x);
-                const double u_a = ua_t / u_b;
-                const double u_b2 = ub_t / u_b;
-                hit = (0.0 <= u_a && u_a <= 1.0 && 0.0 <= u_b2 && u_b2 <= 1.0);
+                hit = pp_quot_in01(ua_t, u_b) && pp_quot_in01(ub_t, u_b);
             }
         }
         if (__ballot_sync(0xffffffffu, hit) != 0u) return true;
@@ -102,15 +100,13 @@ __device__ __forceinline__ bool pp_point_inside_ring_warp(const double *__restri
                 if (dx == 0.0 && dy == 0.0) {
                     // the vertex test above already covers it
                 } else if (dy == 0.0) {
-                    const double t = (px - x0) / dx;
-                    on = on || (py == y0 && 0.0 <= t && t <= 1.0);
+                    on = on || (py == y0 && pp_quot_in01(px - x0, dx));
                 } else if (dx == 0.0) {
-                    const double t = (py - y0) / dy;
-                    on = on || (px == x0 && 0.0 <= t && t <= 1.0);
+                    on = on || (px == x0 && pp_quot_in01(py - y0, dy));
                 } else {
-                    const double tx = (px - x0) / dx;
-                    const double ty = (py - y0) / dy;
-                    on = on || (fabs(tx - ty) <= PP_F64_EPSILON && 0.0 <= tx && tx <= 1.0);
+                    const double nx = px - x0, ny = py - y0;
+                    if (pp_quot_in01(nx, dx) && fabs(ny) <= 2.0 * fabs(dy))  // see pp_ring_has_point
+                        on = on || (fabs(nx / dx - ny / dy) <= PP_F64_EPSILON);
                 }
                 const double ymin = (y0 < y1) ? y0 : y1, ymax = (y0 > y1) ? y0 : y1;
                 const double xmax = (x0 > x1) ? x0 : x1;

@@ -19,6 +19,22 @@
 
 #define PP_F64_EPSILON 2.220446049250313e-16
 
+// 0.0 <= a / b && a / b <= 1.0 for the correctly rounded IEEE quotient (b != 0), without the division.
+//   * a == 0: the quotient is +-0 and passes both tests.
+//   * equal signs: the quotient is positive, and RN(|a| / |b|) <= 1 iff |a| <= |b| -- if |a| > |b| then
+//     |a| >= |b| + ulp(|b|) > |b| (1 + 2^-53), which rounds to 1 + 2^-52 or more.
+//   * opposite signs: the quotient is negative and fails, unless it underflows to -0 (which passes `0.0 <= q`).
+// Operands outside [2^-900, 2^100] in magnitude (where underflow / overflow of the quotient is conceivable) and
+// non-finite ones take the division itself; world-scale coordinates never get there.
+PP_HD bool pp_quot_in01(double a, double b) {
+    const double aa = fabs(a), ab = fabs(b);
+    if (!(aa >= 0x1p-900 && aa <= 0x1p+100 && ab >= 0x1p-900 && ab <= 0x1p+100)) {
+        const double q = a / b;
+        return 0.0 <= q && q <= 1.0;
+    }
+    return ((a < 0.0) == (b < 0.0)) && aa <= ab;
+}
+
 // `impl Contains<Point> for LineString`: vertex equality, then the per-segment tx/ty test
 PP_HD bool pp_ring_has_point(const double *rx, const double *ry, uint32_t n, double px, double py) {
     if (n == 0) return false;
@@ -32,15 +48,19 @@ PP_HD bool pp_ring_has_point(const double *rx, const double *ry, uint32_t n, dou
         if (dx == 0.0 && dy == 0.0) {
             hit = (px == x0 && py == y0);
         } else if (dy == 0.0) {
-            const double t = (px - x0) / dx;
-            hit = (py == y0 && 0.0 <= t && t <= 1.0);
+            hit = (py == y0 && pp_quot_in01(px - x0, dx));
         } else if (dx == 0.0) {
-            const double t = (py - y0) / dy;
-            hit = (px == x0 && 0.0 <= t && t <= 1.0);
+            hit = (px == x0 && pp_quot_in01(py - y0, dy));
         } else {
-            const double tx = (px - x0) / dx;
-            const double ty = (py - y0) / dy;
-            hit = (fabs(tx - ty) <= PP_F64_EPSILON && 0.0 <= tx && tx <= 1.0);
+            // tx in [0, 1] is decided without dividing; |tx - ty| <= eps then needs ty in [-eps, 1 + eps], hence
+            // |py - y0| <= 2 |dy|: only points next to the segment pay for the two quotients
+            const double nx = px - x0, ny = py - y0;
+            hit = false;
+            if (pp_quot_in01(nx, dx) && fabs(ny) <= 2.0 * fabs(dy)) {
+                const double tx = nx / dx;
+                const double ty = ny / dy;
+                hit = (fabs(tx - ty) <= PP_F64_EPSILON);
+            }
         }
         if (hit) return true;
     }
@@ -76,9 +96,8 @@ PP_HD bool pp_ring_hits_segment(const double *rx, const double *ry, uint32_t n, 
         if (u_b == 0.0) continue;
         const double ua_t = b_dx * (a0y - b0y) - b_dy * (a0x - b0x);
         const double ub_t = a_dx * (a0y - b0y) - a_dy * (a0x - b0x);
-        const double u_a = ua_t / u_b;
-        const double u_b2 = ub_t / u_b;
-        if (0.0 <= u_a && u_a <= 1.0 && 0.0 <= u_b2 && u_b2 <= 1.0) return true;
+        // u_a = ua_t / u_b and u_b2 = ub_t / u_b are only compared with 0 and 1 (pp_quot_in01: same answers)
+        if (pp_quot_in01(ua_t, u_b) && pp_quot_in01(ub_t, u_b)) return true;
     }
     return false;
 }
