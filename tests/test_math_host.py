@@ -18,6 +18,18 @@ def test_math_kernels_accuracy(tmp_path):
     assert v["batch_mismatch"] == 0 and v["special_bad"] == 0, v
 
 
+def test_division_free_predicates_are_exact(tmp_path):
+    """geo_predicates.cuh decides geo's `0 <= a/b <= 1` tests without dividing (pp_quot_in01): same answers as the IEEE
+    quotient on random, near-equal, tiny / huge / zero / non-finite operands, and the ring predicates built on it agree
+    with a restatement that performs every division (tools/predicate_check.cpp)"""
+    exe = str(tmp_path / "predicate_check")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off",
+                    os.path.join(ROOT, "tools", "predicate_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe, "2000000"], capture_output=True, text=True, check=True).stdout
+    v = {k: int(x) for k, x in (ln.split() for ln in out.strip().splitlines())}
+    assert v == {"bad_random": 0, "bad_close": 0, "bad_special": 0, "bad_ring": 0}, v
+
+
 def test_tables_are_reproducible(tmp_path):
     """the committed coefficient tables are what tools/gen_math_tables.py generates"""
     import shutil
