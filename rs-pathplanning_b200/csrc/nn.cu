@@ -701,54 +701,91 @@ __global__ void __launch_bounds__(256)
     if (i < n) atomicAdd(&hist1[pp_nn_grid_cell(x[i], y[i], gminx, gminy, ginv, gx, gy)], 1u);
 }
 
-// single block, in place: v[i] <- v[0] + ... + v[i]; 16 values per thread and round (16 384 per round), and a
-// copy of the exclusive prefix into cursor[] (the scatter's running slot per cell)
+// In-place inclusive scan v[i] <- v[0] + ... + v[i] plus a copy of the exclusive prefix in cursor[] (the scatter's
+// running slot per cell), in three small launches: every block scans its own 16 384 values (16 per thread) and
+// records its total, one block scans the <= 1 024 totals, and the offsets are added back.  (A single block looping
+// over all cells took 0.70 ms for the 5.2e5 cells of a 2^20-node tree: 32 rounds of strided accesses and barriers.)
 #define PP_GRID_SCAN_VPT 16
+#define PP_GRID_SCAN_BLOCK (1024 * PP_GRID_SCAN_VPT)
 __global__ void __launch_bounds__(1024)
-    pp_nn_grid_scan_kernel(uint32_t *__restrict__ v, uint32_t nb, uint32_t *__restrict__ cursor) {
+    pp_nn_grid_scan_local_kernel(uint32_t *__restrict__ v, uint32_t nb, uint32_t *__restrict__ cursor,
+                                 uint32_t *__restrict__ block_sums) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < nb; base += 1024 * PP_GRID_SCAN_VPT) {
-        const uint32_t first = base + threadIdx.x * PP_GRID_SCAN_VPT;
-        uint32_t a[PP_GRID_SCAN_VPT];
-        uint32_t sum = 0;
+    const uint32_t first = blockIdx.x * PP_GRID_SCAN_BLOCK + threadIdx.x * PP_GRID_SCAN_VPT;
+    uint32_t a[PP_GRID_SCAN_VPT];
+    uint32_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < PP_GRID_SCAN_VPT; ++k) {
-            a[k] = (first + k < nb) ? v[first + k] : 0u;
-            sum += a[k];
-        }
-        uint32_t inc = sum;
+    for (int k = 0; k < PP_GRID_SCAN_VPT; ++k) {
+        a[k] = (first + k < nb) ? v[first + k] : 0u;
+        sum += a[k];
+    }
+    uint32_t inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t winc = w;
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
         }
-        if (lane == 31) warp_sums[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = warp_sums[lane];
-            uint32_t winc = w;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            warp_sums[lane] = winc - w;
-        }
-        __syncthreads();
-        uint32_t run = carry + warp_sums[warp] + inc - sum;  // exclusive prefix of this thread's first value
+        warp_sums[lane] = winc - w;
+        if (lane == 31) block_sums[blockIdx.x] = winc;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + inc - sum;  // exclusive prefix of this thread's first value inside the block
 #pragma unroll
-        for (int k = 0; k < PP_GRID_SCAN_VPT; ++k) {
-            if (first + k < nb) {
-                cursor[first + k] = run;
-                run += a[k];
-                v[first + k] = run;
-            }
+    for (int k = 0; k < PP_GRID_SCAN_VPT; ++k) {
+        if (first + k < nb) {
+            cursor[first + k] = run;
+            run += a[k];
+            v[first + k] = run;
         }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = run;
-        __syncthreads();
+    }
+}
+
+// exclusive scan of the <= 1 024 block totals, in place
+__global__ void __launch_bounds__(1024) pp_nn_grid_scan_sums_kernel(uint32_t *__restrict__ block_sums, uint32_t nblk) {
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t val = (threadIdx.x < nblk) ? block_sums[threadIdx.x] : 0u;
+    uint32_t inc = val;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_sums[lane] = winc - w;
+    }
+    __syncthreads();
+    if (threadIdx.x < nblk) block_sums[threadIdx.x] = warp_sums[warp] + inc - val;
+}
+
+__global__ void __launch_bounds__(1024)
+    pp_nn_grid_scan_add_kernel(uint32_t *__restrict__ v, uint32_t nb, uint32_t *__restrict__ cursor,
+                               const uint32_t *__restrict__ block_offsets) {
+    const uint32_t off = block_offsets[blockIdx.x];
+    if (off == 0u) return;
+    const uint32_t first = blockIdx.x * PP_GRID_SCAN_BLOCK + threadIdx.x * PP_GRID_SCAN_VPT;
+#pragma unroll
+    for (int k = 0; k < PP_GRID_SCAN_VPT; ++k) {
+        if (first + k < nb) {
+            v[first + k] += off;
+            cursor[first + k] += off;
+        }
     }
 }
 
@@ -766,12 +803,13 @@ int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
     const size_t n = t.n;
     // geometry: ~2 nodes per cell, square cells over the bounding box of the finite nodes
     long g = (long)floor(sqrt((double)(n > 1 ? n : 1) / 2.0));
-    g = g < 1 ? 1 : (g > 4096 ? 4096 : g);
+    g = g < 1 ? 1 : (g > 4095 ? 4095 : g);  // (g + 1)^2 cells <= 1 024 scan blocks
     const size_t max_cells = (size_t)(g + 1) * (size_t)(g + 1);
-    int rc = pp_scratch_reserve(ctx, 64 + max_cells * 4);
+    int rc = pp_scratch_reserve(ctx, 64 + 4096 + max_cells * 4);
     if (rc) return rc;
     unsigned long long *mm = (unsigned long long *)ctx->scratch;
-    uint32_t *cursor = (uint32_t *)((char *)ctx->scratch + 64);
+    uint32_t *block_sums = (uint32_t *)((char *)ctx->scratch + 64);  // <= 1 024 scan blocks (g <= 4096)
+    uint32_t *cursor = block_sums + 1024;
     if (max_cells + 1 > t.cell_cap) {
         PP_CUDA(ctx, cudaStreamSynchronize(stream));
         cudaFree(t.cell_start);
@@ -796,7 +834,7 @@ int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
         }
         t.item_cap = cap;
     }
-    pp_launch_scope scope(ctx, "nn_grid_build", 4);
+    pp_launch_scope scope(ctx, "nn_grid_build", 6);
     const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
     unsigned long long got[4] = {~0ull, 0ull, ~0ull, 0ull};
     if (n) {
@@ -832,7 +870,10 @@ int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
     if (n) {
         const unsigned g1 = (unsigned)((n + 255) / 256);
         pp_nn_grid_count_kernel<<<g1, 256, 0, stream>>>(t.x, t.y, (uint32_t)n, minx, miny, inv, gx, gy, t.cell_start + 1);
-        pp_nn_grid_scan_kernel<<<1, 1024, 0, stream>>>(t.cell_start + 1, ncell, cursor);
+        const unsigned nblk = (ncell + PP_GRID_SCAN_BLOCK - 1) / PP_GRID_SCAN_BLOCK;  // <= 1 024 + 1
+        pp_nn_grid_scan_local_kernel<<<nblk, 1024, 0, stream>>>(t.cell_start + 1, ncell, cursor, block_sums);
+        pp_nn_grid_scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nblk);
+        pp_nn_grid_scan_add_kernel<<<nblk, 1024, 0, stream>>>(t.cell_start + 1, ncell, cursor, block_sums);
         pp_nn_grid_scatter_kernel<<<g1, 256, 0, stream>>>(t.x, t.y, (uint32_t)n, minx, miny, inv, gx, gy, cursor,
                                                           t.cell_items);
     }
