@@ -170,6 +170,7 @@ static void pp_tree_free(pp_tree_dev &t) {
     cudaFree(t.x32);
     cudaFree(t.cell_start);
     cudaFree(t.cell_items);
+    cudaFree(t.cell_xy);
     t = pp_tree_dev();
 }
 static void pp_world_free(pp_world_dev &w) {

@@ -236,48 +236,64 @@ __global__ void __launch_bounds__(PP_NN_WIDE_THREADS)
 
 // ---------------------------------------------------------------------------------------------
 // uniform grid (built by pp_tree_build_grid in api.cu): cell c holds node ids
-// cell_items[cell_start[c] .. cell_start[c+1]) in ascending order.
+// cell_items[cell_start[c] .. cell_start[c+1]) (any order) with their coordinates in cell_xy[] at the same positions.
 // Search: rings of cells of Chebyshev radius r = 0, 1, ... around the query's (clamped) cell; every
 // node in a cell at Chebyshev distance >= r is farther than (r-1)*cell from the query, so the search
 // stops once best < ((r-1)*cell*(1-2^-30))^2.  Same d2 arithmetic, ties to the lowest index.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-    pp_nn_grid_kernel(const double *__restrict__ nx, const double *__restrict__ ny, uint32_t n_nodes,
-                      const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_items, int gx, int gy,
-                      double gminx, double gminy, double gcell, double ginv, const double *__restrict__ qx,
-                      const double *__restrict__ qy, size_t m, uint32_t *__restrict__ idx_out,
-                      double *__restrict__ d2_out) {
+    pp_nn_grid_kernel(uint32_t n_nodes, const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_items,
+                      const double2 *__restrict__ cell_xy, int gx, int gy, double gminx, double gminy, double gcell,
+                      double ginv, const double *__restrict__ qx, const double *__restrict__ qy, size_t m,
+                      uint32_t *__restrict__ idx_out, double *__restrict__ d2_out) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const double x = qx[j], y = qy[j];
     double best = CUDART_INF;
     uint32_t bi = 0xFFFFFFFFu;
+    // candidates k0 <= k < k1 of the cell-sorted arrays: same d2 arithmetic as the scans, (d2, id) lexicographic
+    // minimum; the id is fetched only when a candidate ties or improves
+    auto scan = [&](uint32_t k0, uint32_t k1) {
+        for (uint32_t k = k0; k < k1; ++k) {
+            const double2 p = __ldg(cell_xy + k);
+            const double dx = p.x - x, dy = p.y - y;
+            const double v = dx * dx + dy * dy;
+            if (v <= best) {
+                const uint32_t i = __ldg(cell_items + k);
+                if (v < best || i < bi) {
+                    best = v;
+                    bi = i;
+                }
+            }
+        }
+    };
     if (n_nodes > 0) {
         double fx = floor((x - gminx) * ginv), fy = floor((y - gminy) * ginv);
         int cx = (fx >= (double)gx) ? gx - 1 : ((fx > 0.0) ? (int)fx : 0);  // NaN -> 0
         int cy = (fy >= (double)gy) ? gy - 1 : ((fy > 0.0) ? (int)fy : 0);
+        // rings 0 and 1 together: the 3 x 3 block is three runs of the cell-sorted arrays (a row of cells is
+        // contiguous), i.e. six offset loads instead of eighteen
+        {
+            const int xa = max(cx - 1, 0), xb = min(cx + 1, gx - 1);
+            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gy - 1); ++yy) {
+                const uint32_t *row = cell_start + (size_t)yy * gx;
+                scan(__ldg(row + xa), __ldg(row + xb + 1));
+            }
+        }
         const int maxr = max(gx, gy);
-        for (int r = 0; r <= maxr; ++r) {
-            if (r >= 2 && bi != 0xFFFFFFFFu) {
+        for (int r = 2; r <= maxr; ++r) {
+            if (bi != 0xFFFFFFFFu) {
                 double lim = (double)(r - 1) * gcell * (1.0 - 0x1p-30);
                 if (best < lim * lim) break;
             }
             const int y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
             for (int yy = max(y0, 0); yy <= min(y1, gy - 1); ++yy) {
-                const bool edge_row = (yy == y0) || (yy == y1);
-                const int xstep = edge_row ? 1 : max(x1 - x0, 1);
-                for (int xx = x0; xx <= x1; xx += xstep) {
-                    if (xx < 0 || xx >= gx) continue;
-                    const uint32_t c0 = cell_start[(size_t)yy * gx + xx], c1 = cell_start[(size_t)yy * gx + xx + 1];
-                    for (uint32_t k = c0; k < c1; ++k) {
-                        const uint32_t i = cell_items[k];
-                        double dx = __ldg(nx + i) - x, dy = __ldg(ny + i) - y;
-                        double v = dx * dx + dy * dy;
-                        if (v < best || (v == best && i < bi)) {
-                            best = v;
-                            bi = i;
-                        }
-                    }
+                const uint32_t *row = cell_start + (size_t)yy * gx;
+                if (yy == y0 || yy == y1) {  // full row of the ring: one run
+                    scan(__ldg(row + max(x0, 0)), __ldg(row + min(x1, gx - 1) + 1));
+                } else {  // the two end cells
+                    if (x0 >= 0) scan(__ldg(row + x0), __ldg(row + x0 + 1));
+                    if (x1 < gx) scan(__ldg(row + x1), __ldg(row + x1 + 1));
                 }
             }
         }
@@ -600,7 +616,7 @@ int pp_launch_nn(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint
     const uint32_t n_nodes = (uint32_t)t.n;
     if (flags & PP_NN_GRID) {
         pp_launch_scope scope(ctx, "nn_grid");
-        pp_nn_grid_kernel<<<(unsigned)((m + 127) / 128), 128, 0, stream>>>(t.x, t.y, n_nodes, t.cell_start, t.cell_items,
+        pp_nn_grid_kernel<<<(unsigned)((m + 127) / 128), 128, 0, stream>>>(n_nodes, t.cell_start, t.cell_items, t.cell_xy,
                                                                           t.gx, t.gy, t.gminx, t.gminy, t.gcell, t.ginv,
                                                                           qx, qy, m, idx, d2);
         PP_CUDA(ctx, cudaGetLastError());
@@ -792,9 +808,14 @@ __global__ void __launch_bounds__(1024)
 __global__ void __launch_bounds__(256)
     pp_nn_grid_scatter_kernel(const double *__restrict__ x, const double *__restrict__ y, uint32_t n, double gminx,
                               double gminy, double ginv, int gx, int gy, uint32_t *__restrict__ cursor,
-                              uint32_t *__restrict__ items) {
+                              uint32_t *__restrict__ items, double2 *__restrict__ items_xy) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i < n) items[atomicAdd(&cursor[pp_nn_grid_cell(x[i], y[i], gminx, gminy, ginv, gx, gy)], 1u)] = i;
+    if (i < n) {
+        const double xi = x[i], yi = y[i];
+        const uint32_t pos = atomicAdd(&cursor[pp_nn_grid_cell(xi, yi, gminx, gminy, ginv, gx, gy)], 1u);
+        items[pos] = i;
+        items_xy[pos] = make_double2(xi, yi);  // the search reads coordinates cell by cell, ids only on improvement
+    }
 }
 
 int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
@@ -825,10 +846,12 @@ int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
     if ((n > 1 ? n : 1) > t.item_cap) {
         PP_CUDA(ctx, cudaStreamSynchronize(stream));
         cudaFree(t.cell_items);
+        cudaFree(t.cell_xy);
         t.cell_items = nullptr;
+        t.cell_xy = nullptr;
         t.item_cap = 0;
         const size_t cap = t.cap > n ? t.cap : (n > 1 ? n : 1);  // grows with the node arrays
-        if (cudaMalloc(&t.cell_items, cap * 4) != cudaSuccess) {
+        if (cudaMalloc(&t.cell_items, cap * 4) != cudaSuccess || cudaMalloc(&t.cell_xy, cap * sizeof(double2)) != cudaSuccess) {
             cudaGetLastError();
             return pp_fail(ctx, PP_ERR_NOMEM, "nn grid allocation failed");
         }
@@ -875,7 +898,7 @@ int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
         pp_nn_grid_scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nblk);
         pp_nn_grid_scan_add_kernel<<<nblk, 1024, 0, stream>>>(t.cell_start + 1, ncell, cursor, block_sums);
         pp_nn_grid_scatter_kernel<<<g1, 256, 0, stream>>>(t.x, t.y, (uint32_t)n, minx, miny, inv, gx, gy, cursor,
-                                                          t.cell_items);
+                                                          t.cell_items, t.cell_xy);
     }
     PP_CUDA(ctx, cudaGetLastError());
     t.gx = gx;

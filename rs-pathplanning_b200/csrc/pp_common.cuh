@@ -27,7 +27,8 @@ struct pp_tree_dev {
     int gx = 0, gy = 0;
     double gminx = 0, gminy = 0, gcell = 1, ginv = 1;
     uint32_t *cell_start = nullptr;  // gx*gy+1
-    uint32_t *cell_items = nullptr;  // n, ascending node index inside each cell
+    uint32_t *cell_items = nullptr;  // n node ids, cell by cell (any order inside a cell)
+    double2 *cell_xy = nullptr;      // (x, y) of cell_items[k]: a row of cells is one contiguous run of coordinates
     size_t cell_cap = 0, item_cap = 0;
 };
 
