@@ -22,7 +22,7 @@
  *     internal mutex, matching the `&self` + rayon use at src/rrt.rs:600-609).
  *   - numeric contract: NN indices and straight-edge verify flags are bit-exact with
  *     the oracle (non-fused f64, lowest index on ties); Dubins costs / samples agree
- *     to 1e-9 relative (CUDA libm differs from glibc by <= 2 ulp).
+ *     to 1e-9 relative (the kernels' own f64 sincos / atan2 / acos are within 1.5 ulp of glibc's).
  */
 #ifndef PATHPLANNING_B200_H
 #define PATHPLANNING_B200_H

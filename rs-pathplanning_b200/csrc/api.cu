@@ -384,6 +384,9 @@ int pp_dubins_eval_dev(pp_ctx *ctx, size_t n, const double *sx, const double *sy
 // host pointers: the batch is cut into chunks that rotate over three streams so that the H2D copy of
 // chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (both PCIe directions busy).
 // With pinned buffers (pp_host_alloc) the copies are truly asynchronous.
+#ifndef PP_EVAL_CHUNK_LOG2
+#define PP_EVAL_CHUNK_LOG2 20  // pairs per pipelined chunk of the host-pointer entry (8 MB per input array)
+#endif
 int pp_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw, const double *ex,
                    const double *ey, const double *eyaw, const double *radius_arr, double radius, double *cost,
                    uint8_t *word, double *tpq) {
@@ -391,7 +394,7 @@ int pp_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, co
     if (!radius_arr && !pp_pos_finite(radius)) return PP_ERR_INVALID;
     if (n == 0) return PP_OK;
     pp_guard g(ctx);
-    const size_t chunk = std::min(n, (size_t)1 << 20);
+    const size_t chunk = std::min(n, (size_t)1 << PP_EVAL_CHUNK_LOG2);
     const int n_in = radius_arr ? 7 : 6;
     const size_t per_slot = chunk * (8 * (size_t)n_in + 8 + 8 /*word, padded*/ + (tpq ? 24 : 0));
     int rc = pp_scratch_reserve(ctx, per_slot * 3 + 4096);
