@@ -20,9 +20,7 @@ template <bool WANT_TPQ>
 __device__ __forceinline__ void pp_eval_one(double sx, double sy, double syaw, double ex, double ey, double eyaw,
                                             double c, size_t i, double *__restrict__ cost,
                                             uint8_t *__restrict__ word, double *__restrict__ tpq) {
-    double lex, ley, leyaw, ss, cs;
-    pp_dubins_to_local(sx, sy, syaw, ex, ey, eyaw, &lex, &ley, &leyaw, &ss, &cs);
-    pp_dubins_frame f = pp_dubins_frame_from_local(lex, ley, leyaw, c);
+    const pp_dubins_frame f = pp_dubins_frame_world(ex - sx, ey - sy, syaw, eyaw - syaw, c);
     pp_dubins_sol s = pp_dubins_solve<false>(f.alpha, f.beta, f.d, nullptr, nullptr);
     cost[i] = s.cost;
     word[i] = (uint8_t)s.word;
@@ -122,20 +120,16 @@ int pp_launch_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi
 __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, double syaw, double ex, double ey,
                                                        double eyaw, double radius, double step, int from_origin) {
     pp_dubins_plan pl;
-    double lex, ley, leyaw, ss, cs;
-    if (from_origin) {
-        lex = ex;
-        ley = ey;
-        leyaw = eyaw;
+    if (from_origin) {  // the goal is given in the start frame: start pose = origin
         pl.sx = pl.sy = pl.syaw = 0.0;
     } else {
         pl.sx = sx;
         pl.sy = sy;
         pl.syaw = syaw;
-        pp_dubins_to_local(pl.sx, pl.sy, pl.syaw, ex, ey, eyaw, &lex, &ley, &leyaw, &ss, &cs);
     }
     double c = 1.0 / radius;
-    pp_dubins_frame f = pp_dubins_frame_from_local(lex, ley, leyaw, c);
+    pp_dubins_frame f = from_origin ? pp_dubins_frame_world(ex, ey, 0.0, eyaw, c, true)
+                                    : pp_dubins_frame_world(ex - sx, ey - sy, syaw, eyaw - syaw, c);
     pp_dubins_sol s = pp_dubins_solve<false>(f.alpha, f.beta, f.d, nullptr, nullptr);
     pl.word = (uint8_t)s.word;
     pl.from_origin = (uint8_t)(from_origin != 0);

@@ -74,41 +74,43 @@ struct pp_dubins_frame {
     double alpha, beta, d;
 };
 
-// src/dubins.rs:333-338 : d, theta, alpha, beta from the goal in the start frame
-__device__ __forceinline__ pp_dubins_frame pp_dubins_frame_from_local(double lex, double ley, double leyaw,
-                                                                      double c) {
+// src/dubins.rs:402-408 + 333-338 : d, theta, alpha, beta of the goal as seen from the start pose.
+// The reference rotates the goal offset into the start frame (sincos(syaw)) and takes atan2 / hypot of the rotated
+// vector.  A rotation changes neither the norm nor -- up to the subtraction -- the polar angle:
+// theta = atan2(dy, dx) - syaw, which saves the sincos and the rotation (~30 FP64 instructions per pair; a few ulp
+// on theta, the class of difference the 1e-9 contract already covers).  Start yaws beyond +-64 rad (the subtraction
+// would lose digits that the reference's exact range reduction keeps) and coincident positions (atan2 of signed
+// zeros) take the reference's route.  Every kernel (evaluate, plan, scalar path) goes through this one function, so
+// they agree on the chosen word.
+// local_input: (dx, dy, leyaw) are already in the start frame (dubins_path_planning_from_origin, syaw = 0): the
+// reference does not rotate at all, so neither does this.
+__device__ __forceinline__ pp_dubins_frame pp_dubins_frame_world(double dx, double dy, double syaw, double leyaw,
+                                                                 double c, bool local_input = false) {
+    double ay_ = dy, ax_ = dx, sub = syaw;
+    if (!local_input && !(pp_abs_below_pow2(syaw, 6) && (dx != 0.0 || dy != 0.0))) {
+        double ss, cs;
+#ifdef PP_DUBINS_LIBM
+        sincos(syaw, &ss, &cs);
+#else
+        pp_sincos1(syaw, &ss, &cs);
+#endif
+        ax_ = cs * dx + ss * dy;
+        ay_ = -ss * dx + cs * dy;
+        sub = 0.0;
+    }
     pp_dubins_frame f;
 #ifdef PP_DUBINS_LIBM
-    f.d = hypot(lex, ley) * c;
-    double a = atan2(ley, lex);  // [-pi, pi]
+    f.d = hypot(ax_, ay_) * c;
+    const double a = atan2(ay_, ax_) - sub;
 #else
-    f.d = pp_sqrt_pos(fma(lex, lex, ley * ley)) * c;  // world-scale coordinates: no overflow guard needed (<= 1 ulp)
-    double a = pp_atan2(ley, lex);
+    f.d = pp_sqrt_pos(fma(ax_, ax_, ay_ * ay_)) * c;  // world-scale coordinates: no overflow guard needed (<= 1 ulp)
+    const double a = pp_atan2(ay_, ax_) - sub;
 #endif
-    // theta = mod2pi(a): floor(a/2pi) is -1 for a < 0, else 0 (and -0 -> +0)
-    double theta = (a < 0.0) ? (a + PP_TWO_PI) : (a + 0.0);
+    const double theta = pp_mod2pi(a);  // [0, 2pi]; for the rotated route a is in [-pi, pi] and -0 becomes +0
     // alpha = mod2pi(-theta), theta in [0, 2pi]: floor(-theta/2pi) is -1 unless theta == 0
     f.alpha = (theta > 0.0) ? (PP_TWO_PI - theta) : ((theta == 0.0) ? 0.0 : theta /*NaN*/);
     f.beta = pp_mod2pi(leyaw - theta);
     return f;
-}
-
-// src/dubins.rs:402-408
-__device__ __forceinline__ void pp_dubins_to_local(double sx, double sy, double syaw, double ex, double ey,
-                                                   double eyaw, double *lex, double *ley, double *leyaw,
-                                                   double *sin_s, double *cos_s) {
-    double ss, cs;
-#ifdef PP_DUBINS_LIBM
-    sincos(syaw, &ss, &cs);
-#else
-    pp_sincos1(syaw, &ss, &cs);
-#endif
-    double dx = ex - sx, dy = ey - sy;
-    *lex = cs * dx + ss * dy;
-    *ley = -ss * dx + cs * dy;
-    *leyaw = eyaw - syaw;
-    *sin_s = ss;
-    *cos_s = cs;
 }
 
 // the six words (src/dubins.rs:27-153) + the selection fold (src/dubins.rs:347-363).
