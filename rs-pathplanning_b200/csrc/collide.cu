@@ -563,12 +563,21 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
          line += warps_total) {
         uint32_t np;      // points of this polyline
         uint32_t base = 0;
-        pp_dubins_plan pl;
-        pp_seg_origin o[3];
-        double ss = 0.0, cs = 1.0, gx_unused, pex = 0.0, pey = 0.0;
+        // The plan record and the three segment origins are warp-uniform and indexed by a run-time segment
+        // number: ONE copy per warp in shared memory.  (As per-thread arrays they lived in local memory, 232 bytes
+        // replicated per lane: ncu showed 513 MB of DRAM writes per launch for a kernel that outputs 1 MB.)
+        __shared__ pp_dubins_plan s_plan[PP_POLY_THREADS / 32];
+        __shared__ pp_seg_origin s_origin[PP_POLY_THREADS / 32][3];
+        const pp_dubins_plan &pl = s_plan[threadIdx.x >> 5];
+        pp_seg_origin *o = s_origin[threadIdx.x >> 5];
+        double ss = 0.0, cs = 1.0, pex = 0.0, pey = 0.0;
         uint32_t nsamp = 0;
         if (DUBINS) {
-            pl = dub.plans[line];
+            __syncwarp();  // every lane is done with the previous polyline's record
+            if (lane < (int)(sizeof(pp_dubins_plan) / 4))
+                reinterpret_cast<uint32_t *>(&s_plan[threadIdx.x >> 5])[lane] =
+                    __ldg(reinterpret_cast<const uint32_t *>(dub.plans + line) + lane);
+            __syncwarp();
             pex = dub.ex[line];
             pey = dub.ey[line];
             if (pl.count == 0xFFFFFFFFu) {  // replay overflow: the reference would run out of memory; report blocked
@@ -579,8 +588,16 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 nsamp = 1;  // fallback [(sx, sy)] of src/rrt.rs:313
             } else {
                 nsamp = pl.count;
-                pp_segment_origins(pl, o, &gx_unused);
+                pp_seg_origin o_reg[3];
+                double gx_unused;
+                pp_segment_origins(pl, o_reg, &gx_unused);
+                if (lane == 0) {  // (constant indices keep o_reg in registers)
+                    o[0] = o_reg[0];
+                    o[1] = o_reg[1];
+                    o[2] = o_reg[2];
+                }
                 pp_sincos1(pl.syaw, &ss, &cs);
+                __syncwarp();
             }
             np = nsamp + 1;
         } else {
