@@ -292,7 +292,10 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
 // ring segment per lane.  The serial per-lane form ran the predicates at 2.6 active lanes per instruction.
 // An edge whose box covers more cells than there are rings walks the ring list instead (cost bounded by O(rings)).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PP_SEG_THREADS)
+#ifndef PP_SEGGRID_MIN_BLOCKS
+#define PP_SEGGRID_MIN_BLOCKS 6  // 80 registers: 0.186 ms per 2^20 C4 edges (0.211 at 90 registers, 0.189 at 64)
+#endif
+__global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
     pp_collide_segments_grid_kernel(pp_world_view w, size_t m, const double *__restrict__ ax,
                                     const double *__restrict__ ay, const double *__restrict__ bx,
                                     const double *__restrict__ by, const uint32_t *__restrict__ gather_idx,
