@@ -29,8 +29,8 @@ import __graft_entry__ as graft  # noqa: E402
 N_PAIRS = 1 << 24          # C3, per GPU
 W_INSTR_PER_PAIR = 1100.0  # fixed yard-stick of SURVEY.md Appendix D (FP64-pipe thread-instructions per pair)
 BYTES_PER_PAIR = 57.0      # 48 B read + 8 B cost + 1 B word
-NCU_FP64_INSTR_PER_PAIR = 515.0  # DFMA + DADD + DMUL + DSETP executed per pair (ncu source page, same capture)
-NCU_DRAM_BYTES_PER_LAUNCH = 949.1e6  # measured once per kernel change by ncu (see profiles/r01_summary.md)
+NCU_FP64_INSTR_PER_PAIR = 490.0  # DFMA + DADD + DMUL + DSETP executed per pair (ncu source page, same capture)
+NCU_DRAM_BYTES_PER_LAUNCH = 949.3e6  # measured once per kernel change by ncu (see profiles/r01_summary.md)
 FP64_PEAK_NOMINAL = 148 * 64 * 1.965e9  # lanes * clock: used only if the live DFMA measurement fails
 C4_M, C4_NODES, C4_RINGS = 1 << 20, 1 << 20, 10_000
 C5_EDGES, C5_RINGS = 1 << 19, 100_000  # the per-GPU slice of config 5 (2^22 edges over 8 GPUs)
@@ -310,10 +310,10 @@ def run_own(args):
                 "kernel": "pp_dubins_eval_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e9,
                 "unit": "Ginstr/s", "frac": achieved * 1e9 / fp64_peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, dram__bytes_read.sum + "
-                "dram__bytes_write.sum per launch of 2^24 pairs (profiles/r01_dubins_eval_final2_raw.csv); algorithmic 956.3e6",
-                "fp64_pipe_busy_ncu": 0.732, "fp64_instr_per_pair_ncu": NCU_FP64_INSTR_PER_PAIR,
+                "dram__bytes_write.sum per launch of 2^24 pairs (profiles/r01_dubins_eval_final4_raw.csv); algorithmic 956.3e6",
+                "fp64_pipe_busy_ncu": 0.728, "fp64_instr_per_pair_ncu": NCU_FP64_INSTR_PER_PAIR,
                 # `frac` follows the contract (SURVEY 8d yard-stick W = 1100 per pair) and exceeds 1 because the
-                # kernel executes only ~515 FP64-pipe instructions per pair (ncu source page); with the executed count the same
+                # kernel executes only ~490 FP64-pipe instructions per pair (ncu source page); with the executed count the same
                 # timing gives the pipe utilisation ncu reports
                 "frac_of_executed_fp64_work": pairs_per_s_kernel * NCU_FP64_INSTR_PER_PAIR / fp64_peak,
                 "per_unit": f"W = {W_INSTR_PER_PAIR:.0f} FP64-pipe thread-instructions per pair (fixed yard-stick, SURVEY App. D)",
