@@ -54,18 +54,23 @@ __device__ __forceinline__ int pp_cell_clamp(double f, int g) {
     return min(max(__double2int_rd(f), 0), g - 1);
 }
 
-// ---- warp-cooperative narrow phase: all 32 lanes call with IDENTICAL arguments, lane l takes ring segment l
-// (+32, +64, ...).  Per (ring segment, line segment) pair the arithmetic is that of geo_predicates.cuh, so the
-// answers are the same bits; what changes is that a ring's ~10-20 segments are tested in one pass instead of a
-// serial loop executed by the one lane that found the candidate.
-__device__ __forceinline__ bool pp_ring_hits_segment_warp(const double *__restrict__ rx, const double *__restrict__ ry,
-                                                          uint32_t n, double b0x, double b0y, double b1x, double b1y,
-                                                          int lane) {
+// ---- warp-cooperative narrow phase.  The warp is split into four groups of eight lanes; a group works on one
+// pending (line segment, ring) candidate and its lane `sub` takes ring segments sub, sub + 8, ...: the rings of
+// this domain have 4-20 segments, so whole-warp passes would leave three quarters of the lanes idle.  All 32
+// lanes call together (the ballots are warp-wide); a group without a candidate passes n = 0.  Per (ring segment,
+// line segment) pair the arithmetic is that of geo_predicates.cuh, so the answers are the same bits; what changes
+// is that a ring's segments are tested side by side instead of in a serial loop on the lane that found the ring.
+__device__ __forceinline__ bool pp_ring_hits_segment_g8(const double *__restrict__ rx, const double *__restrict__ ry,
+                                                        uint32_t n, double b0x, double b0y, double b1x, double b1y,
+                                                        int sub, unsigned gmask) {
     const double b_dx = b1x - b0x, b_dy = b1y - b0y;
-    for (uint32_t base = 0; base + 1 < n; base += 32) {
-        const uint32_t i = base + lane;
+    bool res = false;
+    for (uint32_t base = 0;; base += 8) {
+        const bool work = base + 1 < n;  // uniform inside a group
+        if (__ballot_sync(0xffffffffu, work) == 0u) break;
+        const uint32_t i = base + (uint32_t)sub;
         bool hit = false;
-        if (i + 1 < n) {
+        if (work && i + 1 < n) {
             const double a0x = rx[i], a0y = ry[i];
             const double a_dx = rx[i + 1] - a0x, a_dy = ry[i + 1] - a0y;
             const double u_b = b_dy * a_dx - b_dx * a_dy;
@@ -75,23 +80,29 @@ __device__ __forceinline__ bool pp_ring_hits_segment_warp(const double *__restri
                 hit = pp_quot_in01(ua_t, u_b) && pp_quot_in01(ub_t, u_b);
             }
         }
-        if (__ballot_sync(0xffffffffu, hit) != 0u) return true;
+        if ((__ballot_sync(0xffffffffu, hit) & gmask) != 0u) {
+            res = true;
+            n = 0;  // this group is done; the others may go on
+        }
     }
-    return false;
+    return res;
 }
 
-// get_position(ring, p) == Inside, cooperatively: a vertex or segment that holds the point makes it OnBoundary
+// get_position(ring, p) == Inside per group: a vertex or segment that holds the point makes it OnBoundary
 // (pp_ring_has_point), otherwise the parity of the crossing count decides (pp_point_position); the `xints` carried
 // between iterations in geo's loop is only read for segments with y0 != y1, which also write it, so every
 // segment's contribution is independent of the others.
-__device__ __forceinline__ bool pp_point_inside_ring_warp(const double *__restrict__ rx, const double *__restrict__ ry,
-                                                          uint32_t n, double px, double py, int lane) {
-    if (n < 2) return false;
+__device__ __forceinline__ bool pp_point_inside_ring_g8(const double *__restrict__ rx, const double *__restrict__ ry,
+                                                        uint32_t n, double px, double py, int sub, unsigned gmask) {
+    if (n < 2) n = 0;  // a ring of one point is never `Inside`
     uint32_t crossings = 0;
-    for (uint32_t base = 0; base < n; base += 32) {
-        const uint32_t i = base + lane;
+    bool boundary = false;
+    for (uint32_t base = 0;; base += 8) {
+        const bool work = base < n;
+        if (__ballot_sync(0xffffffffu, work) == 0u) break;
+        const uint32_t i = base + (uint32_t)sub;
         bool on = false, cross = false;
-        if (i < n) {
+        if (work && i < n) {
             const double x0 = rx[i], y0 = ry[i];
             on = (x0 == px && y0 == py);
             if (i + 1 < n) {
@@ -117,10 +128,25 @@ __device__ __forceinline__ bool pp_point_inside_ring_warp(const double *__restri
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, on) != 0u) return false;
-        crossings += (uint32_t)__popc(__ballot_sync(0xffffffffu, cross));
+        if ((__ballot_sync(0xffffffffu, on) & gmask) != 0u) {
+            boundary = true;
+            n = 0;
+        }
+        crossings += (uint32_t)__popc(__ballot_sync(0xffffffffu, cross) & gmask);
     }
-    return (crossings & 1u) != 0u;
+    return !boundary && (crossings & 1u) != 0u;
+}
+
+// the group's candidate: the (grp)-th lowest set bit of `pend` (or -1), and `pend` without its four lowest bits
+__device__ __forceinline__ int pp_take_candidates(unsigned &pend, int grp) {
+    int mine = -1;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int s = pend ? __ffs(pend) - 1 : -1;
+        pend &= pend - 1;  // 0 stays 0
+        if (g == grp) mine = s;
+    }
+    return mine;
 }
 
 // ---- any obstacle polygon contains the point? ------------------------------------------------------
@@ -380,22 +406,37 @@ __global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
             uint32_t pend = __ballot_sync(0xffffffffu, ring != 0xFFFFFFFFu);
             if (pend == 0u) break;
             do {
-                const int src = __ffs(pend) - 1;
-                pend &= pend - 1;
-                const uint32_t rr = __shfl_sync(0xffffffffu, ring, src);
-                const double ex0 = __shfl_sync(0xffffffffu, x0, src), ey0 = __shfl_sync(0xffffffffu, y0, src);
-                const double ex1 = __shfl_sync(0xffffffffu, x1, src), ey1 = __shfl_sync(0xffffffffu, y1, src);
-                const pp_ring_meta mt = w.meta[rr];
+                const int grp = lane >> 3, sub = lane & 7;
+                const unsigned gmask = 0xFFu << (grp * 8);
+                const int src = pp_take_candidates(pend, grp);
+                const bool act = src >= 0;
+                const int sl = act ? src : 0;
+                const uint32_t rr = __shfl_sync(0xffffffffu, ring, sl);
+                const double ex0 = __shfl_sync(0xffffffffu, x0, sl), ey0 = __shfl_sync(0xffffffffu, y0, sl);
+                const double ex1 = __shfl_sync(0xffffffffu, x1, sl), ey1 = __shfl_sync(0xffffffffu, y1, sl);
+                pp_ring_meta mt;
+                mt.minx = mt.miny = mt.maxx = mt.maxy = mt.pad = 0.0;
+                mt.first = mt.count = 0u;
+                if (act) mt = w.meta[rr];
                 const double *rx = w.ox + mt.first, *ry = w.oy + mt.first;
-                bool h = false;
                 // the f64 padded-box rule of the per-lane path decides whether the pair is tested at all
                 const bool sx = ex1 < ex0, sy = ey1 < ey0;
-                if (!((sx ? ex0 : ex1) < mt.minx - mt.pad || (sx ? ex1 : ex0) > mt.maxx + mt.pad ||
-                      (sy ? ey0 : ey1) < mt.miny - mt.pad || (sy ? ey1 : ey0) > mt.maxy + mt.pad))
-                    h = pp_ring_hits_segment_warp(rx, ry, mt.count, ex0, ey0, ex1, ey1, lane);
-                if (!h && !pp_outside_padded(mt, ex0, ey0)) h = pp_point_inside_ring_warp(rx, ry, mt.count, ex0, ey0, lane);
-                if (!h && !pp_outside_padded(mt, ex1, ey1)) h = pp_point_inside_ring_warp(rx, ry, mt.count, ex1, ey1, lane);
-                if (h && lane == src) {
+                const bool do_seg = act && !((sx ? ex0 : ex1) < mt.minx - mt.pad || (sx ? ex1 : ex0) > mt.maxx + mt.pad ||
+                                             (sy ? ey0 : ey1) < mt.miny - mt.pad || (sy ? ey1 : ey0) > mt.maxy + mt.pad);
+                bool h = pp_ring_hits_segment_g8(rx, ry, do_seg ? mt.count : 0u, ex0, ey0, ex1, ey1, sub, gmask);
+                const bool do_v0 = act && !h && !pp_outside_padded(mt, ex0, ey0);
+                h = pp_point_inside_ring_g8(rx, ry, do_v0 ? mt.count : 0u, ex0, ey0, sub, gmask) || h;
+                const bool do_v1 = act && !h && !pp_outside_padded(mt, ex1, ey1);
+                h = pp_point_inside_ring_g8(rx, ry, do_v1 ? mt.count : 0u, ex1, ey1, sub, gmask) || h;
+                // the verdict belongs to the lane the candidate came from
+                const unsigned hb = __ballot_sync(0xffffffffu, h && sub == 0);
+                bool mine = false;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int sg = __shfl_sync(0xffffffffu, src, g * 8);
+                    if (((hb >> (g * 8)) & 1u) && sg == lane) mine = true;
+                }
+                if (mine) {
                     hit = true;
                     more = false;  // decided: stop walking
                 }
@@ -730,24 +771,28 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 uint32_t pend = __ballot_sync(0xffffffffu, ring != 0xFFFFFFFFu);
                 if (pend == 0u) break;
                 do {
-                    const int src = __ffs(pend) - 1;
-                    pend &= pend - 1;
-                    const uint32_t rr = __shfl_sync(0xffffffffu, ring, src);
-                    const double ax0 = __shfl_sync(0xffffffffu, x, src), ay0 = __shfl_sync(0xffffffffu, y, src);
-                    const pp_ring_meta mt = w.meta[rr];
+                    const int grp = lane >> 3, sub = lane & 7;
+                    const unsigned gmask = 0xFFu << (grp * 8);
+                    const int src = pp_take_candidates(pend, grp);
+                    const bool act = src >= 0;
+                    const int sl = act ? src : 0;
+                    const uint32_t rr = __shfl_sync(0xffffffffu, ring, sl);
+                    const double ax0 = __shfl_sync(0xffffffffu, x, sl), ay0 = __shfl_sync(0xffffffffu, y, sl);
+                    const double ax1 = __shfl_sync(0xffffffffu, xn, sl), ay1 = __shfl_sync(0xffffffffu, yn, sl);
+                    pp_ring_meta mt;
+                    mt.minx = mt.miny = mt.maxx = mt.maxy = mt.pad = 0.0;
+                    mt.first = mt.count = 0u;
+                    if (act) mt = w.meta[rr];
                     const double *rx = w.ox + mt.first, *ry = w.oy + mt.first;
-                    bool hit = false;
-                    if ((seg_mask >> src) & 1u) {
-                        const double ax1 = __shfl_sync(0xffffffffu, xn, src), ay1 = __shfl_sync(0xffffffffu, yn, src);
-                        // the f64 padded-box rule of the per-lane path decides whether the pair is tested at all
-                        const bool sx = ax1 < ax0, sy = ay1 < ay0;
-                        if (!((sx ? ax0 : ax1) < mt.minx - mt.pad || (sx ? ax1 : ax0) > mt.maxx + mt.pad ||
-                              (sy ? ay0 : ay1) < mt.miny - mt.pad || (sy ? ay1 : ay0) > mt.maxy + mt.pad))
-                            hit = pp_ring_hits_segment_warp(rx, ry, mt.count, ax0, ay0, ax1, ay1, lane);
-                    }
-                    if (!hit && !pp_outside_padded(mt, ax0, ay0))
-                        hit = pp_point_inside_ring_warp(rx, ry, mt.count, ax0, ay0, lane);
-                    if (hit) bad = true;
+                    // the f64 padded-box rule of the per-lane path decides whether the pair is tested at all
+                    const bool sx = ax1 < ax0, sy = ay1 < ay0;
+                    const bool do_seg = act && ((seg_mask >> sl) & 1u) &&
+                                        !((sx ? ax0 : ax1) < mt.minx - mt.pad || (sx ? ax1 : ax0) > mt.maxx + mt.pad ||
+                                          (sy ? ay0 : ay1) < mt.miny - mt.pad || (sy ? ay1 : ay0) > mt.maxy + mt.pad);
+                    bool hit = pp_ring_hits_segment_g8(rx, ry, do_seg ? mt.count : 0u, ax0, ay0, ax1, ay1, sub, gmask);
+                    const bool do_vtx = act && !hit && !pp_outside_padded(mt, ax0, ay0);
+                    hit = pp_point_inside_ring_g8(rx, ry, do_vtx ? mt.count : 0u, ax0, ay0, sub, gmask) || hit;
+                    if (__ballot_sync(0xffffffffu, hit) != 0u) bad = true;
                 } while (pend != 0u && !bad);
                 if (bad) break;
             }
