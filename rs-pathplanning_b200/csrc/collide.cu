@@ -116,7 +116,7 @@ __device__ __forceinline__ bool pp_point_inside_ring_g8(const double *__restrict
                     on = on || (px == x0 && pp_quot_in01(py - y0, dy));
                 } else {
                     const double nx = px - x0, ny = py - y0;
-                    if (pp_quot_in01(nx, dx) && fabs(ny) <= 2.0 * fabs(dy))  // see pp_ring_has_point
+                    if (pp_quot_in01(nx, dx) && pp_quot_near01(ny, dy))  // see pp_ring_has_point
                         on = on || (fabs(nx / dx - ny / dy) <= PP_F64_EPSILON);
                 }
                 const double ymin = (y0 < y1) ? y0 : y1, ymax = (y0 > y1) ? y0 : y1;
@@ -356,15 +356,13 @@ __global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
     cx1 = min(cx1, w.gx - 1);
     cy = max(cy, 0);
     cy1 = min(cy1, w.gy - 1);
-    int cx = cx0 - 1;
     uint32_t kcur = 0, kend = 0;
     bool linear = false;
     if (more) {
         if ((unsigned long long)(cx1 - cx0 + 1) * (unsigned long long)(cy1 - cy + 1) > (unsigned long long)w.n_rings + 64ull) {
             linear = true;
             kend = w.n_rings;
-            cx = cx1;
-            cy = cy1;
+            cy = cy1 + 1;
         } else {
             uint32_t cnt = 0;
             for (int r = cy; r <= cy1; ++r) {
@@ -389,18 +387,15 @@ __global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
                         ring = r;
                         break;
                     }
-                } else {
-                    if (++cx > cx1) {
-                        cx = cx0;
-                        ++cy;
-                    }
+                } else {  // next row of cells: one contiguous run of ids
                     if (cy > cy1) {
                         more = false;
                         break;
                     }
-                    const size_t c = (size_t)cy * w.gx + cx;
-                    kcur = __ldg(w.cell_start + c);
-                    kend = __ldg(w.cell_start + c + 1);
+                    const uint32_t *row = w.cell_start + (size_t)cy * w.gx;
+                    kcur = __ldg(row + cx0);
+                    kend = __ldg(row + cx1 + 1);
+                    ++cy;
                 }
             }
             uint32_t pend = __ballot_sync(0xffffffffu, ring != 0xFFFFFFFFu);
@@ -715,7 +710,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             cx1 = min(cx1, w.gx - 1);
             cy = max(cy, 0);
             cy1 = min(cy1, w.gy - 1);
-            int cx = cx0 - 1;
             if (more) {
                 // rings registered under the box's cells, row by row (a row's cells are contiguous in the CSR
                 // array): in free space the sum is zero for every lane and the chunk is done after one vote
@@ -740,9 +734,9 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 (unsigned long long)(cx1 - cx0 + 1) * (unsigned long long)(cy1 - cy + 1) > (unsigned long long)w.n_rings + 64ull) {
                 linear = true;
                 kend = w.n_rings;
-                cx = cx1;
-                cy = cy1;
+                cy = cy1 + 1;
             }
+            // the ids of a ROW of cells are one contiguous run of cell_items: the walk goes row by row
             for (;;) {
                 uint32_t ring = 0xFFFFFFFFu;
                 while (more) {
@@ -755,17 +749,14 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                             break;
                         }
                     } else {
-                        if (++cx > cx1) {
-                            cx = cx0;
-                            ++cy;
-                        }
                         if (cy > cy1) {
                             more = false;
                             break;
                         }
-                        const size_t c = (size_t)cy * w.gx + cx;
-                        kcur = __ldg(w.cell_start + c);
-                        kend = __ldg(w.cell_start + c + 1);
+                        const uint32_t *row = w.cell_start + (size_t)cy * w.gx;
+                        kcur = __ldg(row + cx0);
+                        kend = __ldg(row + cx1 + 1);
+                        ++cy;
                     }
                 }
                 uint32_t pend = __ballot_sync(0xffffffffu, ring != 0xFFFFFFFFu);

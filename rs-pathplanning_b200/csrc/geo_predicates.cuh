@@ -35,6 +35,13 @@ PP_HD bool pp_quot_in01(double a, double b) {
     return ((a < 0.0) == (b < 0.0)) && aa <= ab;
 }
 
+// Necessary for -eps <= RN(a / b) <= 1 + eps (eps = 2^-52): |a| at most a hair above |b|, and a negative quotient
+// only if it is tiny.  A cheap filter in front of the two divisions of the on-boundary test, never the decision.
+PP_HD bool pp_quot_near01(double a, double b) {
+    const double aa = fabs(a), ab = fabs(b);
+    return aa <= 1.0000001 * ab && (((a < 0.0) == (b < 0.0)) || aa <= 1e-15 * ab);
+}
+
 // `impl Contains<Point> for LineString`: vertex equality, then the per-segment tx/ty test
 PP_HD bool pp_ring_has_point(const double *rx, const double *ry, uint32_t n, double px, double py) {
     if (n == 0) return false;
@@ -52,11 +59,11 @@ PP_HD bool pp_ring_has_point(const double *rx, const double *ry, uint32_t n, dou
         } else if (dx == 0.0) {
             hit = (px == x0 && pp_quot_in01(py - y0, dy));
         } else {
-            // tx in [0, 1] is decided without dividing; |tx - ty| <= eps then needs ty in [-eps, 1 + eps], hence
-            // |py - y0| <= 2 |dy|: only points next to the segment pay for the two quotients
+            // tx in [0, 1] is decided without dividing; |tx - ty| <= eps then needs ty in [-eps, 1 + eps]
+            // (pp_quot_near01): only points inside the segment's box pay for the two quotients
             const double nx = px - x0, ny = py - y0;
             hit = false;
-            if (pp_quot_in01(nx, dx) && fabs(ny) <= 2.0 * fabs(dy)) {
+            if (pp_quot_in01(nx, dx) && pp_quot_near01(ny, dy)) {
                 const double tx = nx / dx;
                 const double ty = ny / dy;
                 hit = (fabs(tx - ty) <= PP_F64_EPSILON);
