@@ -17,7 +17,7 @@ int pp_launch_dubins_words(pp_ctx *, size_t, const double *, const double *, con
                            cudaStream_t);
 int pp_launch_mod2pi(pp_ctx *, size_t, const double *, double *, int, cudaStream_t);
 int pp_launch_dubins_plan(pp_ctx *, size_t, const double *, const double *, const double *, const double *,
-                          const double *, const double *, double, double, int, uint32_t *, void *, cudaStream_t);
+                          const double *, const double *, double, double, int, uint32_t *, void *, void *, cudaStream_t);
 int pp_launch_dubins_fill(pp_ctx *, size_t, const void *, const uint64_t *, double *, cudaStream_t);
 int pp_launch_dubins_path(pp_ctx *, double, double, double, double, double, double, double, double, int, uint32_t, void *,
                           double *, cudaStream_t);
@@ -34,8 +34,8 @@ int pp_launch_collide_segments(pp_ctx *, size_t, const double *, const double *,
                                const uint32_t *, double *, uint8_t *, int, cudaStream_t);
 int pp_launch_verify_polylines(pp_ctx *, size_t, const double *, const double *, const uint32_t *, uint8_t *, int,
                                cudaStream_t);
-int pp_launch_collide_dubins(pp_ctx *, size_t, const void *, const double *, const double *, uint8_t *, int,
-                             cudaStream_t);
+int pp_launch_collide_dubins(pp_ctx *, size_t, const void *, const void *, const double *, const double *, uint8_t *,
+                             int, cudaStream_t);
 int pp_launch_fp64_peak(pp_ctx *, int, double *, cudaStream_t, unsigned *, unsigned *);
 int pp_launch_extend_gather(pp_ctx *, size_t, const double *, const double *, const uint32_t *, double *, double *,
                             double *, double *, cudaStream_t);
@@ -432,7 +432,7 @@ int pp_dubins_sample_count_dev(pp_ctx *ctx, size_t n, const double *sx, const do
     if (n && !from_origin && (!sx || !sy || !syaw)) return PP_ERR_INVALID;
     if (!pp_pos_finite(radius) || !pp_pos_finite(step)) return PP_ERR_INVALID;
     pp_guard g(ctx);
-    return pp_launch_dubins_plan(ctx, n, sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin, counts, plan,
+    return pp_launch_dubins_plan(ctx, n, sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin, counts, plan, nullptr,
                                  ctx->stream);
 }
 
@@ -457,7 +457,7 @@ int pp_dubins_sample_count(pp_ctx *ctx, size_t n, const double *sx, const double
             PP_CUDA(ctx, cudaMemsetAsync(d + k * n, 0, n * 8, s));
     }
     int rc = pp_launch_dubins_plan(ctx, n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n, radius, step,
-                                   from_origin, dcnt.as<uint32_t>(), plan ? dplan.p : nullptr, s);
+                                   from_origin, dcnt.as<uint32_t>(), plan ? dplan.p : nullptr, nullptr, s);
     if (rc) return rc;
     PP_CUDA(ctx, cudaMemcpyAsync(counts, dcnt.p, n * 4, cudaMemcpyDeviceToHost, s));
     if (plan) PP_CUDA(ctx, cudaMemcpyAsync(plan, dplan.p, n * PP_DUBINS_PLAN_BYTES, cudaMemcpyDeviceToHost, s));
@@ -1063,9 +1063,11 @@ static int pp_collide_dubins_impl(pp_ctx *ctx, size_t m, const double *sx, const
     // pass 1: plan records (evaluate + replay of the sampling loop); pass 2: generate-and-test per warp
     PP_TMP(ctx, dcnt, s, m * 4);
     PP_TMP(ctx, dplan, s, m * PP_DUBINS_PLAN_BYTES);
-    int rc = pp_launch_dubins_plan(ctx, m, sx, sy, syaw, ex, ey, eyaw, radius, step, 0, dcnt.as<uint32_t>(), dplan.p, s);
+    PP_TMP(ctx, daux, s, m * 136);  // pp_plan_aux: segment origins + sincos(syaw), computed once per path by pass 1
+    int rc = pp_launch_dubins_plan(ctx, m, sx, sy, syaw, ex, ey, eyaw, radius, step, 0, dcnt.as<uint32_t>(), dplan.p,
+                                   daux.p, s);
     if (rc) return rc;
-    return pp_launch_collide_dubins(ctx, m, dplan.p, ex, ey, ok, flags, s);
+    return pp_launch_collide_dubins(ctx, m, dplan.p, daux.p, ex, ey, ok, flags, s);
 }
 
 int pp_collide_dubins_dev(pp_ctx *ctx, size_t m, const double *sx, const double *sy, const double *syaw,

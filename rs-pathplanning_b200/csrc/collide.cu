@@ -584,6 +584,7 @@ struct pp_points_csr {
 
 struct pp_points_dubins {
     const pp_dubins_plan *plans;
+    const pp_plan_aux *aux;  // segment origins + sincos(syaw) per path, written by the plan kernel
     const double *ex, *ey;  // parent point appended after the samples
 };
 
@@ -606,9 +607,9 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
         // number: ONE copy per warp in shared memory.  (As per-thread arrays they lived in local memory, 232 bytes
         // replicated per lane: ncu showed 513 MB of DRAM writes per launch for a kernel that outputs 1 MB.)
         __shared__ pp_dubins_plan s_plan[PP_POLY_THREADS / 32];
-        __shared__ pp_seg_origin s_origin[PP_POLY_THREADS / 32][3];
+        __shared__ pp_plan_aux s_aux[PP_POLY_THREADS / 32];
         const pp_dubins_plan &pl = s_plan[threadIdx.x >> 5];
-        pp_seg_origin *o = s_origin[threadIdx.x >> 5];
+        const pp_seg_origin *o = s_aux[threadIdx.x >> 5].o;
         double ss = 0.0, cs = 1.0, pex = 0.0, pey = 0.0;
         uint32_t nsamp = 0;
         if (DUBINS) {
@@ -616,6 +617,9 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             if (lane < (int)(sizeof(pp_dubins_plan) / 4))
                 reinterpret_cast<uint32_t *>(&s_plan[threadIdx.x >> 5])[lane] =
                     __ldg(reinterpret_cast<const uint32_t *>(dub.plans + line) + lane);
+            if (lane < PP_PLAN_AUX_DOUBLES)
+                reinterpret_cast<double *>(&s_aux[threadIdx.x >> 5])[lane] =
+                    __ldg(reinterpret_cast<const double *>(dub.aux + line) + lane);
             __syncwarp();
             pex = dub.ex[line];
             pey = dub.ey[line];
@@ -627,16 +631,8 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 nsamp = 1;  // fallback [(sx, sy)] of src/rrt.rs:313
             } else {
                 nsamp = pl.count;
-                pp_seg_origin o_reg[3];
-                double gx_unused;
-                pp_segment_origins(pl, o_reg, &gx_unused);
-                if (lane == 0) {  // (constant indices keep o_reg in registers)
-                    o[0] = o_reg[0];
-                    o[1] = o_reg[1];
-                    o[2] = o_reg[2];
-                }
-                pp_sincos1(pl.syaw, &ss, &cs);
-                __syncwarp();
+                ss = s_aux[threadIdx.x >> 5].ss;
+                cs = s_aux[threadIdx.x >> 5].cs;
             }
             np = nsamp + 1;
         } else {
@@ -853,12 +849,12 @@ int pp_launch_verify_polylines(pp_ctx *ctx, size_t n_lines, const double *px, co
     return PP_OK;
 }
 
-int pp_launch_collide_dubins(pp_ctx *ctx, size_t m, const void *plans, const double *ex, const double *ey,
-                             uint8_t *ok, int flags, cudaStream_t stream) {
+int pp_launch_collide_dubins(pp_ctx *ctx, size_t m, const void *plans, const void *aux, const double *ex,
+                             const double *ey, uint8_t *ok, int flags, cudaStream_t stream) {
     if (m == 0) return PP_OK;
     pp_world_view w = pp_make_world_view(ctx->world);
     pp_points_csr csr{nullptr, nullptr, nullptr};
-    pp_points_dubins dub{(const pp_dubins_plan *)plans, ex, ey};
+    pp_points_dubins dub{(const pp_dubins_plan *)plans, (const pp_plan_aux *)aux, ex, ey};
     pp_launch_scope scope(ctx, "collide_dubins");
     if (flags & PP_COLLIDE_NO_CULL)
         pp_verify_polylines_kernel<false, true><<<pp_poly_grid(ctx, m), PP_POLY_THREADS, 0, stream>>>(w, m, csr, dub,

@@ -118,7 +118,8 @@ int pp_launch_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi
 
 // one path: evaluate + replay; (sx, sy, syaw) are ignored when from_origin
 __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, double syaw, double ex, double ey,
-                                                       double eyaw, double radius, double step, int from_origin) {
+                                                       double eyaw, double radius, double step, int from_origin,
+                                                       pp_plan_aux *aux = nullptr) {
     pp_dubins_plan pl;
     if (from_origin) {  // the goal is given in the start frame: start pose = origin
         pl.sx = pl.sy = pl.syaw = 0.0;
@@ -170,6 +171,11 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
             pp_seg_origin o[3];
             double gx;
             pp_segment_origins(pl, o, &gx);
+            if (aux) {
+                aux->o[0] = o[0];
+                aux->o[1] = o[1];
+                aux->o[2] = o[2];
+            }
             uint32_t cntout;
             if (gx != 0.0) {
                 cntout = N + 1;
@@ -187,6 +193,7 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
             pl.count = cntout;
         }
     }
+    if (aux) pp_sincos1(pl.syaw, &aux->ss, &aux->cs);
     return pl;
 }
 
@@ -194,14 +201,20 @@ __global__ void __launch_bounds__(128)
     pp_dubins_plan_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
                           const double *__restrict__ syaw, const double *__restrict__ ex,
                           const double *__restrict__ ey, const double *__restrict__ eyaw, double radius, double step,
-                          int from_origin, uint32_t *__restrict__ counts, pp_dubins_plan *__restrict__ plans) {
+                          int from_origin, uint32_t *__restrict__ counts, pp_dubins_plan *__restrict__ plans,
+                          pp_plan_aux *__restrict__ aux_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    pp_plan_aux aux;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) aux.o[k].ox = aux.o[k].oy = aux.o[k].oyaw = aux.o[k].so = aux.o[k].co = 0.0;
+    pp_plan_aux *ap = aux_out ? &aux : nullptr;
     const pp_dubins_plan pl = from_origin
-                                  ? pp_make_plan(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, 1)
-                                  : pp_make_plan(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0);
+                                  ? pp_make_plan(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, 1, ap)
+                                  : pp_make_plan(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0, ap);
     counts[i] = pl.count;
     if (plans) plans[i] = pl;
+    if (aux_out) aux_out[i] = aux;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,12 +299,12 @@ int pp_launch_dubins_path(pp_ctx *ctx, double sx, double sy, double syaw, double
 
 int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
                           const double *ex, const double *ey, const double *eyaw, double radius, double step,
-                          int from_origin, uint32_t *counts, void *plans, cudaStream_t stream) {
+                          int from_origin, uint32_t *counts, void *plans, void *aux, cudaStream_t stream) {
     if (n == 0) return PP_OK;
     pp_launch_scope scope(ctx, "dubins_plan");
     pp_dubins_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius, step,
-                                                                           from_origin, counts,
-                                                                           (pp_dubins_plan *)plans);
+                                                                           from_origin, counts, (pp_dubins_plan *)plans,
+                                                                           (pp_plan_aux *)aux);
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;
 }

@@ -420,6 +420,16 @@ struct pp_seg_origin {
     double ox, oy, oyaw, so, co;
 };
 
+// What the fused sample-and-verify kernel needs besides the plan record.  The plan kernel has it anyway (one
+// thread per path); recomputing it in the verify kernel costs every WARP four sincos and three interpolations per
+// path, ~340 warp-instructions of the ~1 900 a short extend-step edge takes.
+struct pp_plan_aux {
+    pp_seg_origin o[3];
+    double ss, cs;  // sincos(syaw): local -> world
+};
+#define PP_PLAN_AUX_DOUBLES 17
+static_assert(sizeof(pp_plan_aux) == PP_PLAN_AUX_DOUBLES * 8, "aux record is copied as doubles");
+
 // origins of the three segments: segment i starts at segment i-1's end point, written by
 // interpolate(ind, l) at src/dubins.rs:258-271 and read back at :230.
 __device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_seg_origin o[3], double *gx) {
