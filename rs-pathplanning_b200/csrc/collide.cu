@@ -49,11 +49,6 @@ __device__ __forceinline__ bool pp_outside_padded(const pp_ring_meta &m, double 
     return (x < m.minx - m.pad) || (x > m.maxx + m.pad) || (y < m.miny - m.pad) || (y > m.maxy + m.pad);
 }
 
-__device__ __forceinline__ int pp_cell_clamp(double f, int g) {
-    // f may be NaN / inf: the floor conversion saturates (NaN -> 0), the clamp runs on the integer pipe
-    return min(max(__double2int_rd(f), 0), g - 1);
-}
-
 // ---- warp-cooperative narrow phase.  The warp is split into four groups of eight lanes; a group works on one
 // pending (line segment, ring) candidate and its lane `sub` takes ring segments sub, sub + 8, ...: the rings of
 // this domain have 4-20 segments, so whole-warp passes would leave three quarters of the lanes idle.  All 32
@@ -149,71 +144,18 @@ __device__ __forceinline__ int pp_take_candidates(unsigned &pend, int grp) {
     return mine;
 }
 
-// ---- any obstacle polygon contains the point? ------------------------------------------------------
-template <bool CULL>
-__device__ __forceinline__ bool pp_vertex_in_obstacle(const pp_world_view &w, double x, double y) {
-    if (!CULL) {
-        for (uint32_t r = 0; r < w.n_rings; ++r)
-            if (pp_point_in_ring(w, w.meta[r], x, y)) return true;
-        return false;
-    }
-    if (w.n_rings == 0) return false;
-    const double fx = (x - w.gminx) * w.ginv, fy = (y - w.gminy) * w.ginv;
-    if (!(fx >= 0.0 && fx < (double)w.gx && fy >= 0.0 && fy < (double)w.gy)) return false;
-    const size_t c = (size_t)(int)fy * w.gx + (int)fx;
-    const uint32_t c0 = __ldg(w.cell_start + c), c1 = __ldg(w.cell_start + c + 1);
-    for (uint32_t k = c0; k < c1; ++k) {
-        const pp_ring_meta m = w.meta[__ldg(w.cell_items + k)];
-        if (pp_outside_padded(m, x, y)) continue;
-        if (pp_point_in_ring(w, m, x, y)) return true;
-    }
+// ---- exhaustive per-lane loops of PP_COLLIDE_NO_CULL: every ring, no broad phase (geo's own loop order) -------
+__device__ __forceinline__ bool pp_vertex_in_any_obstacle(const pp_world_view &w, double x, double y) {
+    for (uint32_t r = 0; r < w.n_rings; ++r)
+        if (pp_point_in_ring(w, w.meta[r], x, y)) return true;
     return false;
 }
-
-// ---- any obstacle ring meets the segment? ----------------------------------------------------------
-// LONG_SEGMENTS: the caller's segments may be long compared with the grid (user-supplied straight edges); the
-// polyline kernels pass false (sample spacing <= a cell or two) and skip the extra branch.
-template <bool CULL, bool LONG_SEGMENTS = false>
-__device__ __forceinline__ bool pp_segment_hits_obstacle(const pp_world_view &w, double x0, double y0, double x1,
-                                                         double y1) {
-    if (!CULL) {
-        for (uint32_t r = 0; r < w.n_rings; ++r) {
-            const pp_ring_meta m = w.meta[r];
-            if (pp_ring_hits_segment(w.ox + m.first, w.oy + m.first, m.count, x0, y0, x1, y1)) return true;
-        }
-        return false;
+__device__ __forceinline__ bool pp_segment_hits_any_obstacle(const pp_world_view &w, double x0, double y0, double x1,
+                                                             double y1) {
+    for (uint32_t r = 0; r < w.n_rings; ++r) {
+        const pp_ring_meta m = w.meta[r];
+        if (pp_ring_hits_segment(w.ox + m.first, w.oy + m.first, m.count, x0, y0, x1, y1)) return true;
     }
-    if (w.n_rings == 0) return false;
-    const double sminx = fmin(x0, x1), smaxx = fmax(x0, x1), sminy = fmin(y0, y1), smaxy = fmax(y0, y1);
-    const double fx0 = (sminx - w.gminx) * w.ginv, fx1 = (smaxx - w.gminx) * w.ginv;
-    const double fy0 = (sminy - w.gminy) * w.ginv, fy1 = (smaxy - w.gminy) * w.ginv;
-    if (fx1 < 0.0 || fy1 < 0.0 || fx0 >= (double)w.gx || fy0 >= (double)w.gy) return false;
-    const int cx0 = pp_cell_clamp(fx0, w.gx), cx1 = pp_cell_clamp(fx1, w.gx);
-    const int cy0 = pp_cell_clamp(fy0, w.gy), cy1 = pp_cell_clamp(fy1, w.gy);
-    // a long segment whose box covers more cells than there are rings (not the RRT's short edges): walking the
-    // ring list once is cheaper than walking the cells, and bounds the cost per segment by O(rings)
-    if (LONG_SEGMENTS &&
-        (unsigned long long)(cx1 - cx0 + 1) * (unsigned long long)(cy1 - cy0 + 1) > (unsigned long long)w.n_rings + 64ull) {
-        for (uint32_t r = 0; r < w.n_rings; ++r) {
-            const pp_ring_meta m = w.meta[r];
-            if (smaxx < m.minx - m.pad || sminx > m.maxx + m.pad || smaxy < m.miny - m.pad || sminy > m.maxy + m.pad)
-                continue;
-            if (pp_ring_hits_segment(w.ox + m.first, w.oy + m.first, m.count, x0, y0, x1, y1)) return true;
-        }
-        return false;
-    }
-    for (int cy = cy0; cy <= cy1; ++cy)
-        for (int cx = cx0; cx <= cx1; ++cx) {
-            const size_t c = (size_t)cy * w.gx + cx;
-            const uint32_t c0 = __ldg(w.cell_start + c), c1 = __ldg(w.cell_start + c + 1);
-            for (uint32_t k = c0; k < c1; ++k) {
-                const pp_ring_meta m = w.meta[__ldg(w.cell_items + k)];
-                if (smaxx < m.minx - m.pad || sminx > m.maxx + m.pad || smaxy < m.miny - m.pad ||
-                    sminy > m.maxy + m.pad)
-                    continue;
-                if (pp_ring_hits_segment(w.ox + m.first, w.oy + m.first, m.count, x0, y0, x1, y1)) return true;
-            }
-        }
     return false;
 }
 
@@ -257,8 +199,8 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
 
     if (MODE == 1) {
         if (good)
-            hit = pp_segment_hits_obstacle<false>(w, x0, y0, x1, y1) || pp_vertex_in_obstacle<false>(w, x0, y0) ||
-                  pp_vertex_in_obstacle<false>(w, x1, y1);
+            hit = pp_segment_hits_any_obstacle(w, x0, y0, x1, y1) || pp_vertex_in_any_obstacle(w, x0, y0) ||
+                  pp_vertex_in_any_obstacle(w, x1, y1);
     } else {
         const float eminx = __double2float_rd(fmin(x0, x1)), emaxx = __double2float_ru(fmax(x0, x1));
         const float eminy = __double2float_rd(fmin(y0, y1)), emaxy = __double2float_ru(fmax(y0, y1));
@@ -673,8 +615,8 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             const bool own_segment = (lane < 31) && (k + 1 < np);
             bool fail = false;
             if (!CULL) {  // exhaustive per-lane loops (PP_COLLIDE_NO_CULL)
-                if (own_vertex) fail = !pp_bounds_contains(w, x, y) || pp_vertex_in_obstacle<false>(w, x, y);
-                if (!fail && own_segment) fail = pp_segment_hits_obstacle<false>(w, x, y, xn, yn);
+                if (own_vertex) fail = !pp_bounds_contains(w, x, y) || pp_vertex_in_any_obstacle(w, x, y);
+                if (!fail && own_segment) fail = pp_segment_hits_any_obstacle(w, x, y, xn, yn);
                 if (__ballot_sync(0xffffffffu, fail) != 0u) {
                     bad = true;
                     break;
