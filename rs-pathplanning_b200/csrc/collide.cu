@@ -532,7 +532,7 @@ struct pp_points_dubins {
 
 #define PP_POLY_THREADS 128
 #ifndef PP_POLY_MIN_BLOCKS
-#define PP_POLY_MIN_BLOCKS 8  // 64 registers (some spills): measured faster than 80 / 96 / 109 registers on the C5 slice
+#define PP_POLY_MIN_BLOCKS 7  // 72 registers; C5 slice / Dubins extend / no-hit: 2.17 / 2.09 / 3.35 ms (64 registers: 2.16 / 2.12 / 3.56; 80: 2.32 / 2.23 / 3.39)
 #endif
 
 template <bool CULL, bool DUBINS>
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
         __shared__ pp_plan_aux s_aux[PP_POLY_THREADS / 32];
         const pp_dubins_plan &pl = s_plan[threadIdx.x >> 5];
         const pp_seg_origin *o = s_aux[threadIdx.x >> 5].o;
-        double ss = 0.0, cs = 1.0, pex = 0.0, pey = 0.0;
+        const pp_plan_aux &aux = s_aux[threadIdx.x >> 5];
         uint32_t nsamp = 0;
         if (DUBINS) {
             __syncwarp();  // every lane is done with the previous polyline's record
@@ -563,8 +563,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 reinterpret_cast<double *>(&s_aux[threadIdx.x >> 5])[lane] =
                     __ldg(reinterpret_cast<const double *>(dub.aux + line) + lane);
             __syncwarp();
-            pex = dub.ex[line];
-            pey = dub.ey[line];
             if (pl.count == 0xFFFFFFFFu) {  // replay overflow: the reference would run out of memory; report blocked
                 if (lane == 0) ok[line] = 0;
                 continue;
@@ -573,8 +571,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 nsamp = 1;  // fallback [(sx, sy)] of src/rrt.rs:313
             } else {
                 nsamp = pl.count;
-                ss = s_aux[threadIdx.x >> 5].ss;
-                cs = s_aux[threadIdx.x >> 5].cs;
             }
             np = nsamp + 1;
         } else {
@@ -592,16 +588,16 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             const bool have = k < np;
             if (have) {
                 if (DUBINS) {
-                    if (k >= nsamp) {
-                        x = pex;
-                        y = pey;
+                    if (k >= nsamp) {  // the parent point closes the polyline (one lane of the last chunk)
+                        x = __ldg(dub.ex + line);
+                        y = __ldg(dub.ey + line);
                     } else if (pl.word == PP_WORD_NONE || k == 0) {
                         x = pl.sx;  // sample 0 is exactly the start pose (0*cos + 0*sin + sx)
                         y = pl.sy;
                     } else {
                         double lx, ly, lyaw;
                         pp_plan_sample_local(pl, o, k, &lx, &ly, &lyaw);
-                        pp_local_to_world(ss, cs, pl.sx, pl.sy, lx, ly, &x, &y);
+                        pp_local_to_world(aux.ss, aux.cs, pl.sx, pl.sy, lx, ly, &x, &y);
                     }
                 } else {
                     x = csr.px[base + k];
