@@ -129,6 +129,29 @@ def test_eval_radius_array_and_no_tpq(ctx, O, pp):
     assert none is None and np.array_equal(cost, cost2) and np.array_equal(word, word2)
 
 
+def test_eval_start_yaw_routes(ctx, O, pp):
+    """the frame change takes theta = atan2(dy, dx) - syaw for |syaw| < 64 and the reference's rotation beyond (and for
+    coincident positions): yaws across the switch, far beyond it, and whole turns added to both yaws"""
+    n = 60_000
+    sx, sy, syaw, ex, ey, eyaw = pp.synth.dubins_pairs(n, seed=21)
+    rng = np.random.default_rng(3)
+    kind = rng.integers(0, 6, n)
+    syaw = np.where(kind == 0, rng.uniform(-64.0, 64.0, n), syaw)
+    syaw = np.where(kind == 1, rng.choice([63.999, -63.999, 64.0, -64.0, 64.001, 70.0], n), syaw)
+    syaw = np.where(kind == 2, rng.uniform(-1e4, 1e4, n), syaw)
+    turns = np.where(kind == 3, rng.integers(-9, 10, n) * 2.0 * math.pi, 0.0)
+    syaw, eyaw = syaw + turns, eyaw + np.where(kind == 4, rng.uniform(-500.0, 500.0, n), turns)
+    same = kind == 5  # coincident positions: only the yaws differ
+    ex, ey = np.where(same, sx, ex), np.where(same, sy, ey)
+    cost, word, tpq = ctx.dubins_eval(sx, sy, syaw, ex, ey, eyaw, radius=1.0)
+    flagged = _check_eval(O, cost, word, tpq, sx, sy, syaw, ex, ey, eyaw, 1.0)
+    assert flagged < n * 0.2  # coincident positions are flagged near-ties by construction
+    # the plan kernel goes through the same frame function: same words, same lengths
+    counts, plans = ctx.dubins_sample_count(sx[:2000], sy[:2000], syaw[:2000], ex[:2000], ey[:2000], eyaw[:2000], 1.0, 0.25)
+    pw = plans.reshape(-1, 112)[:, 104]  # PP_DUBINS_PLAN_BYTES, word at byte 104
+    assert np.array_equal(pw, word[:2000])
+
+
 def test_eval_structured_axis_aligned(ctx, O):
     """the 1296 axis-aligned grid poses of SURVEY A.3 Q3: many sit on a mod2pi wrap"""
     vals = [-2.0, -1.0, 0.0, 1.0, 2.0, 3.0]
