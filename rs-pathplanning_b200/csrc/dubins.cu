@@ -7,7 +7,7 @@
 #include "pp_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// kernel 1: evaluate.  One thread per pose pair; FP64-pipe bound (about 800 DP instructions per
+// kernel 1: evaluate.  One thread per pose pair; FP64-pipe bound (about 490 DP instructions per
 // 57 algorithmic bytes), so the grid is simply n/128 CTAs of 4 warps: small CTAs keep the tail short.
 // ------------------------------------------------------------------------------------------------
 #define PP_EVAL_THREADS 128

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128)
 
 
 // ---------------------------------------------------------------------------------------------
-// Bucketed scan (default for many queries).  The queries are binned into the cells of a G x G grid over
+// Bucketed scan (PP_NN_SCAN; the tiled brute-force design).  The queries are binned into the cells of a G x G grid over
 // their bounding box (counting sort: histogram, single-block scan, scatter -> a permutation), so the 128
 // queries of a warp lie in a small box.  The warp keeps ONE outward-rounded float box = union of its
 // threads' rejection boxes [q - r, q + r] (r = sqrt_ru(best)) and tests 128 nodes per step: lane l compares
