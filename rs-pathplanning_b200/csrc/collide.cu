@@ -539,10 +539,11 @@ template <bool CULL, bool DUBINS>
 __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
     pp_verify_polylines_kernel(pp_world_view w, size_t n_lines, pp_points_csr csr, pp_points_dubins dub,
                                uint8_t *__restrict__ ok) {
-    const int lane = threadIdx.x & 31;
+    unsigned tid;  // read once: left to itself the compiler re-reads the special register all over the chunk loop
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int lane = (int)(tid & 31u), wib = (int)(tid >> 5);
     const size_t warps_total = (size_t)gridDim.x * (PP_POLY_THREADS / 32);
-    for (size_t line = (size_t)blockIdx.x * (PP_POLY_THREADS / 32) + (threadIdx.x >> 5); line < n_lines;
-         line += warps_total) {
+    for (size_t line = (size_t)blockIdx.x * (PP_POLY_THREADS / 32) + wib; line < n_lines; line += warps_total) {
         uint32_t np;      // points of this polyline
         uint32_t base = 0;
         // The plan record and the three segment origins are warp-uniform and indexed by a run-time segment
@@ -550,17 +551,17 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
         // replicated per lane: ncu showed 513 MB of DRAM writes per launch for a kernel that outputs 1 MB.)
         __shared__ pp_dubins_plan s_plan[PP_POLY_THREADS / 32];
         __shared__ pp_plan_aux s_aux[PP_POLY_THREADS / 32];
-        const pp_dubins_plan &pl = s_plan[threadIdx.x >> 5];
-        const pp_seg_origin *o = s_aux[threadIdx.x >> 5].o;
-        const pp_plan_aux &aux = s_aux[threadIdx.x >> 5];
+        const pp_dubins_plan &pl = s_plan[wib];
+        const pp_seg_origin *o = s_aux[wib].o;
+        const pp_plan_aux &aux = s_aux[wib];
         uint32_t nsamp = 0;
         if (DUBINS) {
             __syncwarp();  // every lane is done with the previous polyline's record
             if (lane < (int)(sizeof(pp_dubins_plan) / 4))
-                reinterpret_cast<uint32_t *>(&s_plan[threadIdx.x >> 5])[lane] =
+                reinterpret_cast<uint32_t *>(&s_plan[wib])[lane] =
                     __ldg(reinterpret_cast<const uint32_t *>(dub.plans + line) + lane);
             if (lane < PP_PLAN_AUX_DOUBLES)
-                reinterpret_cast<double *>(&s_aux[threadIdx.x >> 5])[lane] =
+                reinterpret_cast<double *>(&s_aux[wib])[lane] =
                     __ldg(reinterpret_cast<const double *>(dub.aux + line) + lane);
             __syncwarp();
             if (pl.count == 0xFFFFFFFFu) {  // replay overflow: the reference would run out of memory; report blocked
@@ -586,23 +587,26 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             const uint32_t k = k0 + lane;
             double x = 0.0, y = 0.0;
             const bool have = k < np;
-            if (have) {
-                if (DUBINS) {
-                    if (k >= nsamp) {  // the parent point closes the polyline (one lane of the last chunk)
-                        x = __ldg(dub.ex + line);
-                        y = __ldg(dub.ey + line);
-                    } else if (pl.word == PP_WORD_NONE || k == 0) {
-                        x = pl.sx;  // sample 0 is exactly the start pose (0*cos + 0*sin + sx)
-                        y = pl.sy;
-                    } else {
-                        double lx, ly, lyaw;
-                        pp_plan_sample_local(pl, o, k, &lx, &ly, &lyaw);
-                        pp_local_to_world(aux.ss, aux.cs, pl.sx, pl.sy, lx, ly, &x, &y);
-                    }
-                } else {
-                    x = csr.px[base + k];
-                    y = csr.py[base + k];
+            if (DUBINS) {
+                // every lane evaluates a (clamped) sample slot, then the two special points are patched in: no
+                // divergence between the lanes of a chunk except where a chunk straddles a segment junction
+                if (nsamp > 1u) {  // uniform; implies a feasible word
+                    const uint32_t kk = min(max(k, 1u), nsamp - 1u);
+                    double lx, ly, lyaw;
+                    pp_plan_sample_local(pl, o, kk, &lx, &ly, &lyaw);
+                    pp_local_to_world(aux.ss, aux.cs, pl.sx, pl.sy, lx, ly, &x, &y);
                 }
+                if (k == 0u) {  // slot 0 is exactly the start pose (0*cos + 0*sin + sx)
+                    x = pl.sx;
+                    y = pl.sy;
+                }
+                if (k == nsamp) {  // the parent point closes the polyline (one lane of the last chunk)
+                    x = __ldg(dub.ex + line);
+                    y = __ldg(dub.ey + line);
+                }
+            } else if (have) {
+                x = csr.px[base + k];
+                y = csr.py[base + k];
             }
             const double xn = __shfl_down_sync(0xffffffffu, x, 1);
             const double yn = __shfl_down_sync(0xffffffffu, y, 1);
