@@ -16,7 +16,7 @@ ncu --set full --clock-control none --import-source on -k regex:pp_dubins_eval_k
 echo "dubins_eval capture rc=$?"
 if [ "${2:-}" = "all" ]; then
   $CMD > /dev/null 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"pp_nn_scan_kernel|pp_nn_grid_kernel|pp_collide_segments_kernel|pp_verify_polylines_kernel|pp_dubins_plan_kernel" \
-      -c 8 -o gpurun_out/${R}_rrt $CMD > gpurun_out/${R}_rrt_run.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"pp_nn_bucketed_kernel|pp_nn_grid_kernel|pp_collide_segments_grid_kernel|pp_collide_segments_bucketed_kernel|pp_verify_polylines_kernel|pp_dubins_plan_kernel" \
+      -c 24 -o gpurun_out/${R}_rrt $CMD > gpurun_out/${R}_rrt_run.log 2>&1
   echo "rrt capture rc=$?"
 fi
