@@ -533,6 +533,30 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
                      "unit": "GB/s", "frac": total * 24.0 / f_s / 1e9 / hbm_peak, "traffic": None,
                      "per_unit": "24 B written per sample (+112 B plan record per path)"},
     }
+    # ---- C2 (functional, host-driven): the examples/rrt shape -- 100 x 100 world, 50 create_circle obstacles, 10 k
+    # iterations, fixed seed -- through the Python mirror's batched rounds (NN -> yaw -> fused Dubins verify ->
+    # append -> goal connection per round).  Wall clock of the whole planner incl. the Python bookkeeping and every
+    # host<->device copy: a statement about the drop-in API, not a kernel benchmark.  Every rank runs its own copy.
+    try:
+        rng = np.random.default_rng(0xC2)
+        rings = [pp.rrt.create_circle((float(cx), float(cy)), float(r))
+                 for cx, cy, r in zip(rng.uniform(10, 90, 50), rng.uniform(10, 90, 50), rng.uniform(1.0, 3.0, 50))]
+        bounds_ring = (np.array([0.0, 0.0, 100.0, 100.0, 0.0]), np.array([0.0, 100.0, 100.0, 0.0, 0.0]))
+        space = pp.rrt.Space(bounds_ring, pp.rrt.Robot(1.8, 3.0, 0.8), rings, ctx=ctx, seed=7)
+        planner = pp.rrt.RRT((4.0, 4.0), 0.0, (96.0, 96.0), 0.0, 10_000, 0.1, space)
+        l0 = ctx.launch_count
+        t0 = time.perf_counter()
+        path = planner.plan_rounds(batch=512)
+        dt = time.perf_counter() - t0
+        out["c2_rrt_plan_rounds"] = {
+            "metric": "rrt_iterations_per_s", "value": 10_000 / dt, "unit": "iterations/s", "wall_s": dt,
+            "tree_nodes": len(planner.nodes), "path_found": path is not None,
+            "path_points": 0 if path is None else int(len(path[0])), "gpu_launches": ctx.launch_count - l0,
+            "config": {"workload": "c2: RRT.plan_rounds(batch=512), 10 000 iterations, 100 x 100 world, 50 create_circle "
+                                   "obstacles (r in [1, 3)), Robot(1.8, 3.0, 0.8), step 0.1, seed 7; host-driven, per rank"},
+        }
+    except Exception as e:  # the functional leg must never take the benchmark line down
+        out["c2_rrt_plan_rounds"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     return out
 
 
