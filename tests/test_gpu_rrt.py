@@ -181,6 +181,42 @@ def test_verify_polylines(ctx, O, pp):
     assert 0 < want.sum() < len(lines)
 
 
+def test_many_vertex_rings(ctx, O, pp):
+    """rings of 3 ... 700 points (stars, non-convex): the grouped narrow phase strides a ring eight segments at a time,
+    so rings longer than one pass, longer than a warp, and the tiny ones all take different trip counts"""
+    rng = np.random.default_rng(23)
+    rings = []
+    for k in range(60):
+        n = int(rng.choice([3, 4, 8, 9, 16, 17, 33, 64, 65, 130, 700]))
+        cx, cy = rng.uniform(8, 92, 2)
+        th = np.sort(rng.uniform(0, 2 * math.pi, n))
+        rad = rng.uniform(1.0, 4.0) * (1.0 + 0.45 * np.sin(7 * th + rng.uniform(0, 6)))  # star-ish, non-convex
+        rings.append((cx + rad * np.cos(th), cy + rad * np.sin(th)))
+    bounds = (np.array([0.0, 0.0, 100.0, 100.0, 0.0]), np.array([0.0, 100.0, 100.0, 0.0, 0.0]))
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    m = 40_000
+    ax, ay = rng.uniform(-1, 101, m), rng.uniform(-1, 101, m)
+    ln = rng.choice([0.05, 0.5, 3.0, 25.0], m)
+    th = rng.uniform(-math.pi, math.pi, m)
+    bx, by = ax + ln * np.cos(th), ay + ln * np.sin(th)
+    want = W.verify_segments(ax, ay, bx, by)
+    for flags in (DEFAULT, SCAN, UNSORTED):
+        assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=flags), want), flags
+    assert 0.05 < want.mean() < 0.95
+    lines = []
+    for k in range(300):
+        npts = int(rng.choice([2, 5, 40, 90]))
+        x0, y0 = rng.uniform(5, 95, 2)
+        lines.append((x0 + np.cumsum(rng.normal(0, 0.3, npts)), y0 + np.cumsum(rng.normal(0, 0.3, npts))))
+    wantl = np.array([W.verify(lx, ly) for lx, ly in lines], np.uint8)
+    assert np.array_equal(ctx.verify_polylines(lines), wantl) and 0 < wantl.sum() < len(lines)
+    e = 2000
+    sx, sy, syaw, ex, ey, eyaw = pp.synth.dubins_edges(e, world=100.0, reach=10.0)
+    ok = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.05)
+    assert (ok != W.verify_dubins_edges(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.05)).sum() <= 2
+
+
 @pytest.mark.parametrize("radius,step", [(1.0, 0.05), (0.8, 0.1)])
 def test_collide_dubins_edges(ctx, O, pp, radius, step):
     bounds, rings = pp.synth.circle_world(400, world=100.0, rmin=0.5, rmax=1.5)
