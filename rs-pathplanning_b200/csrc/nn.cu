@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(128)
             const double v = dx * dx + dy * dy;
             if (v <= best) {
                 const uint32_t i = __ldg(cell_items + k);
-                if (v < best || i < bi) {
+                // a tie only counts against a node already held: d2 = +inf (a query or node at 1e300, +-inf) ties
+                // with the initial best and must leave "no node", as the strict compare of the scans does
+                if (v < best || (i < bi && bi != 0xFFFFFFFFu)) {
                     best = v;
                     bi = i;
                 }

@@ -181,6 +181,38 @@ def test_verify_polylines(ctx, O, pp):
     assert 0 < want.sum() < len(lines)
 
 
+def test_collide_nonfinite_coordinates(ctx, O, pp):
+    """NaN / infinite end points and huge finite ones: never `contained` by the bounds, whatever the integer cell
+    arithmetic makes of them (saturating conversions, NaN -> cell 0)"""
+    bounds, rings = pp.synth.circle_world(300, world=100.0, rmin=1.0, rmax=3.0)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    nan, inf = float("nan"), float("inf")
+    bad = [nan, inf, -inf, 1e300, -1e300, 1e15, -4e9]
+    ax, ay, bx, by = [], [], [], []
+    for v in bad:
+        for pos in range(4):
+            p = [50.0, 50.0, 50.5, 50.5]
+            p[pos] = v
+            ax.append(p[0]); ay.append(p[1]); bx.append(p[2]); by.append(p[3])
+    ax += [50.0] * 3; ay += [50.0] * 3; bx += [50.5, 50.0, 99.9]; by += [50.5, 50.0, 0.1]  # a few ordinary ones
+    ax, ay, bx, by = (np.array(v) for v in (ax, ay, bx, by))
+    want = W.verify_segments(ax, ay, bx, by)
+    assert not want[: 4 * len(bad)].any()
+    for flags in (DEFAULT, SCAN, UNSORTED, NO_CULL):
+        assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=flags), want), flags
+    lines = [(np.array([50.0, v, 51.0]), np.array([50.0, 50.0, 50.0])) for v in bad]
+    lines += [(np.array([50.0, 50.2, 50.4]), np.array([v, 50.0, 50.0])) for v in bad]
+    assert not ctx.verify_polylines(lines).any()
+    # NN queries with non-finite coordinates through the grid path (tree large enough for the grid)
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(200, 5000, world=100.0)
+    ctx.tree_upload(nx, ny, nyaw)
+    qx[:7], qy[7:14] = bad, bad
+    for flags in (NN_DEFAULT, NN_GRID, NN_SCAN):
+        idx = ctx.nn(qx, qy, flags=flags, want_d2=False)
+        assert np.array_equal(idx, O.nn_brute(nx, ny, qx, qy)[0]), flags
+
+
 def test_many_vertex_rings(ctx, O, pp):
     """rings of 3 ... 700 points (stars, non-convex): the grouped narrow phase strides a ring eight segments at a time,
     so rings longer than one pass, longer than a warp, and the tiny ones all take different trip counts"""
