@@ -211,6 +211,20 @@ def test_collide_nonfinite_coordinates(ctx, O, pp):
     for flags in (NN_DEFAULT, NN_GRID, NN_SCAN):
         idx = ctx.nn(qx, qy, flags=flags, want_d2=False)
         assert np.array_equal(idx, O.nn_brute(nx, ny, qx, qy)[0]), flags
+    # Dubins edges with a non-finite pose component: no feasible word -> [(sx, sy), parent] -> not contained
+    e = 7 * 6
+    sx, sy, syaw, ex, ey, eyaw = (np.full(e, v) for v in (40.0, 40.0, 0.3, 43.0, 41.0, -0.2))
+    for k, v in enumerate(bad):
+        for pos, arr in enumerate((sx, sy, syaw, ex, ey, eyaw)):
+            arr[6 * k + pos] = v
+    ok = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.1)
+    want = W.verify_dubins_edges(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.1)
+    finite_yaw_only = np.zeros(e, bool)
+    finite_yaw_only[[6 * k + p for k in range(3, 7) for p in (2, 5)]] = True  # huge but finite yaws are legal poses
+    declined = want == 255  # the oracle refuses to replay a path of ~1e16 samples (positions at 1e15); the GPU reports blocked
+    assert not ok[~finite_yaw_only].any()
+    assert np.array_equal(ok[~finite_yaw_only & ~declined], want[~finite_yaw_only & ~declined])
+    assert (ok[finite_yaw_only] != want[finite_yaw_only]).sum() <= 1  # 1e300-rad yaws: the last digits of sincos decide
 
 
 def test_many_vertex_rings(ctx, O, pp):
