@@ -227,6 +227,30 @@ def test_collide_nonfinite_coordinates(ctx, O, pp):
     assert (ok[finite_yaw_only] != want[finite_yaw_only]).sum() <= 1  # 1e300-rad yaws: the last digits of sincos decide
 
 
+def test_world_without_obstacles_and_degenerate_rings(ctx, O, pp):
+    """no rings at all; then rings of 0, 1 and 2 points and a zero-area ring next to ordinary ones"""
+    bounds = (np.array([0.0, 0.0, 50.0, 50.0, 0.0]), np.array([0.0, 50.0, 50.0, 0.0, 0.0]))
+    rng = np.random.default_rng(31)
+    m = 5000
+    ax, ay = rng.uniform(-1, 51, m), rng.uniform(-1, 51, m)
+    th, ln = rng.uniform(-math.pi, math.pi, m), rng.choice([0.2, 4.0, 30.0], m)
+    bx, by = ax + ln * np.cos(th), ay + ln * np.sin(th)
+    sx, sy, syaw, ex, ey, eyaw = pp.synth.dubins_edges(600, world=50.0, reach=8.0)
+    worlds = [[], [(np.zeros(0), np.zeros(0)), (np.array([10.0]), np.array([10.0])),
+                   (np.array([20.0, 24.0]), np.array([20.0, 23.0])),
+                   (np.array([30.0, 34.0, 30.0]), np.array([30.0, 30.0, 30.0])),  # zero area
+                   pp.rrt.create_circle((25.0, 25.0), 3.0), pp.rrt.create_circle((12.0, 40.0), 1.0)]]
+    for rings in worlds:
+        ctx.obstacles_upload(bounds, rings)
+        W = O.OracleWorld(bounds, rings)
+        want = W.verify_segments(ax, ay, bx, by)
+        for flags in (DEFAULT, SCAN, UNSORTED, NO_CULL):
+            assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=flags), want), (len(rings), flags)
+        ok = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.1)
+        assert (ok != W.verify_dubins_edges(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.1)).sum() <= 1, len(rings)
+        assert 0 < want.sum() < m
+
+
 def test_many_vertex_rings(ctx, O, pp):
     """rings of 3 ... 700 points (stars, non-convex): the grouped narrow phase strides a ring eight segments at a time,
     so rings longer than one pass, longer than a warp, and the tiny ones all take different trip counts"""
