@@ -92,6 +92,35 @@ def test_nn_grid_clustered_tree(ctx, O):
     assert np.array_equal(one, idx[:3])
 
 
+def test_nn_grid_degenerate_geometries(ctx, O):
+    """node sets that stress the device-built grid's geometry: all nodes identical, collinear (zero height), a 1e6 : 1
+    aspect ratio, the 4 096-node switch point, and growth by appends past the allocated capacity"""
+    rng = np.random.default_rng(17)
+    q = (rng.uniform(-2, 12, 700), rng.uniform(-2, 12, 700))
+    sets = {
+        "identical": (np.full(5000, 3.25), np.full(5000, -1.5)),
+        "collinear_x": (rng.uniform(0, 10, 6000), np.full(6000, 4.0)),
+        "collinear_y": (np.full(4096, 7.0), rng.uniform(0, 10, 4096)),
+        "thin": (rng.uniform(0, 1e6, 9000), rng.uniform(0, 1.0, 9000)),
+        "switch": (rng.uniform(0, 10, 4096), rng.uniform(0, 10, 4096)),
+        "below_switch": (rng.uniform(0, 10, 4095), rng.uniform(0, 10, 4095)),
+    }
+    for name, (nx, ny) in sets.items():
+        qx, qy = (q[0] * (1e5 if name == "thin" else 1.0), q[1] * (0.1 if name == "thin" else 1.0))
+        ctx.tree_upload(nx, ny)
+        oidx, od2 = O.nn_brute(nx, ny, qx, qy)
+        for flags in (NN_DEFAULT, NN_GRID):
+            idx, d2 = ctx.nn(qx, qy, flags=flags)
+            assert np.array_equal(idx, oidx) and np.array_equal(d2, od2), (name, flags)
+    # growth: 5 000 -> 40 000 nodes in uneven appends, default method after every step
+    nx, ny = rng.uniform(0, 10, 40_000), rng.uniform(0, 10, 40_000)
+    ctx.tree_upload(nx[:5000], ny[:5000])
+    for a, b in [(5000, 5001), (5001, 9000), (9000, 20_000), (20_000, 40_000)]:
+        ctx.tree_append(nx[a:b], ny[a:b], np.zeros(b - a), np.zeros(b - a, dtype=np.int32))
+        idx = ctx.nn(q[0], q[1], want_d2=False)
+        assert np.array_equal(idx, O.nn_brute(nx[:b], ny[:b], q[0], q[1])[0]), b
+
+
 def test_nn_nonfinite(ctx, O):
     nx = np.array([0.0, np.nan, 5.0, np.inf, 1.0])
     ny = np.array([0.0, 1.0, np.nan, 2.0, 1.0])
