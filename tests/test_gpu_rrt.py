@@ -280,6 +280,28 @@ def test_world_without_obstacles_and_degenerate_rings(ctx, O, pp):
         assert 0 < want.sum() < m
 
 
+def test_collide_dubins_zero_length_and_tiny_paths(ctx, O, pp):
+    """identical poses (every sample trimmed: the polyline is the parent point alone), pure turns on the spot and
+    paths shorter than one step, in free space, inside an obstacle and outside the bounds"""
+    bounds, rings = pp.synth.circle_world(150, world=60.0, rmin=1.0, rmax=3.0)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    rng = np.random.default_rng(41)
+    n = 1500
+    sx, sy = rng.uniform(-2, 62, n), rng.uniform(-2, 62, n)
+    syaw = rng.uniform(-math.pi, math.pi, n)
+    kind = rng.integers(0, 4, n)
+    ex = sx + np.where(kind == 2, rng.uniform(-0.02, 0.02, n), 0.0)
+    ey = sy + np.where(kind == 2, rng.uniform(-0.02, 0.02, n), 0.0)
+    eyaw = np.where(kind == 0, syaw, np.where(kind == 1, syaw + rng.uniform(-3, 3, n), rng.uniform(-math.pi, math.pi, n)))
+    ex = np.where(kind == 3, sx + rng.uniform(-0.3, 0.3, n), ex)
+    for radius, step in [(1.0, 0.1), (0.5, 0.05)]:
+        ok = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, radius, step)
+        want = W.verify_dubins_edges(sx, sy, syaw, ex, ey, eyaw, radius, step)
+        assert (ok != want).sum() <= 2, (radius, step, np.nonzero(ok != want)[0][:10])
+        assert 0 < want.sum() < n
+
+
 def test_many_vertex_rings(ctx, O, pp):
     """rings of 3 ... 700 points (stars, non-convex): the grouped narrow phase strides a ring eight segments at a time,
     so rings longer than one pass, longer than a warp, and the tiny ones all take different trip counts"""
