@@ -245,6 +245,74 @@ class RRT:  # src/rrt.rs:325-619
             chain_ok[: n - 1] = np.logical_and.accumulate(own[::-1])[::-1]
         return first & chain_ok
 
+    # -- the same recursion for MANY start nodes at once: all candidates of all nodes of a recursion level go into one
+    # fused launch, so a round's goal checks cost RECURSION_LIMIT launches instead of RECURSION_LIMIT per node.
+    # Per node the candidates, their order and the verdicts are those of optimize() (tests compare them).
+    def _optimize_many(self, nodes: List[Node], i: int = 0) -> List[Optional[Node]]:
+        if i >= RECURSION_LIMIT or not nodes:
+            return [None] * len(nodes)
+        chains = [list(NodeIter(n)) for n in nodes]
+        cands = [[Node(n.get_coord(), to_node) for to_node in ch] for n, ch in zip(nodes, chains)]
+        sx, sy, syaw, ex, ey, eyaw, spans = [], [], [], [], [], [], []
+        for ch, cd in zip(chains, cands):
+            a = len(sx)
+            sx += [c.point[0] for c in cd] + [v.point[0] for v in ch[:-1]]
+            sy += [c.point[1] for c in cd] + [v.point[1] for v in ch[:-1]]
+            syaw += [c.yaw for c in cd] + [v.yaw for v in ch[:-1]]
+            ex += [v.point[0] for v in ch] + [v.parent.point[0] for v in ch[:-1]]
+            ey += [v.point[1] for v in ch] + [v.parent.point[1] for v in ch[:-1]]
+            eyaw += [v.yaw for v in ch] + [v.parent.yaw for v in ch[:-1]]
+            spans.append((a, len(ch)))
+        ok = self.ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, self.space.get_steer(), self.step_size).astype(bool)
+        picks: List[int] = []
+        for (a, n), ch in zip(spans, chains):
+            first, own = ok[a:a + n], ok[a + n:a + 2 * n - 1]
+            chain_ok = np.ones(n, bool)
+            if n > 1:
+                chain_ok[: n - 1] = np.logical_and.accumulate(own[::-1])[::-1]
+            valid = np.nonzero(first & chain_ok)[0]
+            picks.append(int(valid[-1]) if valid.size else -1)  # .rev(): the candidate closest to the root wins
+        live = [j for j, k in enumerate(picks) if k >= 0]
+        deeper = self._optimize_many([chains[j][picks[j]] for j in live], i + 1)
+        out: List[Optional[Node]] = [None] * len(nodes)
+        for j, d in zip(live, deeper):
+            out[j] = Node(nodes[j].get_coord(), d) if d is not None else cands[j][picks[j]]
+        return out
+
+    # -- check_finish (src/rrt.rs:428-438) for many nodes: batched optimize, one batched line_to_origin over all the
+    # chains' edges, one verify launch.  Same lines as [check_finish(n) for n in nodes].
+    def check_finish_many(self, nodes: List[Node]) -> List[Optional[Ring]]:
+        if not nodes:
+            return []
+        goals = [Node.new_goal(self.goal, n, self.goal_yaw) for n in nodes]
+        opt = self._optimize_many(list(nodes), 0)
+        tops = [Node.new_goal(g.get_coord(), o, self.goal_yaw) if o is not None else g for g, o in zip(goals, opt)]
+        edges = [_chain_edges(t) for t in tops]
+        flat = [sum((e[c] for e in edges), []) for c in range(6)]
+        steer = self.space.get_steer()
+        lines: List[Ring] = []
+        if flat[0]:
+            counts, plan = self.ctx.dubins_sample_count(*flat, steer, self.step_size)
+            out, offsets = self.ctx.dubins_sample_fill(plan, counts)
+            words = np.frombuffer(plan, np.uint8).reshape(-1, _ffi.PLAN_BYTES)[:, 104]
+        pos = 0
+        for e in edges:
+            xs, ys = [], []
+            for k in range(len(e[0])):
+                i = pos + k
+                if words[i] == _ffi.WORD_NONE:  # src/rrt.rs:313
+                    xs.append(np.array([e[0][k]])); ys.append(np.array([e[1][k]]))
+                else:
+                    o, c = int(offsets[i]), int(counts[i])
+                    xs.append(out[o:o + c, 0]); ys.append(out[o:o + c, 1])
+            pos += len(e[0])
+            # line_to_origin appends the root's point and finalize drops it again (:532): the samples alone, reversed
+            lx = np.concatenate(xs) if xs else np.zeros(0)
+            ly = np.concatenate(ys) if ys else np.zeros(0)
+            lines.append((lx[::-1].copy(), ly[::-1].copy()))
+        good = self.space.verify_many(lines)
+        return [ln if g else None for ln, g in zip(lines, good)]
+
     # -- src/rrt.rs:489-501
     def optimize_from_goal(self, goal_node: Node) -> Node:
         parent = goal_node.get_parent()
@@ -299,10 +367,7 @@ class RRT:  # src/rrt.rs:325-619
                                            [self.goal_yaw] * len(fresh), [c.point[0] for c in fresh],
                                            [c.point[1] for c in fresh], [c.yaw for c in fresh], steer,
                                            self.step_size).astype(bool)
-            for c, reach in zip(fresh, g_ok):
-                if not reach:
-                    continue
-                line = self.check_finish(c)
+            for line in self.check_finish_many([c for c, reach in zip(fresh, g_ok) if reach]):
                 if line is not None:
                     length = euclidean_length(line)
                     if length < best_len:

@@ -430,6 +430,35 @@ def test_batched_shortcutting_matches_the_sequential_loop(pp, ctx, O):
             # the root itself and nests Node(root, root) until RECURSION_LIMIT -- a quirk both versions reproduce)
 
 
+def test_check_finish_many_matches_check_finish(pp, ctx, O):
+    """the round-level goal check (all nodes' optimize recursions level by level in one launch each, one batched
+    line_to_origin, one verify launch) returns exactly the lines of the per-node check_finish"""
+    r = pp.rrt
+    bounds, rings = _bench_world(pp)
+    space = r.Space(bounds, r.Robot(1.0, 1.0, 0.8), rings, ctx=ctx, seed=7)
+    planner = r.RRT((-5.0, -5.0), math.radians(-45.0), (6.0, 10.0), math.radians(45.0), 8000, 0.1, space)
+    for _ in range(250):
+        planner.plan_one()
+    nodes = planner.nodes[1:60] + sorted(planner.nodes, key=lambda n: -len(list(r.NodeIter(n))))[:12]
+    many = planner.check_finish_many(nodes)
+    assert len(many) == len(nodes)
+    found = 0
+    for n, got in zip(nodes, many):
+        want = planner.check_finish(n)
+        assert (got is None) == (want is None)
+        if got is not None:
+            found += 1
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert found >= 1
+    opt_many = planner._optimize_many(nodes)
+    for n, a in zip(nodes, opt_many):
+        b = planner.optimize(n, 0)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert _chain_points(r, a) == _chain_points(r, b)
+    assert planner.check_finish_many([]) == []
+
+
 def test_plan_rounds_keeps_the_tree_invariant(pp, ctx, O):
     """batched rounds; every inserted node's chain must verify under the oracle, the device
     mirror must track the host tree, and a returned path must verify"""
