@@ -40,7 +40,7 @@ struct Json {  // just enough for nested arrays of numbers keyed by name
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        std::fprintf(stderr, "usage: %s world.json [max_iter] [seed]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s world.json [max_iter] [seed] [round_batch]\n", argv[0]);
         return 2;
     }
     std::ifstream f(argv[1]);
@@ -53,6 +53,7 @@ int main(int argc, char **argv) {
     Json j{ss.str()};
     const size_t max_iter = argc > 2 ? (size_t)std::atol(argv[2]) : 8000;
     const uint64_t seed = argc > 3 ? (uint64_t)std::atoll(argv[3]) : 1;
+    const size_t round_batch = argc > 4 ? (size_t)std::atol(argv[4]) : 0;  // 0: the reference's plan() loop
 
     std::vector<double> v;
     std::vector<int> d;
@@ -101,7 +102,19 @@ int main(int argc, char **argv) {
     RRT planner(Coordinate{st[0], st[1]}, st[2], Coordinate{gl[0], gl[1]}, gl[2], max_iter, 0.1, space);
     std::printf("Start planner (bounds %zu pts, %zu obstacles, %zu iterations)\n", bounds.ring.size(),
                 obstacle_list.size(), max_iter);
-    auto path = planner.plan();
+    auto path = round_batch ? planner.plan_rounds(round_batch) : planner.plan();
+    if (round_batch) {
+        // self-check of the round-level goal test: the same lines as check_finish node by node
+        std::vector<pathplanning::rrt::NodePtr> some(planner.nodes().begin() + 1,
+                                                    planner.nodes().begin() + std::min<size_t>(planner.nodes().size(), 40));
+        auto many = planner.check_finish_many(some);
+        size_t same = 0;
+        for (size_t k = 0; k < some.size(); ++k) {
+            auto one = planner.check_finish(some[k]);
+            same += (bool(one) == bool(many[k])) && (!one || (one->x == many[k]->x && one->y == many[k]->y));
+        }
+        std::printf("check_finish_many agrees on %zu of %zu nodes\n", same, some.size());
+    }
     if (path) {
         std::printf("Path generated!\nNum points: %zu\nlength: %.6f\ntree nodes: %zu\n", path->size(),
                     path->euclidean_length(), planner.tree_size());

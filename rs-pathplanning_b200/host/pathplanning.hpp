@@ -253,6 +253,20 @@ class Space {  // src/rrt.rs:70-159
         detail::check(pp_verify_polylines(detail::ctx(), 1, line.x.data(), line.y.data(), off, &ok, 0), "verify");
         return ok != 0;
     }
+    std::vector<uint8_t> verify_many(const std::vector<LineString> &lines) const {  // one launch for all lines
+        std::vector<uint32_t> off{0};
+        std::vector<double> px, py;
+        for (const LineString &l : lines) {
+            px.insert(px.end(), l.x.begin(), l.x.end());
+            py.insert(py.end(), l.y.begin(), l.y.end());
+            off.push_back((uint32_t)px.size());
+        }
+        std::vector<uint8_t> ok(lines.size());
+        if (!lines.empty())
+            detail::check(pp_verify_polylines(detail::ctx(), lines.size(), px.data(), py.data(), off.data(), ok.data(), 0),
+                          "verify_many");
+        return ok;
+    }
     Point rand_point() {  // src/rrt.rs:139-146
         std::uniform_real_distribution<double> ux(minx_, maxx_), uy(miny_, maxy_);
         std::lock_guard<std::mutex> lk(mu_);
@@ -497,6 +511,170 @@ class RRT {  // src/rrt.rs:325-619
                 if (len < best_len) {
                     best_len = len;
                     best = std::move(r);
+                }
+            }
+        }
+        return best;
+    }
+    // ---- SURVEY 8f-2/3 at round level.  optimize() for MANY start nodes: the candidates of all nodes of a recursion
+    // level go into one fused launch (per node: the candidates, order and verdicts of optimize()).
+    std::vector<std::optional<NodePtr>> optimize_many(const std::vector<NodePtr> &starts, size_t i = 0) const {
+        std::vector<std::optional<NodePtr>> out(starts.size());
+        if (i >= RECURSION_LIMIT || starts.empty()) return out;
+        std::vector<std::vector<NodePtr>> chains(starts.size()), cands(starts.size());
+        std::vector<size_t> first(starts.size());
+        detail_rrt::Edges e;
+        auto push = [&e](const Node &a, const Node &b) {
+            e.sx.push_back(a.get_point().x);
+            e.sy.push_back(a.get_point().y);
+            e.syaw.push_back(a.get_yaw());
+            e.ex.push_back(b.get_point().x);
+            e.ey.push_back(b.get_point().y);
+            e.eyaw.push_back(b.get_yaw());
+        };
+        for (size_t j = 0; j < starts.size(); ++j) {
+            NodeIter it(starts[j]);
+            while (NodePtr n = it.next()) chains[j].push_back(n);
+            first[j] = e.sx.size();
+            for (const NodePtr &to : chains[j]) {
+                cands[j].push_back(std::make_shared<Node>(starts[j]->get_coord(), to));
+                push(*cands[j].back(), *to);
+            }
+            for (size_t k = 0; k + 1 < chains[j].size(); ++k) push(*chains[j][k], *chains[j][k + 1]);
+        }
+        std::vector<uint8_t> ok(e.sx.size());
+        detail::check(pp_collide_dubins(detail::ctx(), ok.size(), e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
+                                        e.ey.data(), e.eyaw.data(), space_->get_steer(), step_size_, ok.data(), 0),
+                      "collide_dubins");
+        std::vector<size_t> live;
+        std::vector<size_t> pick(starts.size());
+        std::vector<NodePtr> next;
+        for (size_t j = 0; j < starts.size(); ++j) {
+            const size_t n = chains[j].size(), a = first[j];
+            std::vector<uint8_t> chain_ok(n, 1);
+            for (size_t k = n - 1; k-- > 0;) chain_ok[k] = (uint8_t)(chain_ok[k + 1] && ok[a + n + k]);
+            for (size_t k = n; k-- > 0;) {  // .rev(): root first
+                if (ok[a + k] && chain_ok[k]) {
+                    pick[j] = k;
+                    live.push_back(j);
+                    next.push_back(chains[j][k]);
+                    break;
+                }
+            }
+        }
+        std::vector<std::optional<NodePtr>> deeper = optimize_many(next, i + 1);
+        for (size_t q = 0; q < live.size(); ++q) {
+            const size_t j = live[q];
+            out[j] = deeper[q] ? std::make_shared<Node>(starts[j]->get_coord(), *deeper[q]) : cands[j][pick[j]];
+        }
+        return out;
+    }
+    // check_finish for many nodes: batched optimize, one count + fill over all final chains, one verify launch;
+    // the same lines as check_finish(node) per node
+    std::vector<std::optional<LineString>> check_finish_many(const std::vector<NodePtr> &from) const {
+        std::vector<std::optional<LineString>> res(from.size());
+        if (from.empty()) return res;
+        std::vector<std::optional<NodePtr>> opt = optimize_many(from, 0);
+        std::vector<detail_rrt::Edges> edges(from.size());
+        detail_rrt::Edges all;
+        for (size_t j = 0; j < from.size(); ++j) {
+            NodePtr top = std::make_shared<Node>(Node::new_goal(goal_, opt[j] ? *opt[j] : from[j], goal_yaw_));
+            edges[j] = detail_rrt::chain_edges(top);
+            all.sx.insert(all.sx.end(), edges[j].sx.begin(), edges[j].sx.end());
+            all.sy.insert(all.sy.end(), edges[j].sy.begin(), edges[j].sy.end());
+            all.syaw.insert(all.syaw.end(), edges[j].syaw.begin(), edges[j].syaw.end());
+            all.ex.insert(all.ex.end(), edges[j].ex.begin(), edges[j].ex.end());
+            all.ey.insert(all.ey.end(), edges[j].ey.begin(), edges[j].ey.end());
+            all.eyaw.insert(all.eyaw.end(), edges[j].eyaw.begin(), edges[j].eyaw.end());
+        }
+        const size_t m = all.sx.size();
+        std::vector<uint32_t> counts(m);
+        std::vector<unsigned char> plan(m * PP_DUBINS_PLAN_BYTES);
+        detail::check(pp_dubins_sample_count(detail::ctx(), m, all.sx.data(), all.sy.data(), all.syaw.data(), all.ex.data(),
+                                             all.ey.data(), all.eyaw.data(), space_->get_steer(), step_size_, 0,
+                                             counts.data(), plan.data()),
+                      "sample_count");
+        std::vector<uint64_t> offsets(m);
+        uint64_t total = 0;
+        for (size_t i = 0; i < m; ++i) {
+            offsets[i] = total;
+            total += (counts[i] == 0xFFFFFFFFu) ? 0 : counts[i];
+        }
+        std::vector<double> xyyaw(3 * total);
+        detail::check(pp_dubins_sample_fill(detail::ctx(), m, plan.data(), offsets.data(), total, xyyaw.data()),
+                      "sample_fill");
+        std::vector<LineString> lines(from.size());
+        size_t pos = 0;
+        for (size_t j = 0; j < from.size(); ++j) {
+            LineString fwd;  // node -> root order, the root's own point left out (finalize drops it, :532)
+            for (size_t k = 0; k < edges[j].sx.size(); ++k, ++pos) {
+                if (plan[pos * PP_DUBINS_PLAN_BYTES + 104] == PP_WORD_NONE) {  // src/rrt.rs:313
+                    fwd.push(edges[j].sx[k], edges[j].sy[k]);
+                    continue;
+                }
+                for (uint64_t s = offsets[pos]; s < offsets[pos] + counts[pos]; ++s) fwd.push(xyyaw[3 * s], xyyaw[3 * s + 1]);
+            }
+            for (size_t k = fwd.size(); k-- > 0;) lines[j].push(fwd.x[k], fwd.y[k]);  // :538 reverse
+        }
+        std::vector<uint8_t> good = space_->verify_many(lines);
+        for (size_t j = 0; j < from.size(); ++j)
+            if (good[j]) res[j] = std::move(lines[j]);
+        return res;
+    }
+    // Rounds of `batch` samples against one tree snapshot (the reference's four racy workers at width `batch`,
+    // src/rrt.rs:600-609): one pp_rrt_extend_dubins call (NN -> Node::new yaw -> fused Dubins verify of the new
+    // edges; the parents' chains are verified already, that is the tree invariant), one batched append, one fused
+    // launch for the goal connections, check_finish_many for the nodes that see the goal; min_by length on the host.
+    std::optional<LineString> plan_rounds(size_t batch = 256) {
+        std::optional<LineString> best;
+        double best_len = std::numeric_limits<double>::infinity();
+        const double steer = space_->get_steer();
+        for (size_t budget = max_iter_; budget > 0;) {
+            const size_t b = std::min(batch, budget);
+            budget -= b;
+            std::vector<double> px(b), py(b), yaw(b);
+            for (size_t k = 0; k < b; ++k) {
+                const Point p = space_->rand_point();
+                px[k] = p.x;
+                py[k] = p.y;
+            }
+            std::vector<uint32_t> idx(b);
+            std::vector<uint8_t> ok(b);
+            detail::check(pp_rrt_extend_dubins(detail::ctx(), b, px.data(), py.data(), steer, step_size_, idx.data(),
+                                               yaw.data(), ok.data(), 0, 0),
+                          "rrt_extend_dubins");
+            std::vector<NodePtr> fresh;
+            std::vector<double> ax, ay, ayaw;
+            std::vector<int32_t> apar;
+            for (size_t k = 0; k < b; ++k) {
+                if (!ok[k]) continue;
+                NodePtr n = std::make_shared<Node>(Point{px[k], py[k]}, nodes_[idx[k]]);
+                n->slot = (int64_t)(nodes_.size() + fresh.size());
+                fresh.push_back(n);
+                ax.push_back(px[k]);
+                ay.push_back(py[k]);
+                ayaw.push_back(n->get_yaw());
+                apar.push_back((int32_t)nodes_[idx[k]]->slot);
+            }
+            if (fresh.empty()) continue;
+            detail::check(pp_tree_append(detail::ctx(), fresh.size(), ax.data(), ay.data(), ayaw.data(), apar.data()),
+                          "tree_append");
+            nodes_.insert(nodes_.end(), fresh.begin(), fresh.end());
+            const size_t f = fresh.size();
+            std::vector<double> gx(f, goal_.x), gy(f, goal_.y), gyaw(f, goal_yaw_);
+            std::vector<uint8_t> reach(f);
+            detail::check(pp_collide_dubins(detail::ctx(), f, gx.data(), gy.data(), gyaw.data(), ax.data(), ay.data(),
+                                            ayaw.data(), steer, step_size_, reach.data(), 0),
+                          "collide_dubins");
+            std::vector<NodePtr> visible;
+            for (size_t k = 0; k < f; ++k)
+                if (reach[k]) visible.push_back(fresh[k]);
+            for (std::optional<LineString> &line : check_finish_many(visible)) {
+                if (!line) continue;
+                const double len = line->euclidean_length();
+                if (len < best_len) {
+                    best_len = len;
+                    best = std::move(line);
                 }
             }
         }

@@ -47,3 +47,11 @@ def test_example_rrt_on_reference_world_format(ctx, tmp_path):
     assert nodes > 1
     if "Path generated!" in out:
         assert "verify(path) = 1" in out
+    # the round-based planner of the C++ mirror (plan_rounds + check_finish_many) and its node-by-node self-check
+    out = subprocess.run([_bin("example_rrt"), str(p), "2000", "7", "256"], capture_output=True, text=True,
+                         check=True).stdout
+    m = re.search(r"check_finish_many agrees on (\d+) of (\d+) nodes", out)
+    assert m and m.group(1) == m.group(2) and int(m.group(2)) > 5, out[-400:]
+    assert int(re.search(r"tree nodes: (\d+)", out).group(1)) > 50
+    if "Path generated!" in out:
+        assert "verify(path) = 1" in out
