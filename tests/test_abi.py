@@ -38,6 +38,11 @@ def test_constants_match_header(pp):
     assert int(re.search(r"#define PP_ABI_VERSION (\d+)", src).group(1)) == pp._ffi.lib.pp_abi_version()
     assert pp._ffi.lib.pp_status_string(-2).decode().startswith("no sm_100")
     assert pp._ffi.WORDS == ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")  # ALL_PLANNERS order, src/dubins.rs:291
+    # method flags: the binding's constants are the header's enumerators
+    enums = dict(re.findall(r"\b(PP_(?:NN|COLLIDE)_[A-Z0-9_]+)\s*=\s*(\d+)", src))
+    for name, value in enums.items():
+        assert getattr(pp._ffi, name[3:]) == int(value), name
+    assert {"PP_NN_DEFAULT", "PP_NN_GRID", "PP_NN_SCAN", "PP_COLLIDE_DEFAULT", "PP_COLLIDE_SCAN"} <= set(enums)
 
 
 def test_no_cpu_fallback(pp):
