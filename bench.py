@@ -351,7 +351,21 @@ def cpu_baseline_leg(pp):
         t = time.perf_counter()
         O.dubins_eval_batch(*b, 1.0, want_flags=False)
         best = max(best, nall / (time.perf_counter() - t))
-    return {"value": best, "unit": "pairs/s", "cores": threads, "kind": "port",
+    # the second metric on the CPU: exact grid NN (the honest comparator for the reference's R-tree) + the
+    # culled straight-edge verify (per edge: every ring's box, then geo's predicates -- the reference has no broad phase)
+    mq = 1 << 16
+    qx, qy, nx, ny, _ = pp.synth.extend_inputs(mq, C4_NODES)
+    bounds, rings = pp.synth.circle_world(C4_RINGS)
+    W = O.OracleWorld(bounds, rings)
+    t = time.perf_counter()
+    oidx, _ = O.nn_grid(nx, ny, qx, qy)
+    t_nn = time.perf_counter() - t
+    W.verify_segments(qx, qy, nx[oidx], ny[oidx], culled=True)
+    t_ext = time.perf_counter() - t
+    extend = {"value": mq / t_ext, "unit": "steps/s", "cores": threads, "kind": "port", "nn_share": t_nn / t_ext,
+              "sample": "2^16 queries of the C4 workload vs the 2^20-node tree and 10 k rings: exact grid NN + culled "
+                        "Space::verify of the straight edge, all host threads"}
+    return {"value": best, "unit": "pairs/s", "cores": threads, "kind": "port", "extend": extend,
             "sample": "2^22 pairs of the C3 workload, all host threads (OpenMP static), best of 3; single thread on 2^20 pairs",
             "single_thread_value": single,
             "note": "C restatement of src/dubins.rs (oracle/pp_oracle.c, gcc -O2 -ffp-contract=off), not rustc output"}
@@ -424,6 +438,27 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
         }
         if kname == "nn_grid":
             out[name]["nn_grid_build_ms_after_upload"] = grid_build_ms
+            # the same step end to end through the host C-ABI call (pp_rrt_extend on pinned host buffers: 16 B in and
+            # 13 B out per query cross PCIe inside the timed region); wall clock, max over ranks
+            hq = [pp.PinnedArray(m, np.float64) for _ in range(2)]
+            hq[0].array[:] = qx.cpu().numpy()
+            hq[1].array[:] = qy.cpu().numpy()
+            ho = (pp.PinnedArray(m, np.uint32), pp.PinnedArray(m, np.float64), pp.PinnedArray(m, np.uint8))
+            outs = tuple(h.array for h in ho)
+            ctx.rrt_extend(hq[0].array, hq[1].array, out=outs)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                ctx.rrt_extend(hq[0].array, hq[1].array, out=outs)
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            out[name]["e2e"] = {"value": world * m * steps / float(dt.item()), "unit": "steps/s",
+                                "h2d_bytes_per_step": 16 * m, "d2h_bytes_per_step": 13 * m,
+                                "matches_device_run": bool(np.array_equal(outs[0].astype(np.int32), idx.cpu().numpy())
+                                                           and np.array_equal(outs[2], ok.cpu().numpy()))}
     # the same step with the reference's real edge geometry: Dubins curve new node -> nearest node, sampled at 0.1
     fn = lambda: ctx.rrt_extend_dubins_dev(m, qx, qy, 0.8, 0.1, idx, yaw, ok)  # noqa: E731
     ctx.timing_enable(True)
