@@ -110,3 +110,51 @@ def test_two_rank_gloo_sharding(pp, O, tmp_path):
     qy = pp.synth.uniform(pp.synth.SEED_C4_Q, 1, 4001, 0.0, 100.0)
     want, _ = O.nn_brute(nx, ny, qx, qy)
     assert np.array_equal(got, want)  # sharded run is byte-identical to the single-process run
+
+
+class _FakeCtx:
+    """stands in for the GPU context: verdicts are a deterministic function of each edge's coordinates, so the batched
+    and the node-by-node code paths must see the same answers (pure host-logic test, no device)"""
+
+    def __init__(self):
+        self.calls = 0
+
+    def obstacles_upload(self, *a):
+        pass
+
+    def tree_upload(self, *a):
+        pass
+
+    def tree_append(self, *a):
+        pass
+
+    def collide_dubins(self, sx, sy, syaw, ex, ey, eyaw, radius, step):
+        self.calls += 1
+        v = np.asarray(sx) * 12.9898 + np.asarray(sy) * 78.233 + np.asarray(ex) * 37.719 + np.asarray(ey) * 4.581
+        return ((np.sin(v) * 43758.5453) % 1.0 < 0.55).astype(np.uint8)
+
+
+def test_batched_optimize_matches_recursive_optimize_on_the_host(pp):
+    """RRT._optimize_many (all nodes of a round, level by level) picks what RRT.optimize picks node by node"""
+    r = pp.rrt
+    ctx = _FakeCtx()
+    bounds = (np.array([0.0, 0.0, 50.0, 50.0, 0.0]), np.array([0.0, 50.0, 50.0, 0.0, 0.0]))
+    space = r.Space(bounds, r.Robot(1.0, 1.0, 0.8), [], ctx=ctx, seed=3)
+    planner = r.RRT((1.0, 1.0), 0.0, (49.0, 49.0), 0.0, 100, 0.1, space)
+    rng = np.random.default_rng(5)
+    nodes = [planner.nodes[0]]
+    for _ in range(120):  # a random tree: every new node hangs off a random earlier one
+        nodes.append(r.Node((float(rng.uniform(0, 50)), float(rng.uniform(0, 50))), nodes[int(rng.integers(0, len(nodes)))]))
+    picks = nodes[1:]
+    many = planner._optimize_many(picks)
+    batched_calls = ctx.calls
+    assert batched_calls <= r.RECURSION_LIMIT
+    found = 0
+    for n, a in zip(picks, many):
+        b = planner.optimize(n, 0)
+        assert (a is None) == (b is None)
+        if a is not None:
+            found += 1
+            assert [v.point for v in r.NodeIter(a)] == [v.point for v in r.NodeIter(b)]
+    assert found > 10 and ctx.calls > batched_calls * 5
+    assert planner._optimize_many([]) == []
