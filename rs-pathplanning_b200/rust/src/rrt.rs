@@ -96,6 +96,30 @@ impl Space {
         ok != 0
     }
 
+    /// `verify` for many lines in one launch (one warp per line); same verdicts as mapping `verify`
+    pub fn verify_many(&self, lines: &[LineString<f64>]) -> Vec<bool> {
+        if lines.is_empty() {
+            return vec![];
+        }
+        let (mut px, mut py, mut off) = (Vec::<f64>::new(), Vec::<f64>::new(), vec![0u32]);
+        for l in lines {
+            for p in l.points_iter() {
+                let (x, y) = p.x_y();
+                px.push(x);
+                py.push(y);
+            }
+            off.push(px.len() as u32);
+        }
+        let mut ok = vec![0u8; lines.len()];
+        ffi::check(
+            unsafe {
+                ffi::pp_verify_polylines(CTX.0, lines.len(), px.as_ptr(), py.as_ptr(), off.as_ptr(), ok.as_mut_ptr(), 0)
+            },
+            "verify_many",
+        );
+        ok.iter().map(|&v| v != 0).collect()
+    }
+
     pub fn rand_point(&self) -> Point<f64> {
         let mut rng = thread_rng();
         Point::new(rng.gen_range(self.minx, self.maxx), rng.gen_range(self.miny, self.maxy))
@@ -163,6 +187,29 @@ fn chain_edges(node: &Arc<Node>) -> [Vec<f64>; 6] {
         }
     }
     e
+}
+
+fn push_edge(e: &mut [Vec<f64>; 6], from: &Node, to: &Node) {
+    let (sx, sy) = from.get_point().x_y();
+    let (ex, ey) = to.get_point().x_y();
+    e[0].push(sx); e[1].push(sy); e[2].push(from.get_yaw());
+    e[3].push(ex); e[4].push(ey); e[5].push(to.get_yaw());
+}
+
+/// fused Dubins sample-and-verify of m independent edges: ok[i] = Space::verify(samples of edge i ++ [its end point])
+fn collide_dubins(e: &[Vec<f64>; 6], turn_radius: f64, step_size: f64) -> Vec<u8> {
+    let m = e[0].len();
+    let mut ok = vec![0u8; m];
+    if m > 0 {
+        ffi::check(
+            unsafe {
+                ffi::pp_collide_dubins(CTX.0, m, e[0].as_ptr(), e[1].as_ptr(), e[2].as_ptr(), e[3].as_ptr(),
+                                       e[4].as_ptr(), e[5].as_ptr(), turn_radius, step_size, ok.as_mut_ptr(), 0)
+            },
+            "collide_dubins",
+        );
+    }
+    ok
 }
 
 /// per-edge Dubins samples of the chain in node -> root order: one count pass + one fill pass on the GPU
@@ -255,16 +302,7 @@ impl RRT {
         if m == 0 {
             return self.space.verify(&vec![node.get_coord().x_y()].into());
         }
-        let mut ok = vec![0u8; m];
-        ffi::check(
-            unsafe {
-                ffi::pp_collide_dubins(CTX.0, m, e[0].as_ptr(), e[1].as_ptr(), e[2].as_ptr(), e[3].as_ptr(),
-                                       e[4].as_ptr(), e[5].as_ptr(), self.space.get_steer(), self.step_size,
-                                       ok.as_mut_ptr(), 0)
-            },
-            "collide_dubins",
-        );
-        ok.iter().all(|&v| v != 0)
+        collide_dubins(&e, self.space.get_steer(), self.step_size).iter().all(|&v| v != 0)
     }
 
     pub fn check_finish(&self, node: Arc<Node>) -> Option<LineString<f64>> {
@@ -288,6 +326,97 @@ impl RRT {
             }
         }
         None
+    }
+
+    /// `optimize` (src/rrt.rs:463-487) for MANY start nodes: the shortcut candidates of all nodes of a recursion
+    /// level go into one fused launch.  verify(line_to_origin(candidate k)) = verify(edge candidate -> chain[k])
+    /// AND verify(chain of chain[k]), and the chain verdicts are suffix-ANDs over the ancestors' own edges, so
+    /// 2*depth - 1 edges per node replace depth^2.  Per node: the same candidates, root-first order and verdicts.
+    pub fn optimize_many(&self, nodes: &[Arc<Node>], i: usize) -> Vec<Option<Arc<Node>>> {
+        if i >= RECURSION_LIMIT || nodes.is_empty() {
+            return vec![None; nodes.len()];
+        }
+        let chains: Vec<Vec<Arc<Node>>> =
+            nodes.iter().map(|n| (NodeIter { curr: Some(n.clone()) }).collect()).collect(); // node, parent, ..., root
+        let cands: Vec<Vec<Arc<Node>>> = nodes
+            .iter()
+            .zip(chains.iter())
+            .map(|(n, ch)| ch.iter().map(|to| Arc::new(Node::new(n.get_coord().into(), to.clone()))).collect())
+            .collect();
+        let mut e: [Vec<f64>; 6] = Default::default();
+        let mut spans: Vec<(usize, usize)> = Vec::with_capacity(nodes.len());
+        for (ch, cd) in chains.iter().zip(cands.iter()) {
+            spans.push((e[0].len(), ch.len()));
+            for (c, to) in cd.iter().zip(ch.iter()) {
+                push_edge(&mut e, c, to); // candidate -> chain[k]
+            }
+            for v in ch.iter().take(ch.len() - 1) {
+                let p = v.get_parent().expect("only the root has no parent");
+                push_edge(&mut e, v, &p); // chain[k] -> chain[k + 1]
+            }
+        }
+        let ok = collide_dubins(&e, self.space.get_steer(), self.step_size);
+        let mut picks: Vec<Option<usize>> = Vec::with_capacity(nodes.len());
+        for &(a, n) in spans.iter() {
+            // .rev(): the valid candidate closest to the root wins; walking down from the root, the chain below
+            // candidate k is good while every own edge k.. verified
+            let mut pick = None;
+            for k in (0..n).rev() {
+                if k + 1 < n && ok[a + n + k] == 0 {
+                    break;
+                }
+                if ok[a + k] != 0 {
+                    pick = Some(k);
+                    break;
+                }
+            }
+            picks.push(pick);
+        }
+        let live: Vec<usize> = (0..nodes.len()).filter(|&j| picks[j].is_some()).collect();
+        let next: Vec<Arc<Node>> = live.iter().map(|&j| chains[j][picks[j].unwrap()].clone()).collect();
+        let deeper = self.optimize_many(&next, i + 1);
+        let mut out: Vec<Option<Arc<Node>>> = vec![None; nodes.len()];
+        for (&j, d) in live.iter().zip(deeper.into_iter()) {
+            out[j] = Some(match d {
+                Some(to_node) => Arc::new(Node::new(nodes[j].get_coord().into(), to_node)),
+                None => cands[j][picks[j].unwrap()].clone(),
+            });
+        }
+        out
+    }
+
+    /// `check_finish` (src/rrt.rs:428-438) for many nodes: batched optimize, ONE count + fill over the edges of all
+    /// final chains, ONE verify launch.  Same lines as mapping `check_finish`.
+    pub fn check_finish_many(&self, nodes: &[Arc<Node>]) -> Vec<Option<LineString<f64>>> {
+        if nodes.is_empty() {
+            return vec![];
+        }
+        let opt = self.optimize_many(nodes, 0);
+        let tops: Vec<Arc<Node>> = nodes
+            .iter()
+            .zip(opt.into_iter())
+            .map(|(n, o)| Arc::new(Node::new_goal(self.goal.into(), o.unwrap_or_else(|| n.clone()), self.goal_yaw)))
+            .collect();
+        let mut e: [Vec<f64>; 6] = Default::default();
+        let mut spans: Vec<(usize, usize)> = Vec::with_capacity(tops.len());
+        for t in tops.iter() {
+            let te = chain_edges(t);
+            spans.push((e[0].len(), te[0].len()));
+            for c in 0..6 {
+                e[c].extend_from_slice(&te[c]);
+            }
+        }
+        let per_edge = chain_samples(&e, self.space.get_steer(), self.step_size);
+        let lines: Vec<LineString<f64>> = spans
+            .iter()
+            .map(|&(a, n)| {
+                let mut l: Vec<(f64, f64)> = per_edge[a..a + n].iter().flatten().cloned().collect();
+                l.reverse(); // the root contributes nothing (None => vec![], src/rrt.rs:532); start -> goal
+                l.into()
+            })
+            .collect();
+        let good = self.space.verify_many(&lines);
+        lines.into_iter().zip(good.into_iter()).map(|(l, g)| if g { Some(l) } else { None }).collect()
     }
 
     pub fn optimize_from_goal(&self, goal_node: Arc<Node>) -> Arc<Node> {
@@ -331,9 +460,75 @@ impl RRT {
         None
     }
 
+    /// SURVEY 8f-3.  The reference runs max_iter independent plan_one iterations on 4 racy workers that all see a
+    /// slightly stale tree (src/rrt.rs:600-609).  Here a ROUND takes `batch` samples against one tree snapshot: one
+    /// call for NN + Node::new yaw + fused Dubins sample-and-verify of the new edges (the parents' chains are
+    /// verified already: the tree invariant), one batched append, one fused launch for the goal connections and
+    /// the batched goal check for the nodes that see the goal.  min_by length stays on the host (:611-617).
+    pub fn plan_rounds(&self, batch: usize) -> Option<LineString<f64>> {
+        let steer = self.space.get_steer();
+        let mut best: Option<(f64, LineString<f64>)> = None;
+        let mut budget = self.max_iter;
+        while budget > 0 {
+            let b = batch.max(1).min(budget);
+            budget -= b;
+            let pts: Vec<Point<f64>> = (0..b).map(|_| self.space.rand_point()).collect();
+            let (px, py): (Vec<f64>, Vec<f64>) = pts.iter().map(|p| p.x_y()).unzip();
+            let (mut idx, mut yaw, mut ok) = (vec![0u32; b], vec![0f64; b], vec![0u8; b]);
+            ffi::check(
+                unsafe {
+                    ffi::pp_rrt_extend_dubins(CTX.0, b, px.as_ptr(), py.as_ptr(), steer, self.step_size,
+                                              idx.as_mut_ptr(), yaw.as_mut_ptr(), ok.as_mut_ptr(), 0, 0)
+                },
+                "rrt_extend_dubins",
+            );
+            let mut nodes = self.nodes.lock().unwrap();
+            let fresh: Vec<Arc<Node>> = (0..b)
+                .filter(|&k| ok[k] != 0 && idx[k] != 0xFFFF_FFFF)
+                .map(|k| Arc::new(Node::new(pts[k], nodes[idx[k] as usize].clone())))
+                .collect();
+            if fresh.is_empty() {
+                continue;
+            }
+            let (mut fx, mut fy, mut fyaw, mut fpar) =
+                (Vec::<f64>::new(), Vec::<f64>::new(), Vec::<f64>::new(), Vec::<i32>::new());
+            for c in fresh.iter() {
+                let (x, y) = c.get_point().x_y();
+                fx.push(x);
+                fy.push(y);
+                fyaw.push(c.get_yaw());
+                fpar.push(c.get_parent().map(|p| *p.slot.lock().unwrap() as i32).unwrap_or(-1));
+            }
+            ffi::check(
+                unsafe { ffi::pp_tree_append(CTX.0, fresh.len(), fx.as_ptr(), fy.as_ptr(), fyaw.as_ptr(), fpar.as_ptr()) },
+                "tree_append",
+            );
+            for c in fresh.iter() {
+                *c.slot.lock().unwrap() = nodes.len() as i64;
+                nodes.push(c.clone());
+            }
+            drop(nodes);
+            // goal -> node for every fresh node in one launch; only the nodes that see the goal are finalized
+            let goal_node = Node::new_root(self.goal.into(), self.goal_yaw);
+            let mut e: [Vec<f64>; 6] = Default::default();
+            for c in fresh.iter() {
+                push_edge(&mut e, &goal_node, c);
+            }
+            let g_ok = collide_dubins(&e, steer, self.step_size);
+            let reach: Vec<Arc<Node>> =
+                fresh.iter().zip(g_ok.iter()).filter(|p| *p.1 != 0).map(|p| p.0.clone()).collect();
+            for line in self.check_finish_many(&reach).into_iter().flatten() {
+                let len = line.euclidean_length();
+                if best.as_ref().map_or(true, |cur| len < cur.0) {
+                    best = Some((len, line));
+                }
+            }
+        }
+        best.map(|found| found.1)
+    }
+
     pub fn plan(&self) -> Option<LineString<f64>> {
-        // sequential: the GPU context serialises calls anyway; batching B samples per round is the
-        // "next" item of SURVEY.md section 8(f)
+        // sequential, one sample per iteration as in the reference; plan_rounds() is the batched form
         (0..self.max_iter)
             .filter_map(|_| self.plan_one())
             .min_by(|a, b| a.euclidean_length().partial_cmp(&b.euclidean_length()).expect("should compared route costs"))
