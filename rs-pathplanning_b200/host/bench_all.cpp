@@ -42,7 +42,7 @@ static void run(const char *name, double warm, double meas, F &&f) {
         ++it;
         el = std::chrono::duration<double>(Clock::now() - t0).count();
     } while (el < meas);
-    std::printf("%-34s time: %12.3f us/iter  (%zu iterations)\n", name, el / it * 1e6, it);
+    std::printf("%-34s time: %12.3f us/iter  (%zu iterations)\n", name, el / (double)it * 1e6, it);
 }
 
 int main(int argc, char **argv) {
