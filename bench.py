@@ -31,6 +31,7 @@ W_INSTR_PER_PAIR = 1100.0  # fixed yard-stick of SURVEY.md Appendix D (FP64-pipe
 BYTES_PER_PAIR = 57.0      # 48 B read + 8 B cost + 1 B word
 NCU_FP64_INSTR_PER_PAIR = 490.0  # DFMA + DADD + DMUL + DSETP executed per pair (ncu source page, same capture)
 NCU_DRAM_BYTES_PER_LAUNCH = 949.3e6  # measured once per kernel change by ncu (see profiles/r01_summary.md)
+NCU_NN_GRID_L2_BYTES = 25431908 * 32.0  # lts__t_sectors.sum x 32 B, pp_nn_grid_kernel on 2^20 queries / 2^20 nodes
 FP64_PEAK_NOMINAL = 148 * 64 * 1.965e9  # lanes * clock: used only if the live DFMA measurement fails
 C4_M, C4_NODES, C4_RINGS = 1 << 20, 1 << 20, 10_000
 C5_EDGES, C5_RINGS = 1 << 19, 100_000  # the per-GPU slice of config 5 (2^22 edges over 8 GPUs)
@@ -434,7 +435,12 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
                          {"kernel": kname, "bound": "hbm", "achieved": 36.0 * 2 ** 20 / nn_s / 1e9, "peak": hbm_peak,
                           "unit": "GB/s", "frac": 36.0 * 2 ** 20 / nn_s / 1e9 / hbm_peak,
                           "per_unit": "36 MiB algorithmic bytes per launch (queries + nodes + indices); the search is a "
-                                      "latency-bound gather, not a stream"}),
+                                      "latency-bound gather, not a stream",
+                          # what actually bounds it (ncu --set full, profiles/r01_rrt_kernels_final6_raw.csv): 25.4 M L2
+                          # sectors per launch of 2^20 queries, l1tex throughput 78 %, lts throughput 60 %
+                          "l2_view": {"l2_bytes_per_launch_ncu": NCU_NN_GRID_L2_BYTES, "unit": "GB/s",
+                                      "achieved": NCU_NN_GRID_L2_BYTES / nn_s / 1e9, "l1tex_throughput_ncu": 0.777,
+                                      "lts_throughput_ncu": 0.602}}),
         }
         if kname == "nn_grid":
             out[name]["nn_grid_build_ms_after_upload"] = grid_build_ms
