@@ -363,9 +363,16 @@ def cpu_baseline_leg(pp):
     t_nn = time.perf_counter() - t
     W.verify_segments(qx, qy, nx[oidx], ny[oidx], culled=True)
     t_ext = time.perf_counter() - t
+    mb = 1 << 11  # exact brute force, what the tiled GPU scans do: 2^11 x 2^20 pair evaluations
+    t = time.perf_counter()
+    bidx, _ = O.nn_brute(nx, ny, qx[:mb], qy[:mb])
+    t_brute = time.perf_counter() - t
     extend = {"value": mq / t_ext, "unit": "steps/s", "cores": threads, "kind": "port", "nn_share": t_nn / t_ext,
+              "nn_grid_queries_per_s": mq / t_nn, "nn_brute_queries_per_s": mb / t_brute,
+              "nn_brute_matches_grid": bool(np.array_equal(bidx, oidx[:mb])),
               "sample": "2^16 queries of the C4 workload vs the 2^20-node tree and 10 k rings: exact grid NN + culled "
-                        "Space::verify of the straight edge, all host threads"}
+                        "Space::verify of the straight edge, all host threads; nn_brute: the first 2^11 of those queries by "
+                        "exact brute force (SURVEY 8d asks for both NN comparators)"}
     return {"value": best, "unit": "pairs/s", "cores": threads, "kind": "port", "extend": extend,
             "sample": "2^22 pairs of the C3 workload, all host threads (OpenMP static), best of 3; single thread on 2^20 pairs",
             "single_thread_value": single,
