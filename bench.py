@@ -455,7 +455,13 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
                           "unit": "Ginstr/s", "frac": pair_evals * 6.0 / nn_s / fp64_peak,
                           "per_unit": "6 FP64-pipe instructions per (query, node) pair (SURVEY 8d yard-stick)",
                           "hbm_view": {"achieved": 36.0 * 2 ** 20 / nn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                       "per_unit": "36 MiB algorithmic bytes per launch"}} if kname != "nn_grid" else
+                                       "per_unit": "36 MiB algorithmic bytes per launch"},
+                          # SURVEY 8d "report both": node tiles streamed L2 -> shared memory by TMA, m/Q x N x tile
+                          # bytes per node with Q = 512 queries per CTA (20 B per node: x, y, fl32(x); the bucketed
+                          # kernel streams only the 8 B fp32 copies)
+                          "streamed_view": {"bytes_per_launch": m / 512.0 * C4_NODES * (8.0 if kname == "nn_scan" else 20.0),
+                                            "achieved": m / 512.0 * C4_NODES * (8.0 if kname == "nn_scan" else 20.0) / nn_s / 1e9,
+                                            "unit": "GB/s"}} if kname != "nn_grid" else
                          {"kernel": kname, "bound": "hbm", "achieved": 36.0 * 2 ** 20 / nn_s / 1e9, "peak": hbm_peak,
                           "unit": "GB/s", "frac": 36.0 * 2 ** 20 / nn_s / 1e9 / hbm_peak,
                           "per_unit": "36 MiB algorithmic bytes per launch (queries + nodes + indices); the search is a "
