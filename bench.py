@@ -380,11 +380,17 @@ def cpu_baseline_leg(pp):
     t_nn = time.perf_counter() - t
     W.verify_segments(qx, qy, nx[oidx], ny[oidx], culled=True)
     t_ext = time.perf_counter() - t
+    m1 = 1 << 13  # the same step on one thread
+    t = time.perf_counter()
+    i1, _ = O.nn_grid(nx, ny, qx[:m1], qy[:m1], nthreads=1)
+    W.verify_segments(qx[:m1], qy[:m1], nx[i1], ny[i1], culled=True, nthreads=1)
+    t_single = time.perf_counter() - t
     mb = 1 << 11  # exact brute force, what the tiled GPU scans do: 2^11 x 2^20 pair evaluations
     t = time.perf_counter()
     bidx, _ = O.nn_brute(nx, ny, qx[:mb], qy[:mb])
     t_brute = time.perf_counter() - t
     extend = {"value": mq / t_ext, "unit": "steps/s", "cores": threads, "kind": "port", "nn_share": t_nn / t_ext,
+              "single_thread_value": m1 / t_single,
               "nn_grid_queries_per_s": mq / t_nn, "nn_brute_queries_per_s": mb / t_brute,
               "nn_brute_matches_grid": bool(np.array_equal(bidx, oidx[:mb])),
               "sample": "2^16 queries of the C4 workload vs the 2^20-node tree and 10 k rings: exact grid NN + culled "

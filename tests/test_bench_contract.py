@@ -55,3 +55,4 @@ def test_cpu_baseline_leg_has_the_contract_keys(pp):
     ext = cb["extend"]
     assert ext["unit"] == "steps/s" and ext["value"] > 0 and ext["nn_brute_matches_grid"] is True
     assert ext["nn_grid_queries_per_s"] > ext["nn_brute_queries_per_s"] > 0
+    assert 0 < ext["single_thread_value"] <= ext["value"] * 2
