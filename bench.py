@@ -399,7 +399,7 @@ def cpu_baseline_leg(pp):
     return {"value": best, "unit": "pairs/s", "cores": threads, "kind": "port", "extend": extend,
             "sample": "2^22 pairs of the C3 workload, all host threads (OpenMP static), best of 3; single thread on 2^20 pairs",
             "single_thread_value": single,
-            "note": "C restatement of src/dubins.rs (oracle/pp_oracle.c, gcc -O2 -ffp-contract=off), not rustc output"}
+            "note": "C restatement of src/dubins.rs (oracle/pp_oracle.c, gcc -O3 -ffp-contract=off -fno-fast-math), not rustc output"}
 
 
 def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak):

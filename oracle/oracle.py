@@ -37,7 +37,7 @@ def build(force: bool = False) -> str:
     r = subprocess.run(["make", "-C", _HERE, "-B"], capture_output=True, text=True)
     if r.returncode != 0:
         # fall back to a build without OpenMP (single-threaded baseline) rather than no oracle at all
-        r2 = subprocess.run(["gcc", "-O2", "-std=c11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared",
+        r2 = subprocess.run(["gcc", "-O3", "-std=c11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared",
                              "-o", _LIB_PATH, os.path.join(_HERE, "pp_oracle.c"), "-lm"],
                             capture_output=True, text=True)
         if r2.returncode != 0:

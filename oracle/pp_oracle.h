@@ -15,7 +15,7 @@
  * agree bit-for-bit, and (ii) the restatement-derived known answers of
  * SURVEY.md Appendix C.
  *
- * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp (see oracle/Makefile).
+ * Build: gcc -O3 -ffp-contract=off -fno-fast-math -fopenmp (see oracle/Makefile).
  * glibc libm is the same libm Rust's f64::{sin,cos,atan2,acos,hypot} reach on
  * x86_64-unknown-linux-gnu, and no a*b+c is ever contracted, as in rustc.
  */
