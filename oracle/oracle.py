@@ -19,7 +19,8 @@ _LIB_PATH = os.path.join(_HERE, "libpp_oracle.so")
 
 WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
 NONE = 0xFF
-FLAG_NEAR_WRAP, FLAG_NEAR_TIE, FLAG_NEAR_FEAS = 1, 2, 4
+FLAG_NEAR_WRAP, FLAG_NEAR_TIE, FLAG_NEAR_FEAS, FLAG_NEAR_COUNT, FLAG_NEAR_GRAZE, FLAG_HUGE_ANGLE = 1, 2, 4, 8, 16, 32
+GRAZE_TOL = 1e-8  # margin below GRAZE_TOL * max(1, |coordinates|) => a 1e-9-accurate implementation may flip the verdict
 
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
@@ -74,6 +75,10 @@ def lib():
     L.ppo_dubins_path.restype = C.c_long
     L.ppo_dubins_path.argtypes = [d] * 8 + [C.c_int, _dp, _dp, _dp, sz, C.POINTER(C.c_int), _dp,
                                             C.POINTER(C.c_long)]
+    L.ppo_dubins_word_margin.restype = d
+    L.ppo_dubins_word_margin.argtypes = [C.c_int, d, d, d]
+    L.ppo_dubins_path_flags.restype = C.c_long
+    L.ppo_dubins_path_flags.argtypes = [d] * 8 + [C.c_int, _dp, _dp, _dp, sz, C.POINTER(C.c_int), _dp, _u32p]
     L.ppo_dubins_count_batch.restype = None
     L.ppo_dubins_count_batch.argtypes = [sz] + [_dp] * 6 + [d, d, _i64p, C.c_int]
     L.ppo_create_circle.restype = C.c_long
@@ -101,6 +106,17 @@ def lib():
     L.ppo_dubins_edge_polyline.argtypes = [d] * 8 + [_dp, _dp, sz]
     L.ppo_verify_dubins_edges.restype = None
     L.ppo_verify_dubins_edges.argtypes = [wp, sz] + [_dp] * 6 + [d, d, _u8p, C.c_int, C.c_int]
+    L.ppo_verify_margin.restype = C.c_int
+    L.ppo_verify_margin.argtypes = [wp, _dp, _dp, sz, _dp]
+    L.ppo_verify_dubins_edges_flags.restype = None
+    L.ppo_verify_dubins_edges_flags.argtypes = [wp, sz] + [_dp] * 6 + [d, d, d, _u8p, _u32p, _dp, C.c_int]
+    L.ppo_optimize.restype = C.c_long
+    L.ppo_optimize.argtypes = [wp, sz, _dp, _dp, _dp, _i32p, C.c_uint32, d, d, d, _dp, _dp, _dp, sz, _u32p,
+                               C.POINTER(C.c_long)]
+    L.ppo_check_finish.restype = C.c_long
+    L.ppo_check_finish.argtypes = [wp, sz, _dp, _dp, _dp, _i32p, C.c_uint32, d, d, d, d, d, d, _dp, _dp, sz,
+                                   C.POINTER(C.c_long), _dp, _dp, _dp, sz, C.POINTER(C.c_long), _u32p,
+                                   C.POINTER(C.c_long)]
     L.ppo_line_to_origin.restype = C.c_long
     L.ppo_line_to_origin.argtypes = [_dp, _dp, _dp, _i32p, C.c_uint32, d, d, _dp, _dp, sz]
     L.ppo_uniform.restype = d
@@ -188,6 +204,24 @@ def dubins_path(sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin=False):
         return Path(px[:n].copy(), py[:n].copy(), pyaw[:n].copy(), w.value, c.value, npnt.value)
 
 
+def dubins_word_margin(word: int, alpha: float, beta: float, d: float) -> float:
+    return float(lib().ppo_dubins_word_margin(word, alpha, beta, d))
+
+
+def dubins_path_flags(sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin=False):
+    """(sample count or -1 for None, harness flags) of one path"""
+    cap = 4096
+    while True:
+        px, py = np.empty(cap), np.empty(cap)
+        fl = C.c_uint32()
+        n = lib().ppo_dubins_path_flags(sx, sy, syaw, ex, ey, eyaw, radius, step, int(from_origin), _p(px), _p(py),
+                                        None, cap, None, None, C.byref(fl))
+        if n == -2:
+            cap *= 4
+            continue
+        return int(n), int(fl.value)
+
+
 def dubins_count_batch(sx, sy, syaw, ex, ey, eyaw, radius, step, nthreads=0):
     sx, sy, syaw, ex, ey, eyaw = map(_f64, (sx, sy, syaw, ex, ey, eyaw))
     n = sx.size
@@ -266,6 +300,24 @@ class OracleWorld:
         f = lib().ppo_verify_culled if culled else lib().ppo_verify
         return bool(f(C.byref(self.w), _p(lx), _p(ly), lx.size))
 
+    def verify_margin(self, lx, ly):
+        """(verdict, margin): how far the vertices may move without changing the verdict (harness, not reference)"""
+        lx, ly = _f64(lx), _f64(ly)
+        m = C.c_double()
+        v = lib().ppo_verify_margin(C.byref(self.w), _p(lx), _p(ly), lx.size, C.byref(m))
+        return bool(v), m.value
+
+    def verify_dubins_edges_flags(self, sx, sy, syaw, ex, ey, eyaw, radius, step, graze_tol=GRAZE_TOL, nthreads=0):
+        """(ok, flags, margins): verdicts with the classification flags of the parity harness"""
+        sx, sy, syaw, ex, ey, eyaw = map(_f64, (sx, sy, syaw, ex, ey, eyaw))
+        ok = np.empty(sx.size, np.uint8)
+        flags = np.zeros(sx.size, np.uint32)
+        margins = np.empty(sx.size, np.float64)
+        lib().ppo_verify_dubins_edges_flags(C.byref(self.w), sx.size, _p(sx), _p(sy), _p(syaw), _p(ex), _p(ey),
+                                            _p(eyaw), float(radius), float(step), float(graze_tol), _p(ok, _u8p),
+                                            _p(flags, _u32p), _p(margins), int(nthreads))
+        return ok, flags, margins
+
     def verify_segments(self, ax, ay, bx, by, culled=False, nthreads=0):
         ax, ay, bx, by = map(_f64, (ax, ay, bx, by))
         ok = np.empty(ax.size, np.uint8)
@@ -279,6 +331,60 @@ class OracleWorld:
         lib().ppo_verify_dubins_edges(C.byref(self.w), sx.size, _p(sx), _p(sy), _p(syaw), _p(ex), _p(ey), _p(eyaw),
                                       float(radius), float(step), _p(ok, _u8p), int(culled), int(nthreads))
         return ok
+
+
+def _tree(nx, ny, nyaw, parent):
+    return _f64(nx), _f64(ny), _f64(nyaw), np.ascontiguousarray(parent, np.int32)
+
+
+def optimize(world, nx, ny, nyaw, parent, node, radius, step, graze_tol=GRAZE_TOL):
+    """RRT::optimize(node, 0) over a flat tree: (chain poses [(x, y, yaw)] new node -> root or None, flags, verifies)"""
+    nx, ny, nyaw, parent = _tree(nx, ny, nyaw, parent)
+    cap = 4096
+    while True:
+        cx, cy, cyaw = np.empty(cap), np.empty(cap), np.empty(cap)
+        fl, nv = C.c_uint32(), C.c_long()
+        n = lib().ppo_optimize(C.byref(world.w), nx.size, _p(nx), _p(ny), _p(nyaw), _p(parent, _i32p), int(node),
+                               radius, step, graze_tol, _p(cx), _p(cy), _p(cyaw), cap, C.byref(fl), C.byref(nv))
+        if n == -2:
+            cap *= 4
+            continue
+        if n < 0:
+            raise RuntimeError("oracle optimize failed")
+        chain = None if n == 0 else np.stack([cx[:n], cy[:n], cyaw[:n]], 1)
+        return chain, int(fl.value), int(nv.value)
+
+
+@dataclass
+class Finish:
+    line: tuple       # (x, y) of the finalized line, start -> goal, whether or not it verifies
+    ok: bool          # check_finish returned Some(line)
+    chain: np.ndarray  # optimised chain goal -> root as (x, y, yaw) rows
+    flags: int
+    verifies: int
+
+
+def check_finish(world, nx, ny, nyaw, parent, node, goal, goal_yaw, radius, step, graze_tol=GRAZE_TOL):
+    """RRT::check_finish(node) over a flat tree (src/rrt.rs:428-438 via finalize / optimize_from_goal)"""
+    nx, ny, nyaw, parent = _tree(nx, ny, nyaw, parent)
+    cap, ccap = 1 << 16, 4096
+    while True:
+        lx, ly = np.empty(cap), np.empty(cap)
+        cx, cy, cyaw = np.empty(ccap), np.empty(ccap), np.empty(ccap)
+        fl, nv, ln, cn = C.c_uint32(), C.c_long(), C.c_long(), C.c_long()
+        r = lib().ppo_check_finish(C.byref(world.w), nx.size, _p(nx), _p(ny), _p(nyaw), _p(parent, _i32p), int(node),
+                                   float(goal[0]), float(goal[1]), float(goal_yaw), radius, step, graze_tol, _p(lx),
+                                   _p(ly), cap, C.byref(ln), _p(cx), _p(cy), _p(cyaw), ccap, C.byref(cn),
+                                   C.byref(fl), C.byref(nv))
+        if r == -2:
+            cap *= 4
+            ccap *= 4
+            continue
+        if r == -3:
+            raise RuntimeError("reference would panic (finalize: no Dubins word)")
+        n, c = ln.value, cn.value
+        return Finish((lx[:n].copy(), ly[:n].copy()), r >= 0, np.stack([cx[:c], cy[:c], cyaw[:c]], 1),
+                      int(fl.value), int(nv.value))
 
 
 def ring_has_point(rx, ry, px, py):

@@ -131,6 +131,21 @@ int ppo_dubins_word(int word, double alpha, double beta, double d, double tpq[3]
     return 0;
 }
 
+/* HARNESS: signed distance of a word's feasibility test from flipping, relative to 1 + d^2
+ * (CSC: p^2 >= 0, src/dubins.rs:38,61,82,103; CCC: |tmp| <= 1, :124,144) */
+double ppo_dubins_word_margin(int word, double alpha, double beta, double d) {
+    double sa = sin(alpha), sb = sin(beta), c_ab = cos(alpha - beta), m = 0.0;
+    switch (word) {
+    case PPO_LSL: m = 2.0 + d * d - 2.0 * c_ab + 2.0 * d * (sa - sb); break;
+    case PPO_RSR: m = 2.0 + d * d - 2.0 * c_ab + 2.0 * d * (sb - sa); break;
+    case PPO_LSR: m = -2.0 + d * d + 2.0 * c_ab + 2.0 * d * (sa + sb); break;
+    case PPO_RSL: m = -2.0 + d * d + 2.0 * c_ab - 2.0 * d * (sa + sb); break;
+    case PPO_RLR: m = 1.0 - fabs((6.0 - d * d + 2.0 * c_ab + 2.0 * d * (sa - sb)) / 8.0); break;
+    case PPO_LRL: m = 1.0 - fabs((6.0 - d * d + 2.0 * c_ab + 2.0 * d * (-sa + sb)) / 8.0); break;
+    }
+    return m / (1.0 + d * d);
+}
+
 /* segment modes per word: 0 = L, 1 = S, 2 = R  (src/dubins.rs:26,50,73,94,115,135) */
 static const int WORD_MODES[6][3] = {{0, 1, 0}, {2, 1, 2}, {0, 1, 2}, {2, 1, 0}, {2, 0, 2}, {0, 2, 0}};
 
@@ -276,9 +291,14 @@ static void interpolate(long ind, double length, int mode, double max_curvature,
 /* src/dubins.rs:200-289.  Buffers are zero-initialised with n_point entries.
  * Returns the trimmed length, or -3 if an index reaches n_point (Rust would panic). */
 static long generate_local_course(const double lengths[3], const int mode[3], double max_curvature,
-                                  double step_size, double *px, double *py, double *pyaw, long n_point) {
+                                  double step_size, double *px, double *py, double *pyaw, long n_point,
+                                  uint32_t *flags) {
     long ind = 1;
     double ll = 0.0;
+    /* harness only: how close the count-deciding comparisons below are to flipping.  An implementation whose
+     * segment lengths agree to 1e-9 relative can take one iteration more or less of the loop at :239 exactly
+     * when |pd| and |l| are that close at the last accepted or the first rejected iteration. */
+    double count_tol = PPO_COUNT_REL * (1.0 + fabs(lengths[0]) + fabs(lengths[1]) + fabs(lengths[2]));
     for (int i = 0; i < 3; ++i) {
         int m = mode[i];
         double l = lengths[i];
@@ -291,8 +311,10 @@ static long generate_local_course(const double lengths[3], const int mode[3], do
             ind += 1;
             if (ind >= n_point) return -3;
             interpolate(ind, pd, m, max_curvature, ox, oy, oyaw, px, py, pyaw);
+            if (flags && fabs(l) - fabs(pd) <= count_tol) *flags |= PPO_FLAG_NEAR_COUNT; /* accepted by a hair */
             pd += d;
         }
+        if (flags && fabs(pd) - fabs(l) <= count_tol) *flags |= PPO_FLAG_NEAR_COUNT; /* rejected by a hair */
         ll = l - pd - d; /* :256 */
         ind += 1;
         if (ind >= n_point) return -3;
@@ -303,6 +325,10 @@ static long generate_local_course(const double lengths[3], const int mode[3], do
     if (len <= 1) len = 0;
     if (len == 0) return -3; /* path_x[len-1] would panic */
     /* :281-288 trim: pops trailing zeros and then one more element */
+    if (flags) { /* a written slot whose local x is nearly (not exactly) zero makes the trim length a knife edge */
+        for (long k = ind; k >= 1 && k >= ind - 2; --k)
+            if (px[k] != 0.0 && fabs(px[k]) <= count_tol / max_curvature) *flags |= PPO_FLAG_NEAR_COUNT;
+    }
     double last = px[len - 1];
     while (len >= 1 && last == 0.0) {
         last = px[len - 1];
@@ -311,10 +337,34 @@ static long generate_local_course(const double lengths[3], const int mode[3], do
     return len;
 }
 
+static long dubins_path_core(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
+                             double step, int from_origin, double *out_x, double *out_y, double *out_yaw, size_t cap,
+                             int *word, double *cost, long *n_point_out, uint32_t *flags);
+
 long ppo_dubins_path(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
                      double step, int from_origin, double *out_x, double *out_y, double *out_yaw, size_t cap,
                      int *word, double *cost, long *n_point_out) {
+    return dubins_path_core(sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin, out_x, out_y, out_yaw, cap, word,
+                            cost, n_point_out, NULL);
+}
+
+long ppo_dubins_path_flags(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
+                           double step, int from_origin, double *out_x, double *out_y, double *out_yaw, size_t cap,
+                           int *word, double *cost, uint32_t *flags) {
+    return dubins_path_core(sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin, out_x, out_y, out_yaw, cap, word,
+                            cost, NULL, flags);
+}
+
+static long dubins_path_core(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
+                             double step, int from_origin, double *out_x, double *out_y, double *out_yaw, size_t cap,
+                             int *word, double *cost, long *n_point_out, uint32_t *flags) {
     double lex, ley, leyaw, c = 1.0 / radius;
+    if (flags) {
+        *flags = 0;
+        /* one ulp of a yaw beyond ~2^20 rad is more than 1e-10 rad: the sample positions are then decided by
+         * the last digits of the argument reduction, not by the path */
+        if (fabs(syaw) > PPO_HUGE_ANGLE || fabs(eyaw) > PPO_HUGE_ANGLE) *flags |= PPO_FLAG_HUGE_ANGLE;
+    }
     if (from_origin) {
         lex = ex;
         ley = ey;
@@ -327,7 +377,9 @@ long ppo_dubins_path(double sx, double sy, double syaw, double ex, double ey, do
         leyaw = eyaw - syaw;
     }
     double bcost, b[3];
-    int w = eval_from_origin(lex, ley, leyaw, c, &bcost, b, NULL);
+    uint32_t eflags = 0;
+    int w = eval_from_origin(lex, ley, leyaw, c, &bcost, b, flags ? &eflags : NULL);
+    if (flags) *flags |= eflags;
     if (word) *word = w;
     if (cost) *cost = bcost;
     if (w == PPO_NONE) return -1; /* :397 */
@@ -340,7 +392,7 @@ long ppo_dubins_path(double sx, double sy, double syaw, double ex, double ey, do
     double *buf = (double *)calloc((size_t)n_point * 3, sizeof(double));
     if (!buf) return -3;
     double *px = buf, *py = buf + n_point, *pyaw = buf + 2 * n_point;
-    long len = generate_local_course(b, WORD_MODES[w], c, step, px, py, pyaw, n_point);
+    long len = generate_local_course(b, WORD_MODES[w], c, step, px, py, pyaw, n_point, flags);
     if (len < 0) {
         free(buf);
         return -3;
@@ -776,6 +828,457 @@ long ppo_line_to_origin(const double *nx, const double *ny, const double *nyaw, 
         cur = par;
     }
     return (long)n;
+}
+
+/* ------------------------------------------------------------------ harness: decision margins */
+
+static double dist_point_seg(double px, double py, double x0, double y0, double x1, double y1) {
+    double dx = x1 - x0, dy = y1 - y0;
+    double l2 = dx * dx + dy * dy;
+    double t = (l2 > 0.0) ? ((px - x0) * dx + (py - y0) * dy) / l2 : 0.0;
+    if (!(t > 0.0)) t = 0.0; /* also catches NaN */
+    if (t > 1.0) t = 1.0;
+    return hypot(px - (x0 + t * dx), py - (y0 + t * dy));
+}
+
+/* true geometric crossing test (robust enough for a margin: orientation signs, touching counts) */
+static int seg_cross(double ax, double ay, double bx, double by, double cx, double cy, double dx, double dy) {
+    double d1 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+    double d2 = (bx - ax) * (dy - ay) - (by - ay) * (dx - ax);
+    double d3 = (dx - cx) * (ay - cy) - (dy - cy) * (ax - cx);
+    double d4 = (dx - cx) * (by - cy) - (dy - cy) * (bx - cx);
+    return ((d1 > 0.0) != (d2 > 0.0) || d1 == 0.0 || d2 == 0.0) && ((d3 > 0.0) != (d4 > 0.0) || d3 == 0.0 || d4 == 0.0);
+}
+
+static double dist_seg_seg(double ax, double ay, double bx, double by, double cx, double cy, double dx, double dy) {
+    if (seg_cross(ax, ay, bx, by, cx, cy, dx, dy)) {
+        /* the orientation test also fires for collinear disjoint segments; the end-point distances decide then */
+        double d1 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax), d2 = (bx - ax) * (dy - ay) - (by - ay) * (dx - ax);
+        if (!(d1 == 0.0 && d2 == 0.0)) return 0.0;
+    }
+    double m = dist_point_seg(ax, ay, cx, cy, dx, dy);
+    double v = dist_point_seg(bx, by, cx, cy, dx, dy);
+    if (v < m) m = v;
+    v = dist_point_seg(cx, cy, ax, ay, bx, by);
+    if (v < m) m = v;
+    v = dist_point_seg(dx, dy, ax, ay, bx, by);
+    if (v < m) m = v;
+    return m;
+}
+
+/* distance from a point to the boundary of a ring */
+static double dist_point_ring(const double *rx, const double *ry, size_t n, double px, double py) {
+    double m = INFINITY;
+    if (n == 1) return hypot(px - rx[0], py - ry[0]);
+    for (size_t i = 0; i + 1 < n; ++i) {
+        double v = dist_point_seg(px, py, rx[i], ry[i], rx[i + 1], ry[i + 1]);
+        if (v < m) m = v;
+    }
+    return m;
+}
+
+/* Space::verify (src/rrt.rs:124-137) together with a lower bound on how far every vertex of the line may move
+ * without changing the verdict.
+ *   verdict 1 (free): margin = the smallest distance between the line and any ring boundary (bounds included).
+ *     Moving every vertex by less than that cannot create a contact, and without a contact no vertex changes side.
+ *   verdict 0 (blocked): margin = the largest depth by which a point ON the line lies inside an obstacle or
+ *     outside the bounds (vertices and PPO_MARGIN_SUB interior points per segment are probed).  A line whose
+ *     vertices moved by less than that still passes within the obstacle / outside the bounds there.
+ * Not part of the reference; only used to CLASSIFY verdict differences between two implementations whose
+ * sample coordinates agree to a tolerance (margin < tolerance => "near graze"). */
+#define PPO_MARGIN_SUB 4
+int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, size_t n, double *margin) {
+    int verdict = ppo_verify(w, lx, ly, n);
+    double m;
+    if (verdict) {
+        m = INFINITY;
+        for (size_t r = 0; r <= w->n_rings; ++r) { /* r == n_rings: the bounds ring */
+            const double *rx, *ry;
+            size_t rn;
+            if (r == w->n_rings) {
+                rx = w->bx, ry = w->by, rn = w->nb;
+            } else {
+                rx = w->ox + w->ring_off[r], ry = w->oy + w->ring_off[r], rn = w->ring_off[r + 1] - w->ring_off[r];
+            }
+            if (rn == 0) continue;
+            aabb_t b = ring_aabb(rx, ry, rn);
+            for (size_t j = 0; j < n; ++j) {
+                size_t j1 = (j + 1 < n) ? j + 1 : j; /* last vertex: degenerate segment */
+                double sminx = lx[j] < lx[j1] ? lx[j] : lx[j1], smaxx = lx[j] > lx[j1] ? lx[j] : lx[j1];
+                double sminy = ly[j] < ly[j1] ? ly[j] : ly[j1], smaxy = ly[j] > ly[j1] ? ly[j] : ly[j1];
+                if (smaxx < b.minx - m || sminx > b.maxx + m || smaxy < b.miny - m || sminy > b.maxy + m) continue;
+                if (rn == 1) {
+                    double v = dist_point_seg(rx[0], ry[0], lx[j], ly[j], lx[j1], ly[j1]);
+                    if (v < m) m = v;
+                }
+                for (size_t i = 0; i + 1 < rn; ++i) {
+                    double v = dist_seg_seg(lx[j], ly[j], lx[j1], ly[j1], rx[i], ry[i], rx[i + 1], ry[i + 1]);
+                    if (v < m) m = v;
+                }
+            }
+        }
+    } else {
+        m = 0.0;
+        for (size_t j = 0; j < n; ++j) {
+            size_t j1 = (j + 1 < n) ? j + 1 : j;
+            int subs = (j1 == j) ? 1 : PPO_MARGIN_SUB + 1;
+            for (int k = 0; k < subs; ++k) {
+                double t = (double)k / (double)(PPO_MARGIN_SUB + 1);
+                double qx = lx[j] + t * (lx[j1] - lx[j]), qy = ly[j] + t * (ly[j1] - ly[j]);
+                if (!(qx == qx) || !(qy == qy)) { /* a NaN coordinate is outside everything for every implementation */
+                    m = INFINITY;
+                    continue;
+                }
+                if (ppo_point_position(w->bx, w->by, w->nb, qx, qy) == 0) {
+                    double v = w->nb ? dist_point_ring(w->bx, w->by, w->nb, qx, qy) : INFINITY;
+                    if (v > m) m = v;
+                }
+                for (size_t r = 0; r < w->n_rings; ++r) {
+                    const double *rx = w->ox + w->ring_off[r], *ry = w->oy + w->ring_off[r];
+                    size_t rn = w->ring_off[r + 1] - w->ring_off[r];
+                    if (rn < 3) continue;
+                    aabb_t b = ring_aabb(rx, ry, rn);
+                    if (qx < b.minx || qx > b.maxx || qy < b.miny || qy > b.maxy) continue;
+                    if (ppo_point_position(rx, ry, rn, qx, qy) == 1) {
+                        double v = dist_point_ring(rx, ry, rn, qx, qy);
+                        if (v > m) m = v;
+                    }
+                }
+            }
+        }
+    }
+    if (margin) *margin = m;
+    return verdict;
+}
+
+/* verify of Dubins edges with the classification flags of the parity harness: the Dubins flags of the edge's
+ * path (near wrap / tie / feasibility, knife-edge sample count, huge angles) and PPO_FLAG_NEAR_GRAZE when the
+ * verdict's margin is below graze_tol * max(1, largest |coordinate| of the polyline). */
+void ppo_verify_dubins_edges_flags(const ppo_world *w, size_t m, const double *sx, const double *sy,
+                                   const double *syaw, const double *ex, const double *ey, const double *eyaw,
+                                   double radius, double step, double graze_tol, uint8_t *ok, uint32_t *flags,
+                                   double *margins, int nthreads) {
+    int nt = resolve_threads(nthreads);
+    (void)nt;
+#pragma omp parallel num_threads(nt)
+    {
+        size_t cap = 1 << 16;
+        double *lx = (double *)malloc(cap * sizeof(double)), *ly = (double *)malloc(cap * sizeof(double));
+#pragma omp for schedule(dynamic, 4)
+        for (long i = 0; i < (long)m; ++i) {
+            long n;
+            uint32_t f = 0;
+            for (;;) {
+                n = ppo_dubins_path_flags(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0, lx, ly, NULL,
+                                          cap - 1, NULL, NULL, &f);
+                if (n != -2) break;
+                cap *= 2;
+                free(lx);
+                free(ly);
+                lx = (double *)malloc(cap * sizeof(double));
+                ly = (double *)malloc(cap * sizeof(double));
+            }
+            if (n == -1) { /* src/rrt.rs:313 */
+                lx[0] = sx[i];
+                ly[0] = sy[i];
+                n = 1;
+            }
+            if (n < 0) {
+                ok[i] = 0xFF;
+                flags[i] = f;
+                if (margins) margins[i] = 0.0;
+                continue;
+            }
+            lx[n] = ex[i];
+            ly[n] = ey[i];
+            n += 1;
+            double mg = 0.0, scale = 1.0;
+            for (long k = 0; k < n; ++k) {
+                if (fabs(lx[k]) > scale) scale = fabs(lx[k]);
+                if (fabs(ly[k]) > scale) scale = fabs(ly[k]);
+            }
+            ok[i] = (uint8_t)ppo_verify_margin(w, lx, ly, (size_t)n, &mg);
+            if (!(mg >= graze_tol * scale)) f |= PPO_FLAG_NEAR_GRAZE;
+            flags[i] = f;
+            if (margins) margins[i] = mg;
+        }
+        free(lx);
+        free(ly);
+    }
+}
+
+/* ------------------------------------------------------------------ rrt.rs: goal check and shortcutting */
+
+/* growable node arena: slots [0, n_tree) are the tree, later slots are the Node values optimize() creates
+ * (Arc<Node> in the reference; a slot index here) */
+typedef struct {
+    double *x, *y, *yaw;
+    int32_t *parent;
+    size_t n, cap;
+    const ppo_world *w;
+    double radius, step, graze_tol;
+    uint32_t flags;      /* OR of the classification flags of every verify decision taken */
+    long verifies;       /* Space::verify calls made (the reference's cost driver) */
+    double *lx, *ly;     /* polyline scratch */
+    size_t lcap;
+    int error;
+} arena_t;
+
+static int arena_push(arena_t *a, double x, double y, double yaw, int32_t parent) {
+    if (a->n == a->cap) {
+        size_t cap = a->cap * 2;
+        double *nx = (double *)realloc(a->x, cap * sizeof(double));
+        double *ny = (double *)realloc(a->y, cap * sizeof(double));
+        double *nyaw = (double *)realloc(a->yaw, cap * sizeof(double));
+        int32_t *np = (int32_t *)realloc(a->parent, cap * sizeof(int32_t));
+        if (nx) a->x = nx;
+        if (ny) a->y = ny;
+        if (nyaw) a->yaw = nyaw;
+        if (np) a->parent = np;
+        if (!nx || !ny || !nyaw || !np) {
+            a->error = 1;
+            return -1;
+        }
+        a->cap = cap;
+    }
+    a->x[a->n] = x;
+    a->y[a->n] = y;
+    a->yaw[a->n] = yaw;
+    a->parent[a->n] = parent;
+    return (int)a->n++;
+}
+
+/* Node::new, src/rrt.rs:169-175: yaw = compute_yaw(point, parent.point) */
+static int arena_node_new(arena_t *a, double x, double y, int32_t parent) {
+    return arena_push(a, x, y, ppo_compute_yaw(x, y, a->x[parent], a->y[parent]), parent);
+}
+
+/* verify(line_to_origin(node)) with the harness flags; src/rrt.rs:414-426 as used at :476-477 */
+static int arena_verify_chain(arena_t *a, int32_t node) {
+    long n;
+    for (;;) {
+        /* same chunks as ppo_line_to_origin, plus the Dubins flags of every edge */
+        size_t cnt = 0;
+        int32_t cur = node;
+        n = 0;
+        for (;;) {
+            int32_t par = a->parent[cur];
+            if (par < 0) {
+                if (cnt + 1 > a->lcap) {
+                    n = -2;
+                    break;
+                }
+                a->lx[cnt] = a->x[cur];
+                a->ly[cnt] = a->y[cur];
+                cnt += 1;
+                break;
+            }
+            uint32_t f = 0;
+            long k = ppo_dubins_path_flags(a->x[cur], a->y[cur], a->yaw[cur], a->x[par], a->y[par], a->yaw[par], a->radius,
+                                           a->step, 0, a->lx + cnt, a->ly + cnt, NULL, a->lcap - cnt, NULL, NULL, &f);
+            if (k == -2) {
+                n = -2;
+                break;
+            }
+            a->flags |= f;
+            if (k == -1) { /* :313 */
+                if (cnt + 1 > a->lcap) {
+                    n = -2;
+                    break;
+                }
+                a->lx[cnt] = a->x[cur];
+                a->ly[cnt] = a->y[cur];
+                k = 1;
+            } else if (k < 0) {
+                a->error = 1;
+                return 0;
+            }
+            cnt += (size_t)k;
+            cur = par;
+        }
+        if (n != -2) {
+            n = (long)cnt;
+            break;
+        }
+        size_t cap = a->lcap * 2;
+        free(a->lx);
+        free(a->ly);
+        a->lx = (double *)malloc(cap * sizeof(double));
+        a->ly = (double *)malloc(cap * sizeof(double));
+        a->lcap = cap;
+    }
+    double mg = 0.0, scale = 1.0;
+    for (long k = 0; k < n; ++k) {
+        if (fabs(a->lx[k]) > scale) scale = fabs(a->lx[k]);
+        if (fabs(a->ly[k]) > scale) scale = fabs(a->ly[k]);
+    }
+    int v = ppo_verify_margin(a->w, a->lx, a->ly, (size_t)n, &mg);
+    a->verifies += 1;
+    if (!(mg >= a->graze_tol * scale)) a->flags |= PPO_FLAG_NEAR_GRAZE;
+    return v;
+}
+
+#define PPO_RECURSION_LIMIT 16 /* src/rrt.rs:14 */
+
+/* RRT::optimize, src/rrt.rs:463-487.  Returns the arena slot of the new node or -1 (None). */
+static int32_t arena_optimize(arena_t *a, int32_t node, size_t i) {
+    if (i >= PPO_RECURSION_LIMIT) return -1; /* :464-466 */
+    size_t depth = 0;
+    for (int32_t c = node; c >= 0; c = a->parent[c]) depth += 1;
+    int32_t *nodes_vec = (int32_t *)malloc(depth * sizeof(int32_t)); /* :468-471 node, parent, ..., root */
+    depth = 0;
+    for (int32_t c = node; c >= 0; c = a->parent[c]) nodes_vec[depth++] = c;
+    int32_t result = -1;
+    for (size_t k = depth; k-- > 0;) { /* :473 .rev(): root first, the node itself last */
+        int32_t to_node = nodes_vec[k];
+        size_t mark = a->n;
+        int32_t new_node = arena_node_new(a, a->x[node], a->y[node], to_node); /* :474 */
+        if (new_node < 0) break;
+        if (arena_verify_chain(a, new_node)) { /* :476-477 */
+            int32_t deeper = arena_optimize(a, to_node, i + 1); /* :478 */
+            result = (deeper >= 0) ? arena_node_new(a, a->x[node], a->y[node], deeper) /* :479-481 */
+                                   : new_node;                                        /* :482 */
+            break;
+        }
+        a->n = mark; /* nothing refers to a rejected candidate */
+        if (a->error) break;
+    }
+    free(nodes_vec);
+    return result;
+}
+
+static int arena_init(arena_t *a, const ppo_world *w, size_t n_nodes, const double *nx, const double *ny,
+                      const double *nyaw, const int32_t *parent, double radius, double step, double graze_tol) {
+    memset(a, 0, sizeof *a);
+    a->cap = n_nodes + 64;
+    a->x = (double *)malloc(a->cap * sizeof(double));
+    a->y = (double *)malloc(a->cap * sizeof(double));
+    a->yaw = (double *)malloc(a->cap * sizeof(double));
+    a->parent = (int32_t *)malloc(a->cap * sizeof(int32_t));
+    a->lcap = 1 << 14;
+    a->lx = (double *)malloc(a->lcap * sizeof(double));
+    a->ly = (double *)malloc(a->lcap * sizeof(double));
+    if (!a->x || !a->y || !a->yaw || !a->parent || !a->lx || !a->ly) return -1;
+    memcpy(a->x, nx, n_nodes * sizeof(double));
+    memcpy(a->y, ny, n_nodes * sizeof(double));
+    memcpy(a->yaw, nyaw, n_nodes * sizeof(double));
+    memcpy(a->parent, parent, n_nodes * sizeof(int32_t));
+    a->n = n_nodes;
+    a->w = w;
+    a->radius = radius;
+    a->step = step;
+    a->graze_tol = graze_tol;
+    return 0;
+}
+static void arena_free(arena_t *a) {
+    free(a->x);
+    free(a->y);
+    free(a->yaw);
+    free(a->parent);
+    free(a->lx);
+    free(a->ly);
+}
+
+/* writes the chain node -> root as poses; returns its length or -2 when cap is too small */
+static long arena_chain_out(const arena_t *a, int32_t node, double *cx, double *cy, double *cyaw, size_t cap) {
+    size_t k = 0;
+    for (int32_t c = node; c >= 0; c = a->parent[c]) {
+        if (k >= cap) return -2;
+        cx[k] = a->x[c];
+        cy[k] = a->y[c];
+        cyaw[k] = a->yaw[c];
+        k += 1;
+    }
+    return (long)k;
+}
+
+long ppo_optimize(const ppo_world *w, size_t n_nodes, const double *nx, const double *ny, const double *nyaw,
+                  const int32_t *parent, uint32_t node, double radius, double step, double graze_tol, double *cx,
+                  double *cy, double *cyaw, size_t cap, uint32_t *flags, long *verifies) {
+    arena_t a;
+    if (node >= n_nodes || arena_init(&a, w, n_nodes, nx, ny, nyaw, parent, radius, step, graze_tol)) return -3;
+    int32_t r = arena_optimize(&a, (int32_t)node, 0);
+    long out = 0;
+    if (a.error)
+        out = -3;
+    else if (r >= 0)
+        out = arena_chain_out(&a, r, cx, cy, cyaw, cap);
+    if (flags) *flags = a.flags;
+    if (verifies) *verifies = a.verifies;
+    arena_free(&a);
+    return out;
+}
+
+/* RRT::check_finish (src/rrt.rs:428-438) = new_goal over `node`, finalize (:503-540, via optimize_from_goal
+ * :489-501), verify.  Returns the number of points of the final line (start -> goal order), -1 for None
+ * (the line does not verify; the line itself is still written), -2 when a capacity is too small, -3 when the
+ * reference would panic (:529).  The optimised chain goal -> root is written to (cx, cy, cyaw). */
+long ppo_check_finish(const ppo_world *w, size_t n_nodes, const double *nx, const double *ny, const double *nyaw,
+                      const int32_t *parent, uint32_t node, double gx, double gy, double gyaw, double radius,
+                      double step, double graze_tol, double *lx, double *ly, size_t cap, long *line_len, double *cx,
+                      double *cy, double *cyaw, size_t ccap, long *chain_len, uint32_t *flags, long *verifies) {
+    arena_t a;
+    if (node >= n_nodes || arena_init(&a, w, n_nodes, nx, ny, nyaw, parent, radius, step, graze_tol)) return -3;
+    long ret = -3;
+    /* :429-430 Node::new_goal(point, node, goal_yaw) */
+    int32_t goal_node = arena_push(&a, gx, gy, gyaw, (int32_t)node);
+    /* :489-501 optimize_from_goal */
+    int32_t top = goal_node;
+    int32_t opt = arena_optimize(&a, (int32_t)node, 0);
+    if (opt >= 0) top = arena_push(&a, gx, gy, gyaw, opt);
+    if (a.error || goal_node < 0 || top < 0) goto done;
+    if (chain_len) {
+        *chain_len = arena_chain_out(&a, top, cx, cy, cyaw, ccap);
+        if (*chain_len == -2) {
+            ret = -2;
+            goto done;
+        }
+    }
+    /* :503-540 finalize: per node with a parent the Dubins samples, the root contributes nothing; chunks in
+     * node -> root order (Q12), then the whole vector reversed */
+    size_t n = 0;
+    for (int32_t cur = top; a.parent[cur] >= 0; cur = a.parent[cur]) {
+        int32_t par = a.parent[cur];
+        uint32_t f = 0;
+        long k = ppo_dubins_path_flags(a.x[cur], a.y[cur], a.yaw[cur], a.x[par], a.y[par], a.yaw[par], radius, step, 0,
+                                       lx + n, ly + n, NULL, cap - n, NULL, NULL, &f);
+        a.flags |= f;
+        if (k == -2) {
+            ret = -2;
+            goto done;
+        }
+        if (k < 0) { /* :529 panic!("Should plan dubins curve") or an out-of-buffer index */
+            ret = -3;
+            goto done;
+        }
+        n += (size_t)k;
+    }
+    for (size_t i = 0, j = n; i + 1 < j; ++i) { /* :537 l.reverse() */
+        --j;
+        double t = lx[i];
+        lx[i] = lx[j];
+        lx[j] = t;
+        t = ly[i];
+        ly[i] = ly[j];
+        ly[j] = t;
+    }
+    if (line_len) *line_len = (long)n;
+    {
+        double mg = 0.0, scale = 1.0;
+        for (size_t k = 0; k < n; ++k) {
+            if (fabs(lx[k]) > scale) scale = fabs(lx[k]);
+            if (fabs(ly[k]) > scale) scale = fabs(ly[k]);
+        }
+        int v = ppo_verify_margin(w, lx, ly, n, &mg); /* :433 */
+        a.verifies += 1;
+        if (!(mg >= graze_tol * scale)) a.flags |= PPO_FLAG_NEAR_GRAZE;
+        ret = v ? (long)n : -1;
+    }
+done:
+    if (flags) *flags = a.flags;
+    if (verifies) *verifies = a.verifies;
+    arena_free(&a);
+    return ret;
 }
 
 /* ------------------------------------------------------------------ synthetic inputs */

@@ -36,8 +36,16 @@ enum { PPO_LSL = 0, PPO_RSR = 1, PPO_LSR = 2, PPO_RSL = 3, PPO_RLR = 4, PPO_LRL 
 enum {
     PPO_FLAG_NEAR_WRAP = 1, /* a mod2pi result of a contending word lies within PPO_WRAP_EPS of 0 or 2pi */
     PPO_FLAG_NEAR_TIE = 2,  /* runner-up cost within PPO_TIE_REL (relative) of the best cost */
-    PPO_FLAG_NEAR_FEAS = 4  /* a feasibility test (p^2 >= 0, |tmp| <= 1) is within 1e-9 of flipping */
+    PPO_FLAG_NEAR_FEAS = 4, /* a feasibility test (p^2 >= 0, |tmp| <= 1) is within 1e-9 of flipping */
+    /* sampled paths / edges (ppo_dubins_path_flags, ppo_verify_dubins_edges_flags, ppo_optimize, ppo_check_finish) */
+    PPO_FLAG_NEAR_COUNT = 8,  /* a count-deciding comparison of generate_local_course (the loop test at
+                                 src/dubins.rs:239, the zero test of the trim at :281-288) is within
+                                 PPO_COUNT_REL of flipping */
+    PPO_FLAG_NEAR_GRAZE = 16, /* the verify verdict's margin (ppo_verify_margin) is below the tolerance */
+    PPO_FLAG_HUGE_ANGLE = 32  /* |yaw| > PPO_HUGE_ANGLE: one ulp of the angle moves samples by more than 1e-10 */
 };
+#define PPO_COUNT_REL 4e-9
+#define PPO_HUGE_ANGLE 1048576.0
 #define PPO_WRAP_EPS 1e-9
 #define PPO_TIE_REL 1e-9
 
@@ -46,6 +54,9 @@ double ppo_pi_2_pi(double angle); /* src/dubins.rs:22-24 */
 
 /* one word: returns 1 if feasible and writes tpq[3]; src/dubins.rs:27-153 */
 int ppo_dubins_word(int word, double alpha, double beta, double d, double tpq[3]);
+
+/* HARNESS: margin of the word's feasibility test relative to 1 + d^2 (negative = infeasible) */
+double ppo_dubins_word_margin(int word, double alpha, double beta, double d);
 
 /* normalisation + six words + selection (src/dubins.rs:401-408, 333-363).
  * Returns the word id (0..5) or PPO_NONE.  cost is radius-normalised. */
@@ -65,6 +76,11 @@ void ppo_dubins_eval_batch(size_t n, const double *sx, const double *sy, const d
 long ppo_dubins_path(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
                      double step, int from_origin, double *px, double *py, double *pyaw, size_t cap,
                      int *word, double *cost, long *n_point_out);
+
+/* the same path together with the harness flags (PPO_FLAG_*) of its evaluation and its sample count */
+long ppo_dubins_path_flags(double sx, double sy, double syaw, double ex, double ey, double eyaw, double radius,
+                           double step, int from_origin, double *px, double *py, double *pyaw, size_t cap,
+                           int *word, double *cost, uint32_t *flags);
 
 /* sample counts only (same loop semantics), batch */
 void ppo_dubins_count_batch(size_t n, const double *sx, const double *sy, const double *syaw, const double *ex,
@@ -122,6 +138,29 @@ long ppo_dubins_edge_polyline(double sx, double sy, double syaw, double ex, doub
 void ppo_verify_dubins_edges(const ppo_world *w, size_t m, const double *sx, const double *sy, const double *syaw,
                              const double *ex, const double *ey, const double *eyaw, double radius, double step,
                              uint8_t *ok, int culled, int nthreads);
+
+/* HARNESS (not in the reference): Space::verify plus a lower bound on how far the line's vertices can move
+ * without changing the verdict (free: clearance to every ring boundary; blocked: penetration depth). */
+int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, size_t n, double *margin);
+/* verify of Dubins edges with classification flags: path flags | PPO_FLAG_NEAR_GRAZE when
+ * margin < graze_tol * max(1, max |coordinate|).  margins may be NULL. */
+void ppo_verify_dubins_edges_flags(const ppo_world *w, size_t m, const double *sx, const double *sy,
+                                   const double *syaw, const double *ex, const double *ey, const double *eyaw,
+                                   double radius, double step, double graze_tol, uint8_t *ok, uint32_t *flags,
+                                   double *margins, int nthreads);
+
+/* RRT::optimize (src/rrt.rs:463-487, RECURSION_LIMIT :14) of tree node `node` over a flat tree.  Writes the chain
+ * of the returned node (new node ... root) as poses and returns its length; 0 = None; -2 cap too small; -3 error.
+ * flags: OR of the harness flags of every verify decision taken; verifies: number of Space::verify calls. */
+long ppo_optimize(const ppo_world *w, size_t n_nodes, const double *nx, const double *ny, const double *nyaw,
+                  const int32_t *parent, uint32_t node, double radius, double step, double graze_tol, double *cx,
+                  double *cy, double *cyaw, size_t cap, uint32_t *flags, long *verifies);
+/* RRT::check_finish (src/rrt.rs:428-438) through finalize / optimize_from_goal (:489-540).  Returns the point
+ * count of the line (start -> goal), -1 = None (line written, does not verify), -2 capacity, -3 panic. */
+long ppo_check_finish(const ppo_world *w, size_t n_nodes, const double *nx, const double *ny, const double *nyaw,
+                      const int32_t *parent, uint32_t node, double gx, double gy, double gyaw, double radius,
+                      double step, double graze_tol, double *lx, double *ly, size_t cap, long *line_len, double *cx,
+                      double *cy, double *cyaw, size_t ccap, long *chain_len, uint32_t *flags, long *verifies);
 
 /* line_to_origin over a flat tree (src/rrt.rs:291-321, node->root chunk order). Returns points or <0. */
 long ppo_line_to_origin(const double *nx, const double *ny, const double *nyaw, const int32_t *parent,
