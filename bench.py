@@ -619,7 +619,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
         rings = [pp.rrt.create_circle((float(cx), float(cy)), float(r))
                  for cx, cy, r in zip(rng.uniform(10, 90, 50), rng.uniform(10, 90, 50), rng.uniform(1.0, 3.0, 50))]
         bounds_ring = (np.array([0.0, 0.0, 100.0, 100.0, 0.0]), np.array([0.0, 100.0, 100.0, 0.0, 0.0]))
-        space = pp.rrt.Space(bounds_ring, pp.rrt.Robot(1.8, 3.0, 0.8), rings, ctx=ctx, seed=7)
+        space = pp.rrt.Space.from_inflated(bounds_ring, pp.rrt.Robot(1.8, 3.0, 0.8), rings, ctx=ctx, seed=7)
         planner = pp.rrt.RRT((4.0, 4.0), 0.0, (96.0, 96.0), 0.0, 10_000, 0.1, space)
         l0 = ctx.launch_count
         t0 = time.perf_counter()

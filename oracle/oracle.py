@@ -115,7 +115,7 @@ def lib():
                                C.POINTER(C.c_long)]
     L.ppo_check_finish.restype = C.c_long
     L.ppo_check_finish.argtypes = [wp, sz, _dp, _dp, _dp, _i32p, C.c_uint32, d, d, d, d, d, d, _dp, _dp, sz,
-                                   C.POINTER(C.c_long), _dp, _dp, _dp, sz, C.POINTER(C.c_long), _u32p,
+                                   C.POINTER(C.c_long), _dp, _dp, _dp, sz, C.POINTER(C.c_long), _u32p, _u32p,
                                    C.POINTER(C.c_long)]
     L.ppo_line_to_origin.restype = C.c_long
     L.ppo_line_to_origin.argtypes = [_dp, _dp, _dp, _i32p, C.c_uint32, d, d, _dp, _dp, sz]
@@ -360,7 +360,8 @@ class Finish:
     line: tuple       # (x, y) of the finalized line, start -> goal, whether or not it verifies
     ok: bool          # check_finish returned Some(line)
     chain: np.ndarray  # optimised chain goal -> root as (x, y, yaw) rows
-    flags: int
+    flags: int        # fragile decisions (chain choice, verdict)
+    line_flags: int   # raw path flags of the final line's edges (knife-edge counts change samples, not decisions)
     verifies: int
 
 
@@ -371,11 +372,11 @@ def check_finish(world, nx, ny, nyaw, parent, node, goal, goal_yaw, radius, step
     while True:
         lx, ly = np.empty(cap), np.empty(cap)
         cx, cy, cyaw = np.empty(ccap), np.empty(ccap), np.empty(ccap)
-        fl, nv, ln, cn = C.c_uint32(), C.c_long(), C.c_long(), C.c_long()
+        fl, lfl, nv, ln, cn = C.c_uint32(), C.c_uint32(), C.c_long(), C.c_long(), C.c_long()
         r = lib().ppo_check_finish(C.byref(world.w), nx.size, _p(nx), _p(ny), _p(nyaw), _p(parent, _i32p), int(node),
                                    float(goal[0]), float(goal[1]), float(goal_yaw), radius, step, graze_tol, _p(lx),
                                    _p(ly), cap, C.byref(ln), _p(cx), _p(cy), _p(cyaw), ccap, C.byref(cn),
-                                   C.byref(fl), C.byref(nv))
+                                   C.byref(fl), C.byref(lfl), C.byref(nv))
         if r == -2:
             cap *= 4
             ccap *= 4
@@ -384,7 +385,7 @@ def check_finish(world, nx, ny, nyaw, parent, node, goal, goal_yaw, radius, step
             raise RuntimeError("reference would panic (finalize: no Dubins word)")
         n, c = ln.value, cn.value
         return Finish((lx[:n].copy(), ly[:n].copy()), r >= 0, np.stack([cx[:c], cy[:c], cyaw[:c]], 1),
-                      int(fl.value), int(nv.value))
+                      int(fl.value), int(lfl.value), int(nv.value))
 
 
 def ring_has_point(rx, ry, px, py):

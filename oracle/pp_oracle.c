@@ -393,6 +393,9 @@ static long dubins_path_core(double sx, double sy, double syaw, double ex, doubl
     if (!buf) return -3;
     double *px = buf, *py = buf + n_point, *pyaw = buf + 2 * n_point;
     long len = generate_local_course(b, WORD_MODES[w], c, step, px, py, pyaw, n_point, flags);
+    /* bit-identical poses: d = alpha = beta = 0 exactly, every word length is an exact 0 and the path is empty
+     * in any implementation -- nothing about it is a knife edge */
+    if (flags && !from_origin && sx == ex && sy == ey && syaw == eyaw) *flags = 0;
     if (len < 0) {
         free(buf);
         return -3;
@@ -951,6 +954,19 @@ int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, si
     return verdict;
 }
 
+/* Which flags make a verify DECISION fragile, given the verdict's margin: a possible other word / wrap / huge
+ * angle changes the whole path; a knife-edge sample count adds or drops one vertex, which moves the polyline by
+ * at most the sagitta of two sample spacings, (2 s)^2 / (8 R) = step^2 R / 2 with s = step R -- only a margin
+ * below twice that can be affected; a margin below graze_tol * scale is fragile in any case. */
+static uint32_t decision_flags(uint32_t path_flags, double margin, double scale, double graze_tol, double radius,
+                               double step) {
+    uint32_t f = path_flags & (PPO_FLAG_NEAR_WRAP | PPO_FLAG_NEAR_TIE | PPO_FLAG_NEAR_FEAS | PPO_FLAG_HUGE_ANGLE);
+    double graze = graze_tol * scale;
+    if (!(margin >= graze)) f |= PPO_FLAG_NEAR_GRAZE;
+    if ((path_flags & PPO_FLAG_NEAR_COUNT) && !(margin >= step * step * radius + graze)) f |= PPO_FLAG_NEAR_COUNT;
+    return f;
+}
+
 /* verify of Dubins edges with the classification flags of the parity harness: the Dubins flags of the edge's
  * path (near wrap / tie / feasibility, knife-edge sample count, huge angles) and PPO_FLAG_NEAR_GRAZE when the
  * verdict's margin is below graze_tol * max(1, largest |coordinate| of the polyline). */
@@ -998,8 +1014,7 @@ void ppo_verify_dubins_edges_flags(const ppo_world *w, size_t m, const double *s
                 if (fabs(ly[k]) > scale) scale = fabs(ly[k]);
             }
             ok[i] = (uint8_t)ppo_verify_margin(w, lx, ly, (size_t)n, &mg);
-            if (!(mg >= graze_tol * scale)) f |= PPO_FLAG_NEAR_GRAZE;
-            flags[i] = f;
+            flags[i] = decision_flags(f, mg, scale, graze_tol, radius, step);
             if (margins) margins[i] = mg;
         }
         free(lx);
@@ -1017,7 +1032,8 @@ typedef struct {
     size_t n, cap;
     const ppo_world *w;
     double radius, step, graze_tol;
-    uint32_t flags;      /* OR of the classification flags of every verify decision taken */
+    uint32_t flags;      /* OR of the decision flags (decision_flags) of every verify decision taken */
+    uint32_t line_flags; /* OR of the raw path flags of the edges of the final line (sample-level differences) */
     long verifies;       /* Space::verify calls made (the reference's cost driver) */
     double *lx, *ly;     /* polyline scratch */
     size_t lcap;
@@ -1056,7 +1072,9 @@ static int arena_node_new(arena_t *a, double x, double y, int32_t parent) {
 /* verify(line_to_origin(node)) with the harness flags; src/rrt.rs:414-426 as used at :476-477 */
 static int arena_verify_chain(arena_t *a, int32_t node) {
     long n;
+    uint32_t pf = 0;
     for (;;) {
+        pf = 0;
         /* same chunks as ppo_line_to_origin, plus the Dubins flags of every edge */
         size_t cnt = 0;
         int32_t cur = node;
@@ -1080,7 +1098,7 @@ static int arena_verify_chain(arena_t *a, int32_t node) {
                 n = -2;
                 break;
             }
-            a->flags |= f;
+            pf |= f;
             if (k == -1) { /* :313 */
                 if (cnt + 1 > a->lcap) {
                     n = -2;
@@ -1114,7 +1132,7 @@ static int arena_verify_chain(arena_t *a, int32_t node) {
     }
     int v = ppo_verify_margin(a->w, a->lx, a->ly, (size_t)n, &mg);
     a->verifies += 1;
-    if (!(mg >= a->graze_tol * scale)) a->flags |= PPO_FLAG_NEAR_GRAZE;
+    a->flags |= decision_flags(pf, mg, scale, a->graze_tol, a->radius, a->step);
     return v;
 }
 
@@ -1216,7 +1234,8 @@ long ppo_optimize(const ppo_world *w, size_t n_nodes, const double *nx, const do
 long ppo_check_finish(const ppo_world *w, size_t n_nodes, const double *nx, const double *ny, const double *nyaw,
                       const int32_t *parent, uint32_t node, double gx, double gy, double gyaw, double radius,
                       double step, double graze_tol, double *lx, double *ly, size_t cap, long *line_len, double *cx,
-                      double *cy, double *cyaw, size_t ccap, long *chain_len, uint32_t *flags, long *verifies) {
+                      double *cy, double *cyaw, size_t ccap, long *chain_len, uint32_t *flags, uint32_t *line_flags,
+                      long *verifies) {
     arena_t a;
     if (node >= n_nodes || arena_init(&a, w, n_nodes, nx, ny, nyaw, parent, radius, step, graze_tol)) return -3;
     long ret = -3;
@@ -1242,7 +1261,7 @@ long ppo_check_finish(const ppo_world *w, size_t n_nodes, const double *nx, cons
         uint32_t f = 0;
         long k = ppo_dubins_path_flags(a.x[cur], a.y[cur], a.yaw[cur], a.x[par], a.y[par], a.yaw[par], radius, step, 0,
                                        lx + n, ly + n, NULL, cap - n, NULL, NULL, &f);
-        a.flags |= f;
+        a.line_flags |= f;
         if (k == -2) {
             ret = -2;
             goto done;
@@ -1271,11 +1290,12 @@ long ppo_check_finish(const ppo_world *w, size_t n_nodes, const double *nx, cons
         }
         int v = ppo_verify_margin(w, lx, ly, n, &mg); /* :433 */
         a.verifies += 1;
-        if (!(mg >= graze_tol * scale)) a.flags |= PPO_FLAG_NEAR_GRAZE;
+        a.flags |= decision_flags(a.line_flags, mg, scale, graze_tol, radius, step);
         ret = v ? (long)n : -1;
     }
 done:
     if (flags) *flags = a.flags;
+    if (line_flags) *line_flags = a.line_flags;
     if (verifies) *verifies = a.verifies;
     arena_free(&a);
     return ret;

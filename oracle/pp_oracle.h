@@ -142,8 +142,9 @@ void ppo_verify_dubins_edges(const ppo_world *w, size_t m, const double *sx, con
 /* HARNESS (not in the reference): Space::verify plus a lower bound on how far the line's vertices can move
  * without changing the verdict (free: clearance to every ring boundary; blocked: penetration depth). */
 int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, size_t n, double *margin);
-/* verify of Dubins edges with classification flags: path flags | PPO_FLAG_NEAR_GRAZE when
- * margin < graze_tol * max(1, max |coordinate|).  margins may be NULL. */
+/* verify of Dubins edges with DECISION flags: word-level path flags (wrap / tie / feasibility / huge angle);
+ * PPO_FLAG_NEAR_GRAZE when margin < graze_tol * max(1, max |coordinate|); PPO_FLAG_NEAR_COUNT only when the
+ * margin is also below the sagitta one added / dropped sample can move the polyline by.  margins may be NULL. */
 void ppo_verify_dubins_edges_flags(const ppo_world *w, size_t m, const double *sx, const double *sy,
                                    const double *syaw, const double *ex, const double *ey, const double *eyaw,
                                    double radius, double step, double graze_tol, uint8_t *ok, uint32_t *flags,
@@ -156,11 +157,14 @@ long ppo_optimize(const ppo_world *w, size_t n_nodes, const double *nx, const do
                   const int32_t *parent, uint32_t node, double radius, double step, double graze_tol, double *cx,
                   double *cy, double *cyaw, size_t cap, uint32_t *flags, long *verifies);
 /* RRT::check_finish (src/rrt.rs:428-438) through finalize / optimize_from_goal (:489-540).  Returns the point
- * count of the line (start -> goal), -1 = None (line written, does not verify), -2 capacity, -3 panic. */
+ * count of the line (start -> goal), -1 = None (line written, does not verify), -2 capacity, -3 panic.
+ * flags: decisions (which chain, which verdict) that are fragile; line_flags: raw path flags of the final line's
+ * edges (a knife-edge count there changes the number of samples, not the decision). */
 long ppo_check_finish(const ppo_world *w, size_t n_nodes, const double *nx, const double *ny, const double *nyaw,
                       const int32_t *parent, uint32_t node, double gx, double gy, double gyaw, double radius,
                       double step, double graze_tol, double *lx, double *ly, size_t cap, long *line_len, double *cx,
-                      double *cy, double *cyaw, size_t ccap, long *chain_len, uint32_t *flags, long *verifies);
+                      double *cy, double *cyaw, size_t ccap, long *chain_len, uint32_t *flags, uint32_t *line_flags,
+                      long *verifies);
 
 /* line_to_origin over a flat tree (src/rrt.rs:291-321, node->root chunk order). Returns points or <0. */
 long ppo_line_to_origin(const double *nx, const double *ny, const double *nyaw, const int32_t *parent,

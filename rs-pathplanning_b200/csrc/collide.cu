@@ -184,10 +184,13 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
         x0 = ax[i];
         y0 = ay[i];
         if (gather_idx) {  // extend step: b = tree node nearest to the sample a (src/rrt.rs:406-411)
+            // pp_nn answers 0xFFFFFFFF for a query without a nearest node (NaN / Inf coordinates, d2 overflow):
+            // the reference's get_random_node returns None there, here the step reports ok = 0 and yaw = NaN
             const uint32_t g = gather_idx[i];
-            x1 = node_x[g];
-            y1 = node_y[g];
-            if (yaw_out) yaw_out[i] = atan2(y1 - y0, x1 - x0);  // compute_yaw, src/rrt.rs:267-271
+            const bool none = g == 0xFFFFFFFFu;
+            x1 = none ? CUDART_NAN : node_x[g];
+            y1 = none ? CUDART_NAN : node_y[g];
+            if (yaw_out) yaw_out[i] = none ? CUDART_NAN : atan2(y1 - y0, x1 - x0);  // compute_yaw, src/rrt.rs:267-271
         } else {
             x1 = bx[i];
             y1 = by[i];
@@ -277,10 +280,13 @@ __global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
         x0 = ax[i];
         y0 = ay[i];
         if (gather_idx) {  // extend step: b = tree node nearest to the sample a (src/rrt.rs:406-411)
+            // pp_nn answers 0xFFFFFFFF for a query without a nearest node (NaN / Inf coordinates, d2 overflow):
+            // the reference's get_random_node returns None there, here the step reports ok = 0 and yaw = NaN
             const uint32_t g = gather_idx[i];
-            x1 = node_x[g];
-            y1 = node_y[g];
-            if (yaw_out) yaw_out[i] = atan2(y1 - y0, x1 - x0);  // compute_yaw, src/rrt.rs:267-271
+            const bool none = g == 0xFFFFFFFFu;
+            x1 = none ? CUDART_NAN : node_x[g];
+            y1 = none ? CUDART_NAN : node_y[g];
+            if (yaw_out) yaw_out[i] = none ? CUDART_NAN : atan2(y1 - y0, x1 - x0);  // compute_yaw, src/rrt.rs:267-271
         } else {
             x1 = bx[i];
             y1 = by[i];
@@ -420,9 +426,10 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
             y0[e] = ay[i];
             if (gather_idx) {  // extend step: b = tree node nearest to the sample a (src/rrt.rs:406-411)
                 const uint32_t g = gather_idx[i];
-                x1[e] = node_x[g];
-                y1[e] = node_y[g];
-                if (yaw_out) yaw_out[i] = atan2(y1[e] - y0[e], x1[e] - x0[e]);  // compute_yaw, src/rrt.rs:267-271
+                const bool none = g == 0xFFFFFFFFu;  // no nearest node (see pp_collide_segments_kernel)
+                x1[e] = none ? CUDART_NAN : node_x[g];
+                y1[e] = none ? CUDART_NAN : node_y[g];
+                if (yaw_out) yaw_out[i] = none ? CUDART_NAN : atan2(y1[e] - y0[e], x1[e] - x0[e]);  // compute_yaw, src/rrt.rs:267-271
             } else {
                 x1[e] = bx[i];
                 y1[e] = by[i];
@@ -827,6 +834,10 @@ __global__ void __launch_bounds__(256)
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= m) return;
     const uint32_t p = idx[i];
+    if (p == 0xFFFFFFFFu) {  // no nearest node: a NaN goal pose has no feasible word and is never `contained`
+        ex[i] = ey[i] = eyaw[i] = syaw[i] = CUDART_NAN;
+        return;
+    }
     const double px = node_x[p], py = node_y[p];
     ex[i] = px;
     ey[i] = py;

@@ -22,7 +22,8 @@ static std::shared_ptr<rrt::Space> bench_space() {  // benches/all.rs:8-32
     b.push(15.0, 15.0);
     b.push(15.0, -6.0);
     b.push(-6.0, -6.0);
-    return std::make_shared<rrt::Space>(rrt::Polygon(b), rrt::Robot(1.0, 1.0, 0.8), obstacle_list, 42);
+    // geometry as given: no geo-offset inflation in this mirror (see Space::from_inflated)
+    return rrt::Space::from_inflated(rrt::Polygon(b), rrt::Robot(1.0, 1.0, 0.8), obstacle_list, 42);
 }
 static rrt::RRT bench_planner() {  // benches/all.rs:34-42
     const double PI = 3.14159265358979323846;

@@ -98,7 +98,9 @@ int main(int argc, char **argv) {
 
     Polygon bounds(std::move(b));
     Robot robot(1.8, 3.0, 0.8);
-    auto space = std::make_shared<Space>(bounds, robot, obstacle_list, seed);
+    // the world file is taken as already carrying the robot's safety margin (Space::new's geo-offset inflation,
+    // src/rrt.rs:81-111, is not available in this mirror: Space's plain constructor refuses a non-zero width)
+    auto space = Space::from_inflated(bounds, robot, obstacle_list, seed);
     RRT planner(Coordinate{st[0], st[1]}, st[2], Coordinate{gl[0], gl[1]}, gl[2], max_iter, 0.1, space);
     std::printf("Start planner (bounds %zu pts, %zu obstacles, %zu iterations)\n", bounds.ring.size(),
                 obstacle_list.size(), max_iter);

@@ -225,8 +225,34 @@ inline Polygon create_circle(Point center, double radius) {
 
 class Space {  // src/rrt.rs:70-159
    public:
+    // Space::new (src/rrt.rs:81-122) shrinks the bounds and inflates every obstacle by width / 2 with the
+    // geo-offset crate, whose source is not available here: this constructor therefore
+    // REFUSES a robot of non-zero width instead of silently dropping the safety margin.  Geometry that already
+    // carries the margin goes through Space::from_inflated.
     Space(Polygon bounds, Robot robot, std::vector<Polygon> obstacle_list, uint64_t seed = 0x5EED)
+        : Space(std::move(bounds), robot, std::move(obstacle_list), seed, false) {}
+    static std::shared_ptr<Space> from_inflated(Polygon bounds, Robot robot, std::vector<Polygon> obstacle_list,
+                                                uint64_t seed = 0x5EED) {
+        return std::shared_ptr<Space>(new Space(std::move(bounds), robot, std::move(obstacle_list), seed, true));
+    }
+    ~Space() { pp_ctx_destroy(ctx_); }
+    Space(const Space &) = delete;
+    Space &operator=(const Space &) = delete;
+    // every Space owns its GPU context (one world + one tree, as an RRT owns its Space and its RTree in the
+    // reference, src/rrt.rs:325-356): any number of planners can live side by side
+    pp_ctx *ctx() const { return ctx_; }
+
+   private:
+    Space(Polygon bounds, Robot robot, std::vector<Polygon> obstacle_list, uint64_t seed, bool inflated)
         : bounds_(std::move(bounds)), robot_(robot), obstacles_(std::move(obstacle_list)), rng_(seed) {
+        if (!inflated && robot_.get_width() != 0.0)
+            throw Error(PP_ERR_INVALID,
+                        "Space::new: geo-offset inflation by Robot.width / 2 is not available in this mirror; pass "
+                        "pre-inflated bounds / obstacles through Space::from_inflated");
+        int dev = 0;
+        if (const char *e = std::getenv("PP_DEVICE")) dev = std::atoi(e);
+        int rc = pp_ctx_create(dev, &ctx_);
+        if (rc != PP_OK) throw Error(rc, std::string("pp_ctx_create: ") + pp_status_string(rc));
         const LineString &b = bounds_.ring;
         minx_ = maxx_ = b.x.empty() ? 0.0 : b.x[0];
         miny_ = maxy_ = b.y.empty() ? 0.0 : b.y[0];
@@ -243,14 +269,16 @@ class Space {  // src/rrt.rs:70-159
             oy.insert(oy.end(), p.ring.y.begin(), p.ring.y.end());
             off.push_back((uint32_t)ox.size());
         }
-        detail::check(pp_obstacles_upload(detail::ctx(), b.x.data(), b.y.data(), b.size(), ox.data(), oy.data(),
+        detail::check(pp_obstacles_upload(ctx_, b.x.data(), b.y.data(), b.size(), ox.data(), oy.data(),
                                           off.data(), obstacles_.size()),
                       "obstacles_upload");
     }
+
+   public:
     bool verify(const LineString &line) const {  // src/rrt.rs:124-137
         uint32_t off[2] = {0, (uint32_t)line.size()};
         uint8_t ok = 0;
-        detail::check(pp_verify_polylines(detail::ctx(), 1, line.x.data(), line.y.data(), off, &ok, 0), "verify");
+        detail::check(pp_verify_polylines(ctx_, 1, line.x.data(), line.y.data(), off, &ok, 0), "verify");
         return ok != 0;
     }
     std::vector<uint8_t> verify_many(const std::vector<LineString> &lines) const {  // one launch for all lines
@@ -263,7 +291,7 @@ class Space {  // src/rrt.rs:70-159
         }
         std::vector<uint8_t> ok(lines.size());
         if (!lines.empty())
-            detail::check(pp_verify_polylines(detail::ctx(), lines.size(), px.data(), py.data(), off.data(), ok.data(), 0),
+            detail::check(pp_verify_polylines(ctx_, lines.size(), px.data(), py.data(), off.data(), ok.data(), 0),
                           "verify_many");
         return ok;
     }
@@ -283,6 +311,7 @@ class Space {  // src/rrt.rs:70-159
     double minx_, maxx_, miny_, maxy_;
     std::mt19937_64 rng_;
     std::mutex mu_;
+    pp_ctx *ctx_ = nullptr;
 };
 
 inline double compute_yaw(const Point &from, const Point &to) {  // src/rrt.rs:267-271
@@ -397,12 +426,12 @@ class RRT {  // src/rrt.rs:325-619
         root->slot = 0;
         nodes_.push_back(root);
         const int32_t par = -1;
-        detail::check(pp_tree_upload(detail::ctx(), 1, &start.x, &start.y, &start_yaw, &par), "tree_upload");
+        detail::check(pp_tree_upload(space_->ctx(), 1, &start.x, &start.y, &start_yaw, &par), "tree_upload");
     }
 
     std::optional<NodePtr> get_nearest_node(const Point &point) const {  // src/rrt.rs:378-391
         uint32_t idx = 0xFFFFFFFFu;
-        detail::check(pp_nn(detail::ctx(), 1, &point.x, &point.y, &idx, nullptr, PP_NN_DEFAULT), "nn");
+        detail::check(pp_nn(space_->ctx(), 1, &point.x, &point.y, &idx, nullptr, PP_NN_DEFAULT), "nn");
         if (idx == 0xFFFFFFFFu) return std::nullopt;
         std::lock_guard<std::mutex> lk(mu_);
         return nodes_[idx];
@@ -424,7 +453,7 @@ class RRT {  // src/rrt.rs:325-619
             return space_->verify(one);
         }
         std::vector<uint8_t> ok(m);
-        detail::check(pp_collide_dubins(detail::ctx(), m, e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
+        detail::check(pp_collide_dubins(space_->ctx(), m, e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
                                         e.ey.data(), e.eyaw.data(), space_->get_steer(), step_size_, ok.data(), 0),
                       "collide_dubins");
         for (uint8_t v : ok)
@@ -462,7 +491,7 @@ class RRT {  // src/rrt.rs:325-619
         }
         for (size_t k = 0; k + 1 < n; ++k) push(*chain[k], *chain[k + 1]);
         std::vector<uint8_t> ok(e.sx.size());
-        detail::check(pp_collide_dubins(detail::ctx(), ok.size(), e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
+        detail::check(pp_collide_dubins(space_->ctx(), ok.size(), e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
                                         e.ey.data(), e.eyaw.data(), space_->get_steer(), step_size_, ok.data(), 0),
                       "collide_dubins");
         std::vector<uint8_t> chain_ok(n, 1);
@@ -543,7 +572,7 @@ class RRT {  // src/rrt.rs:325-619
             for (size_t k = 0; k + 1 < chains[j].size(); ++k) push(*chains[j][k], *chains[j][k + 1]);
         }
         std::vector<uint8_t> ok(e.sx.size());
-        detail::check(pp_collide_dubins(detail::ctx(), ok.size(), e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
+        detail::check(pp_collide_dubins(space_->ctx(), ok.size(), e.sx.data(), e.sy.data(), e.syaw.data(), e.ex.data(),
                                         e.ey.data(), e.eyaw.data(), space_->get_steer(), step_size_, ok.data(), 0),
                       "collide_dubins");
         std::vector<size_t> live;
@@ -590,7 +619,7 @@ class RRT {  // src/rrt.rs:325-619
         const size_t m = all.sx.size();
         std::vector<uint32_t> counts(m);
         std::vector<unsigned char> plan(m * PP_DUBINS_PLAN_BYTES);
-        detail::check(pp_dubins_sample_count(detail::ctx(), m, all.sx.data(), all.sy.data(), all.syaw.data(), all.ex.data(),
+        detail::check(pp_dubins_sample_count(space_->ctx(), m, all.sx.data(), all.sy.data(), all.syaw.data(), all.ex.data(),
                                              all.ey.data(), all.eyaw.data(), space_->get_steer(), step_size_, 0,
                                              counts.data(), plan.data()),
                       "sample_count");
@@ -601,7 +630,7 @@ class RRT {  // src/rrt.rs:325-619
             total += (counts[i] == 0xFFFFFFFFu) ? 0 : counts[i];
         }
         std::vector<double> xyyaw(3 * total);
-        detail::check(pp_dubins_sample_fill(detail::ctx(), m, plan.data(), offsets.data(), total, xyyaw.data()),
+        detail::check(pp_dubins_sample_fill(space_->ctx(), m, plan.data(), offsets.data(), total, xyyaw.data()),
                       "sample_fill");
         std::vector<LineString> lines(from.size());
         size_t pos = 0;
@@ -640,7 +669,7 @@ class RRT {  // src/rrt.rs:325-619
             }
             std::vector<uint32_t> idx(b);
             std::vector<uint8_t> ok(b);
-            detail::check(pp_rrt_extend_dubins(detail::ctx(), b, px.data(), py.data(), steer, step_size_, idx.data(),
+            detail::check(pp_rrt_extend_dubins(space_->ctx(), b, px.data(), py.data(), steer, step_size_, idx.data(),
                                                yaw.data(), ok.data(), 0, 0),
                           "rrt_extend_dubins");
             std::vector<NodePtr> fresh;
@@ -657,13 +686,13 @@ class RRT {  // src/rrt.rs:325-619
                 apar.push_back((int32_t)nodes_[idx[k]]->slot);
             }
             if (fresh.empty()) continue;
-            detail::check(pp_tree_append(detail::ctx(), fresh.size(), ax.data(), ay.data(), ayaw.data(), apar.data()),
+            detail::check(pp_tree_append(space_->ctx(), fresh.size(), ax.data(), ay.data(), ayaw.data(), apar.data()),
                           "tree_append");
             nodes_.insert(nodes_.end(), fresh.begin(), fresh.end());
             const size_t f = fresh.size();
             std::vector<double> gx(f, goal_.x), gy(f, goal_.y), gyaw(f, goal_yaw_);
             std::vector<uint8_t> reach(f);
-            detail::check(pp_collide_dubins(detail::ctx(), f, gx.data(), gy.data(), gyaw.data(), ax.data(), ay.data(),
+            detail::check(pp_collide_dubins(space_->ctx(), f, gx.data(), gy.data(), gyaw.data(), ax.data(), ay.data(),
                                             ayaw.data(), steer, step_size_, reach.data(), 0),
                           "collide_dubins");
             std::vector<NodePtr> visible;
@@ -690,7 +719,7 @@ class RRT {  // src/rrt.rs:325-619
         nodes_.push_back(n);
         const double x = n->get_point().x, y = n->get_point().y, yaw = n->get_yaw();
         const int32_t par = n->get_parent() ? (int32_t)n->get_parent()->slot : -1;
-        detail::check(pp_tree_append(detail::ctx(), 1, &x, &y, &yaw, &par), "tree_append");
+        detail::check(pp_tree_append(space_->ctx(), 1, &x, &y, &yaw, &par), "tree_append");
     }
     Coordinate goal_;
     double goal_yaw_;

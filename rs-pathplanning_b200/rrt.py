@@ -5,8 +5,12 @@ Node / NodeIter (:161-265), line_to_origin (:291-321, node->root chunk order), R
 get_nearest_node, get_random_node, verify_node, check_finish, optimize, optimize_from_goal, finalize,
 plan_one and plan.  The tree lives twice: Python Node objects (parent links, as Arc<Node>) and a flat SoA
 mirror on the GPU that the NN kernel scans.
-Out of scope (SURVEY.md section 2 rows 5/6): Space::new's geo-offset inflation -- bounds and obstacles
-are taken as already shrunk / inflated; rand_point uses a seedable numpy Generator instead of thread_rng.
+Every Space owns its own GPU context (one world + one tree), as an RRT owns its Space and its RTree in the reference
+(:325-356): any number of Space / RRT pairs can live side by side.
+Out of scope (SURVEY.md section 2 rows 5/6): Space::new's geo-offset inflation -- the geo-offset crate's source is not
+available, so Space(...) REFUSES a robot of non-zero width instead of silently dropping the safety margin, and
+geometry that already carries it goes through Space.from_inflated(...); rand_point uses a seedable numpy Generator
+instead of thread_rng.
 """
 from __future__ import annotations
 
@@ -45,9 +49,18 @@ def _closed(ring: Ring) -> Ring:
 
 
 class Space:  # src/rrt.rs:70-159
-    def __init__(self, bounds: Ring, robot: Robot, obstacle_list: Sequence[Ring], ctx=None, seed=None):
-        from . import default_context
-        self.ctx = ctx or default_context()
+    def __init__(self, bounds: Ring, robot: Robot, obstacle_list: Sequence[Ring], ctx=None, seed=None, device: int = 0,
+                 _inflated: bool = False):
+        if not _inflated and robot.get_width() != 0:
+            # src/rrt.rs:81-111 shrinks the bounds and inflates the obstacles by width / 2 through geo-offset
+            raise _ffi.PathPlanningError(
+                _ffi.PP_ERR_INVALID,
+                "Space::new: geo-offset inflation by Robot.width / 2 is not available in this mirror; pass "
+                "pre-inflated bounds / obstacles through Space.from_inflated(...)")
+        # one context per Space (world + tree live in it); a caller-supplied ctx is used as is and must not be
+        # shared with another live Space / RRT
+        self._own_ctx = ctx is None
+        self.ctx = _ffi.Context(device) if ctx is None else ctx
         self.bounds = _closed(bounds)
         self.robot = robot
         self.obstacles = [_closed(o) for o in obstacle_list]
@@ -55,6 +68,23 @@ class Space:  # src/rrt.rs:70-159
         self.minx, self.maxx, self.miny, self.maxy = float(bx.min()), float(bx.max()), float(by.min()), float(by.max())
         self._rng = np.random.default_rng(seed)
         self.ctx.obstacles_upload(self.bounds, self.obstacles)
+
+    @classmethod
+    def from_inflated(cls, bounds: Ring, robot: Robot, obstacle_list: Sequence[Ring], ctx=None, seed=None,
+                      device: int = 0) -> "Space":
+        """bounds already shrunk and obstacles already inflated by robot.width / 2 (what Space::new computes)"""
+        return cls(bounds, robot, obstacle_list, ctx=ctx, seed=seed, device=device, _inflated=True)
+
+    def close(self):
+        if self._own_ctx and self.ctx is not None:
+            self.ctx.close()
+        self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def verify(self, line: Ring) -> bool:  # src/rrt.rs:124-137
         return bool(self.ctx.verify_polylines([line])[0])
@@ -339,8 +369,8 @@ class RRT:  # src/rrt.rs:325-619
     # -- the reference runs max_iter independent plan_one iterations on 4 racy workers that all see
     # a slightly stale tree (src/rrt.rs:600-609).  Here a ROUND processes `batch` samples against one tree
     # snapshot: one NN launch, one fused Dubins verify launch for the new edges (the parents' chains are already
-    # verified, that is the tree invariant), one batched append, one fused launch for the goal connections, and
-    # the shortcutting only for nodes that can reach the goal.  min_by euclidean_length stays on the host (:611-617).
+    # verified, that is the tree invariant), one batched append, and check_finish_many for the round's fresh nodes
+    # (one fused launch per optimize level).  min_by euclidean_length stays on the host (:611-617).
     def plan_rounds(self, batch: int = 256, max_iter: Optional[int] = None) -> Optional[Ring]:
         budget = self.max_iter if max_iter is None else int(max_iter)
         best, best_len = None, math.inf
@@ -352,9 +382,9 @@ class RRT:  # src/rrt.rs:325-619
             px, py = np.array([p[0] for p in pts]), np.array([p[1] for p in pts])
             # one call: NN -> Node::new yaw -> fused Dubins sample-and-verify of the new edges
             idx, _, ok = self.ctx.rrt_extend_dubins(px, py, steer, self.step_size)
-            parents = [self.nodes[int(i)] for i in idx]
-            cand = [Node(p, par) for p, par in zip(pts, parents)]
-            fresh = [c for c, good in zip(cand, ok.astype(bool)) if good]
+            # idx = 0xFFFFFFFF: no nearest node (get_random_node returns None, src/rrt.rs:408-411); ok is 0 there
+            fresh = [Node(p, self.nodes[int(i)]) for p, i, good in zip(pts, idx, ok.astype(bool))
+                     if good and i != 0xFFFFFFFF]
             if not fresh:
                 continue
             self.ctx.tree_append([c.point[0] for c in fresh], [c.point[1] for c in fresh], [c.yaw for c in fresh],
@@ -362,12 +392,10 @@ class RRT:  # src/rrt.rs:325-619
             for c in fresh:
                 self._slot[id(c)] = len(self.nodes)
                 self.nodes.append(c)
-            # goal connection goal -> node for every fresh node in one launch; finalize only the reachable ones
-            g_ok = self.ctx.collide_dubins([self.goal[0]] * len(fresh), [self.goal[1]] * len(fresh),
-                                           [self.goal_yaw] * len(fresh), [c.point[0] for c in fresh],
-                                           [c.point[1] for c in fresh], [c.yaw for c in fresh], steer,
-                                           self.step_size).astype(bool)
-            for line in self.check_finish_many([c for c, reach in zip(fresh, g_ok) if reach]):
+            # check_finish for every fresh node, as plan_one does (:591): no goal-visibility pre-filter -- the goal
+            # connects to the OPTIMIZED node, whose yaw differs from the fresh node's, so goal -> fresh being blocked
+            # does not imply that the reference finds nothing
+            for line in self.check_finish_many(fresh):
                 if line is not None:
                     length = euclidean_length(line)
                     if length < best_len:

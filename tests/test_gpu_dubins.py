@@ -6,7 +6,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from conftest import check_sample_counts, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -91,12 +91,12 @@ def test_words_against_oracle(ctx, O):
     alpha, beta = rng.uniform(0, 2 * math.pi, n), rng.uniform(0, 2 * math.pi, n)
     d = np.concatenate([rng.uniform(0, 6, n // 2), rng.uniform(0, 60, n - n // 2)])
     tpq, feas = ctx.dubins_words(alpha, beta, d)
-    bad = 0
     for i in range(n):
         for w in range(6):
             r = O.dubins_word(w, float(alpha[i]), float(beta[i]), float(d[i]))
             if (r is not None) != bool(feas[i, w]):
-                bad += 1  # only legitimate right at the feasibility boundary
+                # only legitimate right at the feasibility boundary: the oracle's margin of that test must be ~0
+                assert abs(O.dubins_word_margin(w, float(alpha[i]), float(beta[i]), float(d[i]))) <= 1e-9, (i, w)
                 continue
             if r is None:
                 continue
@@ -104,7 +104,6 @@ def test_words_against_oracle(ctx, O):
                 diff = abs(tpq[i, w, k] - r[k])
                 near_wrap = min(r[k], 2 * math.pi - r[k]) < 1e-9
                 assert diff < 1e-9 * max(1.0, abs(r[k])) or (near_wrap and abs(diff - 2 * math.pi) < 1e-8), (i, w, k)
-    assert bad <= 2
 
 
 @pytest.mark.parametrize("dist,radius", [("mixed", 1.0), ("far", 1.0), ("mixed", 0.5), ("far", 2.5)])
@@ -194,7 +193,8 @@ def test_sampling_random(ctx, O, pp, radius, step, dist):
     ocounts = O.dubins_count_batch(sx, sy, syaw, ex, ey, eyaw, radius, step)
     _, _, _, oflags = O.dubins_eval_batch(sx, sy, syaw, ex, ey, eyaw, radius)
     clean = oflags == 0
-    assert (counts[clean].astype(np.int64) != ocounts[clean]).sum() <= max(1, n // 1000)  # step-boundary knife edges
+    # step-boundary knife edges: a count may differ only where the oracle flags the path (PPO_FLAG_NEAR_COUNT, ...)
+    check_sample_counts(O, counts, sx, sy, syaw, ex, ey, eyaw, radius, step, ocounts)
     assert int(counts.sum()) == out.shape[0]
     worst = 0.0
     for i in np.nonzero(clean)[0][:: max(1, n // 300)]:

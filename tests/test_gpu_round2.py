@@ -1,0 +1,155 @@
+"""GPU: round-2 parity additions -- full-size exhaustive cross-check of the culls, the adversarial near-parallel set,
+extend steps with unanswerable queries, and planners living side by side (one context per Space)."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import check_dubins_verdicts, exactly_free, near_parallel_edges
+
+pytestmark = pytest.mark.gpu
+
+NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED, NN_SCAN = 0, 1, 2, 4, 8
+DEFAULT, NO_CULL, USE_GRID, UNSORTED, SCAN = 0, 1, 2, 4, 8
+
+
+def test_c4_full_size_default_equals_exhaustive_loop(ctx, pp, O):
+    """Space::verify (src/rrt.rs:124-137) on ALL 2^20 C4 edges x 10 k rings: the default (obstacle-grid cull) against
+    PP_COLLIDE_NO_CULL, geo's exhaustive segment-pair loop with no rejection at all -- byte-equal flags.  A difference
+    would have to be rounding noise of a near-parallel pair (free in exact rational geometry)."""
+    m = n_nodes = 1 << 20
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(m, n_nodes)
+    bounds, rings = pp.synth.circle_world(10_000)
+    ctx.tree_upload(nx, ny, nyaw)
+    ctx.obstacles_upload(bounds, rings)
+    idx, _, ok = ctx.rrt_extend(qx, qy)
+    ex, ey = nx[idx], ny[idx]
+    ok_all = ctx.collide_segments(qx, qy, ex, ey, flags=NO_CULL)
+    bad = np.nonzero(ok != ok_all)[0]
+    if bad.size:
+        W = O.OracleWorld(bounds, rings)
+        assert bad.size < 8
+        for i in bad:
+            assert ok_all[i] == 0 and ok[i] == 1 and exactly_free(W, qx[i], qy[i], ex[i], ey[i]), i
+    assert 0.8 < ok.mean() < 0.9
+    # the no-hit obstacle set (rings moved outside the world): everything inside the bounds is free on both paths
+    far = [(rx + 5000.0, ry) for rx, ry in rings[:2000]]
+    ctx.obstacles_upload(bounds, far)
+    sub = slice(0, 1 << 17)
+    a = ctx.collide_segments(qx[sub], qy[sub], ex[sub], ey[sub])
+    b = ctx.collide_segments(qx[sub], qy[sub], ex[sub], ey[sub], flags=NO_CULL)
+    assert np.array_equal(a, b) and a.mean() > 0.99
+
+
+def test_c5_edges_default_equals_exhaustive_loop(ctx, pp, O):
+    """2^16 C5 Dubins edges (step 0.05, ~785 samples each) against the 10 k-ring obstacle set: default culls vs the
+    exhaustive loop on the SAME device-generated samples -- byte-equal flags (5e7 line segments x 1.4e5 ring segments)."""
+    e = 1 << 16
+    bounds, rings = pp.synth.circle_world(10_000)
+    ctx.obstacles_upload(bounds, rings)
+    sx, sy, syaw, ex, ey, eyaw = pp.synth.dubins_edges(e)
+    ok = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.05)
+    ok_all = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, 1.0, 0.05, flags=NO_CULL)
+    assert np.array_equal(ok, ok_all)
+    assert 0.01 < ok.mean() < 0.9
+    # and against the oracle (its own samples, 1e-9 apart) on a sub-sample, differences classified by its margins
+    W = O.OracleWorld(bounds, rings)
+    sub = np.arange(0, e, 331)
+    check_dubins_verdicts(O, W, ok[sub], sx[sub], sy[sub], syaw[sub], ex[sub], ey[sub], eyaw[sub], 1.0, 0.05)
+
+
+def test_near_parallel_extensions(ctx, pp, O):
+    """the adversarial class of DESIGN section 3 (ii): PP_COLLIDE_NO_CULL must reproduce geo's exhaustive answer bit
+    for bit (rounding noise included), every culled path must reproduce the oracle's culled answer, and the two differ
+    only where exact rational geometry says the segment is free."""
+    bounds, rings = pp.synth.circle_world(24, world=100.0, rmin=1.0, rmax=3.0)
+    ctx.obstacles_upload(bounds, rings)
+    W = O.OracleWorld(bounds, rings)
+    ax, ay, bx, by = near_parallel_edges(W.rings())
+    plain = W.verify_segments(ax, ay, bx, by, culled=False)
+    culled = W.verify_segments(ax, ay, bx, by, culled=True)
+    assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=NO_CULL), plain)
+    for flags in (DEFAULT, USE_GRID, UNSORTED, SCAN):
+        assert np.array_equal(ctx.collide_segments(ax, ay, bx, by, flags=flags), culled), flags
+    bad = np.nonzero(plain != culled)[0]
+    assert bad.size > 0
+    for i in bad:
+        assert plain[i] == 0 and exactly_free(W, ax[i], ay[i], bx[i], by[i])
+    # the same segments as 2-point polylines through the polyline kernel
+    lines = [(np.array([ax[i], bx[i]]), np.array([ay[i], by[i]])) for i in range(0, ax.size, 97)]
+    sel = np.arange(0, ax.size, 97)
+    assert np.array_equal(ctx.verify_polylines(lines, flags=NO_CULL), plain[sel])
+    assert np.array_equal(ctx.verify_polylines(lines), culled[sel])
+
+
+def test_extend_with_unanswerable_queries(ctx, pp, O):
+    """pp_nn answers 0xFFFFFFFF for NaN / Inf queries (get_random_node would return None, src/rrt.rs:408-411): the
+    extend steps must report ok = 0 and yaw = NaN for them instead of reading node[0xFFFFFFFF], and leave the context
+    usable (no sticky CUDA error)"""
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(3000, 6000, world=100.0)
+    bounds, rings = pp.synth.circle_world(100, world=100.0)
+    ctx.tree_upload(nx, ny, nyaw)
+    ctx.obstacles_upload(bounds, rings)
+    nan, inf = float("nan"), float("inf")
+    badpos = np.array([0, 1, 2, 31, 32, 1000, 2999])
+    qx[badpos] = [nan, inf, -inf, 5.0, nan, 1e300, 50.0]
+    qy[badpos] = [1.0, 2.0, 3.0, nan, nan, 1e300, inf]
+    oidx, _ = O.nn_brute(nx, ny, qx, qy)
+    none = oidx == 0xFFFFFFFF
+    assert none[badpos].all() and none.sum() == badpos.size
+    W = O.OracleWorld(bounds, rings)
+    good = ~none
+    want = np.zeros(qx.size, np.uint8)
+    want[good] = W.verify_segments(qx[good], qy[good], nx[oidx[good]], ny[oidx[good]])
+    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_SCAN, SCAN), (NN_PLAIN, UNSORTED), (NN_DEFAULT, NO_CULL)]:
+        idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=nnf, collide_flags=cf)
+        assert np.array_equal(idx, oidx), (nnf, cf)
+        assert np.array_equal(ok, want), (nnf, cf)
+        assert np.isnan(yaw[none]).all() and np.isfinite(yaw[good]).all()
+    idx, yaw, ok = ctx.rrt_extend_dubins(qx, qy, 0.8, 0.1)
+    assert np.array_equal(idx, oidx) and not ok[none].any() and np.isnan(yaw[none]).all()
+    wyaw = np.arctan2(ny[oidx[good]] - qy[good], nx[oidx[good]] - qx[good])
+    check_dubins_verdicts(O, W, ok[good], qx[good], qy[good], wyaw, nx[oidx[good]], ny[oidx[good]], nyaw[oidx[good]],
+                          0.8, 0.1)
+    one = ctx.rrt_extend([nan], [0.0])  # scalar call
+    assert one[0][0] == 0xFFFFFFFF and one[2][0] == 0 and math.isnan(one[1][0])
+    # the context is still healthy
+    assert np.array_equal(ctx.nn(qx[good][:100], qy[good][:100], want_d2=False), oidx[good][:100])
+
+
+def test_two_planners_side_by_side(pp, O):
+    """every Space owns its context (world + tree), as an RRT owns its Space and RTree in the reference
+    (src/rrt.rs:325-356; benches/all.rs builds one per bench): two planners on different worlds, interleaved, must not
+    see each other's obstacles or nodes"""
+    r = pp.rrt
+    b1 = (np.array([0.0, 0.0, 30.0, 30.0]), np.array([0.0, 30.0, 30.0, 0.0]))
+    rings1 = [r.create_circle((15.0, 15.0), 6.0)]
+    b2 = (np.array([100.0, 100.0, 140.0, 140.0]), np.array([100.0, 140.0, 140.0, 100.0]))
+    rings2 = [r.create_circle((120.0, 110.0), 3.0), r.create_circle((112.0, 128.0), 4.0)]
+    s1 = r.Space(b1, r.Robot(0.0, 1.0, 0.8), rings1, seed=1)
+    s2 = r.Space(b2, r.Robot(0.0, 1.0, 0.8), rings2, seed=2)
+    assert s1.ctx is not s2.ctx
+    p1 = r.RRT((3.0, 3.0), 0.5, (27.0, 27.0), 0.0, 100, 0.1, s1)
+    p2 = r.RRT((104.0, 104.0), 0.2, (135.0, 136.0), 0.0, 100, 0.1, s2)
+    for _ in range(60):
+        p1.plan_one()
+        p2.plan_one()
+    p1.plan_rounds(batch=32, max_iter=64)
+    p2.plan_rounds(batch=32, max_iter=64)
+    for p, s, bounds, rings in ((p1, s1, b1, rings1), (p2, s2, b2, rings2)):
+        assert s.ctx.tree_size == len(p.nodes) > 10
+        W = O.OracleWorld(bounds, rings)
+        nx = np.array([n.point[0] for n in p.nodes]); ny = np.array([n.point[1] for n in p.nodes])
+        nyaw = np.array([n.yaw for n in p.nodes])
+        par = np.array([p._slot[id(n.parent)] if n.parent is not None else -1 for n in p.nodes], np.int32)
+        assert nx.min() >= bounds[0].min() and nx.max() <= bounds[0].max()
+        for i in range(1, len(p.nodes), 3):  # every inserted chain verifies in ITS world
+            lx, ly = O.line_to_origin(nx, ny, nyaw, par, i, 0.8, 0.1)
+            assert W.verify(lx, ly), i
+        q = (float(nx.mean()), float(ny.mean()))
+        assert p.get_nearest_node(q) is p.nodes[int(O.nn_brute(nx, ny, [q[0]], [q[1]])[0][0])]
+    # the plain constructor refuses to drop the robot's safety margin silently (Space::new inflates by width / 2)
+    with pytest.raises(pp.PathPlanningError):
+        r.Space(b1, r.Robot(1.0, 1.0, 0.8), rings1)
+    s1.close()
+    s2.close()

@@ -139,7 +139,7 @@ def test_batched_optimize_matches_recursive_optimize_on_the_host(pp):
     r = pp.rrt
     ctx = _FakeCtx()
     bounds = (np.array([0.0, 0.0, 50.0, 50.0, 0.0]), np.array([0.0, 50.0, 50.0, 0.0, 0.0]))
-    space = r.Space(bounds, r.Robot(1.0, 1.0, 0.8), [], ctx=ctx, seed=3)
+    space = r.Space.from_inflated(bounds, r.Robot(1.0, 1.0, 0.8), [], ctx=ctx, seed=3)
     planner = r.RRT((1.0, 1.0), 0.0, (49.0, 49.0), 0.0, 100, 0.1, space)
     rng = np.random.default_rng(5)
     nodes = [planner.nodes[0]]

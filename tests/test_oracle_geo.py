@@ -166,3 +166,22 @@ def test_transit_fixture_loads(O):
     W = O.OracleWorld((conf["bounds_x"], conf["bounds_y"]), [(r["x"], r["y"]) for r in conf["rings"]])
     s, g = conf["start"], conf["goal"]
     assert W.verify([s[0]], [s[1]]) and W.verify([g[0]], [g[1]])  # start and goal are free points
+
+
+def test_culls_on_near_parallel_extensions_differ_only_by_rounding_noise(O, pp):
+    """DESIGN section 3 exactness (ii): the one class where the AABB culls can change geo's answer -- a line segment on
+    the extension of a ring segment and parallel to it to within ~2^-45 rad: geo's denominator and numerators are
+    rounding noise there and the exhaustive loop may report an intersection between segments that are far apart.
+    Every such difference must be (a) exhaustive = blocked, culled = free and (b) free in EXACT rational geometry."""
+    from conftest import exactly_free, near_parallel_edges
+    bounds, rings = pp.synth.circle_world(24, world=100.0, rmin=1.0, rmax=3.0)
+    W = O.OracleWorld(bounds, rings)
+    ax, ay, bx, by = near_parallel_edges(W.rings())
+    assert ax.size > 200_000
+    plain = W.verify_segments(ax, ay, bx, by, culled=False)
+    culled = W.verify_segments(ax, ay, bx, by, culled=True)
+    bad = np.nonzero(plain != culled)[0]
+    assert 0 < bad.size < ax.size // 1000  # the class exists, and it is tiny even on this adversarial set
+    for i in bad:
+        assert plain[i] == 0 and culled[i] == 1
+        assert exactly_free(W, ax[i], ay[i], bx[i], by[i]), i

@@ -83,7 +83,7 @@ def _planner(O, pp, seed, max_iter=240, obstacles=True):
     bounds = (np.array([0.0, 0.0, 40.0, 40.0]), np.array([0.0, 40.0, 40.0, 0.0]))
     rings = [r.create_circle((20.0, 20.0), 5.0), r.create_circle((10.0, 28.0), 3.0),
              r.create_circle((30.0, 12.0), 3.0)] if obstacles else []
-    space = r.Space(bounds, r.Robot(1.0, 1.0, 2.0), rings, ctx=ctx, seed=seed)
+    space = r.Space.from_inflated(bounds, r.Robot(1.0, 1.0, 2.0), rings, ctx=ctx, seed=seed)
     return r.RRT((3.0, 3.0), 0.0, (36.0, 36.0), 0.0, max_iter, 0.25, space), ctx
 
 
