@@ -34,9 +34,10 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 
 typedef struct pp_ctx pp_ctx;
+typedef struct pp_group pp_group; /* one host process driving several B200s (section "multi-GPU" below) */
 
 enum pp_status {
     PP_OK = 0,
@@ -45,7 +46,8 @@ enum pp_status {
     PP_ERR_CUDA = -3,      /* a CUDA runtime call or kernel failed; see pp_last_error */
     PP_ERR_NOMEM = -4,     /* device or pinned-host allocation failed */
     PP_ERR_STATE = -5,     /* tree / obstacles not uploaded yet */
-    PP_ERR_OVERFLOW = -6   /* an output capacity given by the caller is too small */
+    PP_ERR_OVERFLOW = -6,  /* an output capacity given by the caller is too small */
+    PP_ERR_COMM = -7       /* NCCL is unavailable (libnccl.so.2 not loadable) or a collective failed */
 };
 
 /* word ids: ALL_PLANNERS order, src/dubins.rs:291 (LSL, RSR, LSR, RSL, RLR, LRL) */
@@ -66,10 +68,12 @@ enum pp_collide_flags {
 /* flags for pp_nn */
 /* Every method returns the same bit-exact argmin of dx*dx + dy*dy with the lowest index on ties. */
 enum pp_nn_flags {
-    PP_NN_DEFAULT = 0,   /* automatic: the grid search for trees of >= PP_NN_GRID_MIN_NODES nodes when there are more
-                            than 64 queries or the node grid is current; otherwise the brute-force scans */
+    PP_NN_DEFAULT = 0,   /* automatic: the grid search for trees of >= PP_NN_GRID_MIN_NODES nodes, otherwise the
+                            brute-force scans */
     PP_NN_PLAIN_F64 = 1, /* tiled brute-force scan, every pair in f64 (the yard-stick kernel) */
-    PP_NN_GRID = 2,      /* exact uniform-grid search; the grid is (re)built on the device after the tree changed */
+    PP_NN_GRID = 2,      /* exact uniform-grid search.  The grid is incremental: nodes appended since the last build
+                            form a tail that every query scans linearly; the O(n) device-side rebuild runs once per
+                            4 096 appended nodes (or when queries x tail outweighs it), never once per append */
     PP_NN_UNSORTED = 4,  /* tiled scan with per-thread fp32 pre-rejection, queries in the caller's order */
     PP_NN_SCAN = 8       /* tiled brute-force scan over ALL nodes, queries binned into a G x G grid, warp-wide exact
                             fp32 pre-rejection (node-parallel variant for <= 64 queries); no index on the tree */
@@ -97,6 +101,8 @@ int pp_ctx_set_stream(pp_ctx *ctx, void *cuda_stream);
 int pp_sync(pp_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t pp_launch_count(pp_ctx *ctx);
+/* number of O(n) rebuilds of the node grid so far (the incremental grid keeps this far below the append count) */
+uint64_t pp_nn_grid_builds(pp_ctx *ctx);
 /* pinned host memory for fast, overlappable transfers through the host entry points */
 int pp_host_alloc(size_t bytes, void **out);
 int pp_host_free(void *p);
@@ -208,7 +214,70 @@ int pp_rrt_extend_dubins(pp_ctx *ctx, size_t m, const double *qx, const double *
 int pp_rrt_extend_dubins_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy, double radius, double step,
                              uint32_t *idx, double *yaw, uint8_t *ok, int nn_flags, int collide_flags);
 
+/* ------------------------------------------------------------------ multi-GPU
+ * Every pose pair, NN query and edge is independent (src/rrt.rs:607-609 treats plan_one iterations that way): each
+ * device takes the contiguous slice [g*n/G, (g+1)*n/G) of a batch, tree and obstacles are REPLICATED, results are
+ * gathered by per-device copies.  The only collective is the broadcast of the tree / obstacle buffers when they
+ * change (ncclBroadcast over NVLink / NVSwitch) -- of just the appended tail for pp_*_tree_append, the insert site
+ * src/rrt.rs:586-589.  NCCL is loaded at run time (dlopen of libnccl.so.2); without it these calls return PP_ERR_COMM.
+ *
+ * Two ways to drive N GPUs:
+ *  (1) ONE host process (a Rust / C++ planner): pp_group owns one pp_ctx + one worker thread per device and one
+ *      communicator over them (ncclCommInitAll).
+ *  (2) ONE process per GPU (torchrun, MPI): each rank creates its own pp_ctx and joins a communicator with
+ *      pp_ctx_comm_init (rank 0 obtains the id with pp_comm_unique_id and the launcher's own channel hands the 128
+ *      bytes to the other ranks); pp_tree_*_bcast / pp_obstacles_upload_bcast are then collective calls. */
+#define PP_COMM_ID_BYTES 128
+/* slice of device g out of G for a batch of n: [*lo, *hi) = [g*n/G, (g+1)*n/G); pure host arithmetic */
+void pp_slice_bounds(size_t n, int parts, int part, size_t *lo, size_t *hi);
+int pp_comm_unique_id(void *id /* PP_COMM_ID_BYTES */);
+int pp_ctx_comm_init(pp_ctx *ctx, const void *id, int n_ranks, int rank);
+int pp_ctx_comm_rank(pp_ctx *ctx); /* -1 without a communicator */
+int pp_ctx_comm_size(pp_ctx *ctx); /* 1 without a communicator */
+/* collective over the ctx's communicator: the host arrays are read on `root` only (other ranks may pass NULL); every
+ * rank ends with the same tree.  n / k must be the same on all ranks.  RTree inserts at src/rrt.rs:345-346, 586-589 */
+int pp_tree_upload_bcast(pp_ctx *ctx, int root, size_t n, const double *x, const double *y, const double *yaw,
+                         const int32_t *parent);
+int pp_tree_append_bcast(pp_ctx *ctx, int root, size_t k, const double *x, const double *y, const double *yaw,
+                         const int32_t *parent);
+/* collective: `root` preprocesses and uploads the world (Space after Space::new, src/rrt.rs:113-121), its device
+ * buffers are broadcast; other ranks may pass NULL / 0 for every geometry argument */
+int pp_obstacles_upload_bcast(pp_ctx *ctx, int root, const double *bounds_x, const double *bounds_y, size_t n_bounds,
+                              const double *ring_x, const double *ring_y, const uint32_t *ring_off, size_t n_rings);
+
+int pp_group_create(const int *devices, int n_dev, pp_group **out);
+void pp_group_destroy(pp_group *g);
+int pp_group_size(pp_group *g);
+pp_ctx *pp_group_ctx(pp_group *g, int i); /* device i's context (owned by the group) */
+const char *pp_group_last_error(pp_group *g);
+/* replicate: H2D once on device 0, ncclBroadcast to the others */
+int pp_group_tree_upload(pp_group *g, size_t n, const double *x, const double *y, const double *yaw,
+                         const int32_t *parent);
+int pp_group_tree_append(pp_group *g, size_t k, const double *x, const double *y, const double *yaw,
+                         const int32_t *parent);
+int pp_group_obstacles_upload(pp_group *g, const double *bounds_x, const double *bounds_y, size_t n_bounds,
+                              const double *ring_x, const double *ring_y, const uint32_t *ring_off, size_t n_rings);
+/* sliced batch calls on HOST pointers: device i works on its contiguous slice concurrently with the others and
+ * copies its results straight into the caller's arrays.  Same arguments and results as the pp_* calls above --
+ * outputs are byte-identical for every device count. */
+int pp_group_dubins_eval(pp_group *g, size_t n, const double *sx, const double *sy, const double *syaw,
+                         const double *ex, const double *ey, const double *eyaw, const double *radius_arr,
+                         double radius, double *cost, uint8_t *word, double *tpq);
+int pp_group_nn(pp_group *g, size_t m, const double *qx, const double *qy, uint32_t *idx, double *d2, int flags);
+int pp_group_collide_segments(pp_group *g, size_t m, const double *ax, const double *ay, const double *bx,
+                              const double *by, uint8_t *ok, int flags);
+int pp_group_collide_dubins(pp_group *g, size_t m, const double *sx, const double *sy, const double *syaw,
+                            const double *ex, const double *ey, const double *eyaw, double radius, double step,
+                            uint8_t *ok, int flags);
+int pp_group_rrt_extend(pp_group *g, size_t m, const double *qx, const double *qy, uint32_t *idx, double *yaw,
+                        uint8_t *ok, int nn_flags, int collide_flags);
+int pp_group_rrt_extend_dubins(pp_group *g, size_t m, const double *qx, const double *qy, double radius, double step,
+                               uint32_t *idx, double *yaw, uint8_t *ok, int nn_flags, int collide_flags);
+
 /* ------------------------------------------------------------------ measurement helpers */
+/* host<->device copy ceiling of this box for the end-to-end figures: h2d_bytes up and d2h_bytes down between pinned
+ * (pinned != 0) or pageable host memory and the device, both directions at once on two streams, no kernel. */
+int pp_measure_copy(pp_ctx *ctx, size_t h2d_bytes, size_t d2h_bytes, int pinned, double *ms);
 /* FP64 pipe peak micro-benchmark: runs `iters` dependent DFMA chains of
  * length `chain` on every SM and returns DFMA thread-instructions per second. */
 int pp_measure_fp64_peak(pp_ctx *ctx, int iters, double *dfma_per_s, double *ms);

@@ -15,7 +15,7 @@ imported under the module name `rs_pathplanning_b200` through `__graft_entry__.i
 There is no CPU fallback anywhere in this package.
 """
 from . import _ffi  # noqa: F401  (raises ImportError when the CUDA library has not been built)
-from ._ffi import Context, PathPlanningError, PinnedArray, device_count  # noqa: F401
+from ._ffi import Context, Group, PathPlanningError, PinnedArray, comm_unique_id, device_count, slice_bounds  # noqa: F401
 from . import synth  # noqa: F401
 
 _default_ctx = None

@@ -2,6 +2,7 @@
 // host-pointer wrappers (pinned staging, chunked copy/compute overlap) and measurement helpers.
 // Host-side geometry set-up uses the same predicates as the kernels (geo_predicates.cuh).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -30,6 +31,7 @@ size_t pp_nn_xy32_floats(size_t cap);
 int pp_launch_nn(pp_ctx *, size_t, const double *, const double *, uint32_t *, double *, int, cudaStream_t);
 int pp_launch_tree_finish(pp_ctx *, size_t, size_t, size_t, cudaStream_t);
 int pp_tree_build_grid(pp_ctx *, cudaStream_t);  // nn.cu: device-side counting sort of the nodes by cell
+bool pp_nn_grid_policy(const pp_tree_dev &, size_t m);  // nn.cu: true when the appended tail is over budget
 int pp_launch_collide_segments(pp_ctx *, size_t, const double *, const double *, const double *, const double *,
                                const uint32_t *, double *, uint8_t *, int, cudaStream_t);
 int pp_launch_verify_polylines(pp_ctx *, size_t, const double *, const double *, const uint32_t *, uint8_t *, int,
@@ -90,6 +92,7 @@ const char *pp_status_string(int s) {
     case PP_ERR_NOMEM: return "out of memory";
     case PP_ERR_STATE: return "tree or obstacles not uploaded";
     case PP_ERR_OVERFLOW: return "output capacity too small";
+    case PP_ERR_COMM: return "NCCL unavailable or collective failed";
     }
     return "unknown status";
 }
@@ -113,15 +116,6 @@ int pp_device_count(void) {
         if (pp_device_ok(d)) ++ok;
     return ok;
 }
-
-// every API entry: serialise on the ctx, select its device, pick the stream
-struct pp_guard {
-    std::lock_guard<std::mutex> lk;
-    explicit pp_guard(pp_ctx *ctx) : lk(ctx->mu) {
-        cudaSetDevice(ctx->device);
-        ctx->active_stream = ctx->stream;
-    }
-};
 
 int pp_ctx_create(int device, pp_ctx **out) {
     if (!out) return PP_ERR_INVALID;
@@ -173,7 +167,7 @@ static void pp_tree_free(pp_tree_dev &t) {
     cudaFree(t.cell_xy);
     t = pp_tree_dev();
 }
-static void pp_world_free(pp_world_dev &w) {
+void pp_world_free(pp_world_dev &w) {
     cudaFree(w.bx);
     cudaFree(w.by);
     cudaFree(w.bcls);
@@ -190,6 +184,7 @@ void pp_ctx_destroy(pp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    pp_comm_release(ctx);
     for (auto &kv : ctx->timings)
         for (auto &pr : kv.second.pending) {
             cudaEventDestroy(pr.first);
@@ -227,6 +222,7 @@ int pp_sync(pp_ctx *ctx) {
     return PP_OK;
 }
 uint64_t pp_launch_count(pp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t pp_nn_grid_builds(pp_ctx *ctx) { return ctx ? ctx->grid_builds : 0; }
 
 int pp_host_alloc(size_t bytes, void **out) {
     if (!out) return PP_ERR_INVALID;
@@ -563,7 +559,7 @@ int pp_dubins_path(pp_ctx *ctx, double sx, double sy, double syaw, double ex, do
 // ---------------------------------------------------------------------------------------------------
 // tree
 // ---------------------------------------------------------------------------------------------------
-static int pp_tree_reserve(pp_ctx *ctx, size_t n_total, bool keep) {
+int pp_tree_reserve(pp_ctx *ctx, size_t n_total, bool keep) {
     pp_tree_dev &t = ctx->tree;
     const size_t tile = pp_nn_tile_nodes();
     size_t need = ((n_total + tile - 1) / tile) * tile;
@@ -610,8 +606,9 @@ static int pp_tree_reserve(pp_ctx *ctx, size_t n_total, bool keep) {
     return PP_OK;
 }
 
-static int pp_tree_put(pp_ctx *ctx, size_t first, size_t k, const double *x, const double *y, const double *yaw,
-                       const int32_t *parent, cudaMemcpyKind kind) {
+// copies k nodes into slots [first, first + k) of the device tree (host or device source)
+int pp_tree_copy_in(pp_ctx *ctx, size_t first, size_t k, const double *x, const double *y, const double *yaw,
+                    const int32_t *parent, cudaMemcpyKind kind) {
     pp_tree_dev &t = ctx->tree;
     cudaStream_t s = ctx->stream;
     if (k) {
@@ -626,14 +623,28 @@ static int pp_tree_put(pp_ctx *ctx, size_t first, size_t k, const double *x, con
         else
             PP_CUDA(ctx, cudaMemsetAsync(t.parent + first, 0xFF, k * 4, s));
     }
+    return PP_OK;
+}
+
+// makes slots [first, first + k) part of the tree: fp32 copies, sentinel padding, NN index bookkeeping
+int pp_tree_commit(pp_ctx *ctx, size_t first, size_t k, bool sync) {
+    pp_tree_dev &t = ctx->tree;
+    cudaStream_t s = ctx->stream;
     t.n = first + k;
-    t.grid_n = (size_t)-1;  // grid is stale
+    if (first == 0) t.grid_n = (size_t)-1;  // a new tree: the node grid (if any) describes another one
     const size_t tile = pp_nn_tile_nodes();
     size_t padded_end = ((t.n + tile - 1) / tile) * tile;
     int rc = pp_launch_tree_finish(ctx, first, t.n, padded_end, s);
     if (rc) return rc;
-    if (kind == cudaMemcpyHostToDevice) PP_CUDA(ctx, cudaStreamSynchronize(s));
+    if (sync) PP_CUDA(ctx, cudaStreamSynchronize(s));
     return PP_OK;
+}
+
+static int pp_tree_put(pp_ctx *ctx, size_t first, size_t k, const double *x, const double *y, const double *yaw,
+                       const int32_t *parent, cudaMemcpyKind kind) {
+    int rc = pp_tree_copy_in(ctx, first, k, x, y, yaw, parent, kind);
+    if (rc) return rc;
+    return pp_tree_commit(ctx, first, k, kind == cudaMemcpyHostToDevice);
 }
 
 int pp_tree_upload(pp_ctx *ctx, size_t n, const double *x, const double *y, const double *yaw,
@@ -904,6 +915,7 @@ int pp_obstacles_upload(pp_ctx *ctx, const double *bounds_x, const double *bound
     w.n_pts = (uint32_t)ox.size();
     w.n_rings = (uint32_t)n_rings;
     w.n_aabb_tiles = (uint32_t)n_tiles;
+    w.n_cell_items = (uint32_t)citems.size();
     w.gx = gx;
     w.gy = gy;
     w.gminx = g0x;
@@ -945,16 +957,16 @@ pp_world_view pp_make_world_view(const pp_world_dev &w) {
 // ---------------------------------------------------------------------------------------------------
 // NN / verify / extend
 // ---------------------------------------------------------------------------------------------------
-// Resolves PP_NN_DEFAULT to a concrete method and makes the node grid current when the grid search is used.
-// Every method returns the same bit-exact argmin (lowest index on ties), so the choice is about time only:
-// the grid search costs O(1) per query but needs the O(n) device-side rebuild after the tree changed; the
-// node-parallel scan serves a handful of queries on a freshly appended tree (the scalar plan_one loop).
+// Resolves PP_NN_DEFAULT to a concrete method and keeps the node grid usable when the grid search is chosen.
+// Every method returns the same bit-exact argmin (lowest index on ties), so the choice is about time only.
 static int pp_nn_prepare(pp_ctx *ctx, size_t m, int *flags) {
     const pp_tree_dev &t = ctx->tree;
-    if (!(*flags & (PP_NN_GRID | PP_NN_SCAN | PP_NN_PLAIN_F64 | PP_NN_UNSORTED)) && t.n >= PP_NN_GRID_MIN_NODES &&
-        (m > 64 || t.grid_n == t.n))
-        *flags |= PP_NN_GRID;
-    if (*flags & PP_NN_GRID) return pp_tree_build_grid(ctx, ctx->stream);
+    const bool forced = (*flags & (PP_NN_GRID | PP_NN_SCAN | PP_NN_PLAIN_F64 | PP_NN_UNSORTED)) != 0;
+    if (!forced && t.n >= PP_NN_GRID_MIN_NODES) *flags |= PP_NN_GRID;
+    // the grid is incremental: appended nodes form a linearly scanned tail, and the O(n) rebuild happens once per
+    // PP_NN_TAIL_MAX appended nodes (or when this call's m * tail outweighs it), never once per append -- the scalar
+    // plan_one loop (one append + one query per iteration, src/rrt.rs:583-597) pays it every 4 096 iterations
+    if ((*flags & PP_NN_GRID) && pp_nn_grid_policy(t, m)) return pp_tree_build_grid(ctx, ctx->stream);
     return PP_OK;
 }
 
@@ -1241,5 +1253,64 @@ int pp_measure_fp64_peak(pp_ctx *ctx, int iters, double *dfma_per_s, double *ms_
     PP_CUDA(ctx, e);
     *dfma_per_s = (double)threads * (double)per_thread * (double)iters / ((double)ms * 1e-3);
     if (ms_out) *ms_out = ms;
+    return PP_OK;
+}
+
+int pp_measure_copy(pp_ctx *ctx, size_t h2d_bytes, size_t d2h_bytes, int pinned, double *ms_out) {
+    if (!ctx || !ms_out) return PP_ERR_INVALID;
+    pp_guard g(ctx);
+    void *h_up = nullptr, *h_dn = nullptr, *d_up = nullptr, *d_dn = nullptr;
+    auto cleanup = [&]() {
+        if (pinned) {
+            if (h_up) cudaFreeHost(h_up);
+            if (h_dn) cudaFreeHost(h_dn);
+        } else {
+            free(h_up);
+            free(h_dn);
+        }
+        cudaFree(d_up);
+        cudaFree(d_dn);
+        cudaGetLastError();
+    };
+    bool ok = true;
+    if (pinned) {
+        ok = cudaHostAlloc(&h_up, h2d_bytes ? h2d_bytes : 1, cudaHostAllocDefault) == cudaSuccess &&
+             cudaHostAlloc(&h_dn, d2h_bytes ? d2h_bytes : 1, cudaHostAllocDefault) == cudaSuccess;
+    } else {
+        h_up = malloc(h2d_bytes ? h2d_bytes : 1);
+        h_dn = malloc(d2h_bytes ? d2h_bytes : 1);
+        ok = h_up && h_dn;
+    }
+    ok = ok && cudaMalloc(&d_up, h2d_bytes ? h2d_bytes : 1) == cudaSuccess &&
+         cudaMalloc(&d_dn, d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
+    if (!ok) {
+        cleanup();
+        return pp_fail(ctx, PP_ERR_NOMEM, "copy benchmark allocation failed");
+    }
+    memset(h_up, 1, h2d_bytes ? h2d_bytes : 1);  // touch the pages: first-touch faults are not copy time
+    memset(h_dn, 1, d2h_bytes ? d2h_bytes : 1);
+    cudaStream_t s0 = ctx->copy_streams[0], s1 = ctx->copy_streams[1];
+    const size_t chunk = (size_t)32 << 20;
+    double best = 1e300;
+    for (int rep = 0; rep < 3; ++rep) {  // best of 3 (the first pass also warms the driver's staging path)
+        cudaDeviceSynchronize();
+        auto t0 = std::chrono::steady_clock::now();
+        for (size_t off = 0; off < h2d_bytes || off < d2h_bytes; off += chunk) {
+            if (off < h2d_bytes)
+                cudaMemcpyAsync((char *)d_up + off, (char *)h_up + off, std::min(chunk, h2d_bytes - off),
+                                cudaMemcpyHostToDevice, s0);
+            if (off < d2h_bytes)
+                cudaMemcpyAsync((char *)h_dn + off, (char *)d_dn + off, std::min(chunk, d2h_bytes - off),
+                                cudaMemcpyDeviceToHost, s1);
+        }
+        cudaStreamSynchronize(s0);
+        cudaStreamSynchronize(s1);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        best = std::min(best, ms);
+    }
+    cudaError_t e = cudaGetLastError();
+    cleanup();
+    PP_CUDA(ctx, e);
+    *ms_out = best;
     return PP_OK;
 }

@@ -234,7 +234,13 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
                         if (overlap && t * PP_AABB_TILE + r < w.n_rings) {
                             const pp_ring_meta mt = w.meta[t * PP_AABB_TILE + r];
                             const double *rx = w.ox + mt.first, *ry = w.oy + mt.first;
-                            if (pp_ring_hits_segment(rx, ry, mt.count, x0, y0, x1, y1) ||
+                            // the f64 padded-box rule decides whether the pair is tested at all (as in the grid and
+                            // polyline kernels and the oracle's culled loop): the fp32 boxes are rounded outward and
+                            // would otherwise let a few more near-parallel noise pairs through than those paths do
+                            const bool sgx = x1 < x0, sgy = y1 < y0;
+                            const bool seg_in = !((sgx ? x0 : x1) < mt.minx - mt.pad || (sgx ? x1 : x0) > mt.maxx + mt.pad ||
+                                                  (sgy ? y0 : y1) < mt.miny - mt.pad || (sgy ? y1 : y0) > mt.maxy + mt.pad);
+                            if ((seg_in && pp_ring_hits_segment(rx, ry, mt.count, x0, y0, x1, y1)) ||
                                 (!pp_outside_padded(mt, x0, y0) && pp_point_position(rx, ry, mt.count, x0, y0) == 1) ||
                                 (!pp_outside_padded(mt, x1, y1) && pp_point_position(rx, ry, mt.count, x1, y1) == 1)) {
                                 hit = true;
@@ -496,7 +502,12 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
                             !(emaxx[e] < rminx || eminx[e] > rmaxx || emaxy[e] < rminy || eminy[e] > rmaxy)) {
                             const pp_ring_meta mt = w.meta[ring];
                             const double *rx = w.ox + mt.first, *ry = w.oy + mt.first;
-                            if (pp_ring_hits_segment(rx, ry, mt.count, x0[e], y0[e], x1[e], y1[e]) ||
+                            // f64 padded-box rule per pair (see pp_collide_segments_kernel)
+                            const bool sgx = x1[e] < x0[e], sgy = y1[e] < y0[e];
+                            const bool seg_in =
+                                !((sgx ? x0[e] : x1[e]) < mt.minx - mt.pad || (sgx ? x1[e] : x0[e]) > mt.maxx + mt.pad ||
+                                  (sgy ? y0[e] : y1[e]) < mt.miny - mt.pad || (sgy ? y1[e] : y0[e]) > mt.maxy + mt.pad);
+                            if ((seg_in && pp_ring_hits_segment(rx, ry, mt.count, x0[e], y0[e], x1[e], y1[e])) ||
                                 (!pp_outside_padded(mt, x0[e], y0[e]) &&
                                  pp_point_position(rx, ry, mt.count, x0[e], y0[e]) == 1) ||
                                 (!pp_outside_padded(mt, x1[e], y1[e]) &&

@@ -22,7 +22,8 @@ struct pp_tree_dev {
     double *x = nullptr, *y = nullptr, *yaw = nullptr;
     int32_t *parent = nullptr;
     float *x32 = nullptr;  // fl32(x), fl32(y) in 2048-node blocks (nn.cu: pp_xy32_index) for the exact fp32 pre-rejection
-    // uniform grid over the nodes (PP_NN_GRID), rebuilt lazily when `grid_n != n`
+    // uniform grid over the nodes [0, grid_n) (PP_NN_GRID); nodes [grid_n, n) appended since are the linearly
+    // scanned tail; rebuilt when the tail outgrows its budget (nn.cu: pp_nn_grid_policy).  (size_t)-1: no grid
     size_t grid_n = (size_t)-1;
     int gx = 0, gy = 0;
     double gminx = 0, gminy = 0, gcell = 1, ginv = 1;
@@ -58,6 +59,7 @@ struct pp_world_dev {
     int gx = 0, gy = 0;
     double gminx = 0, gminy = 0, gcell = 1, ginv = 1;
     uint32_t *cell_start = nullptr, *cell_items = nullptr;
+    uint32_t n_cell_items = 0;
 };
 
 struct pp_timing_slot {
@@ -76,6 +78,7 @@ struct pp_ctx {
     std::mutex mu;
     std::string last_error;
     uint64_t launches = 0;
+    uint64_t grid_builds = 0;  // O(n) rebuilds of the node grid so far (pp_nn_grid_builds)
     bool timing = false;
     std::map<std::string, pp_timing_slot> timings;
     std::vector<cudaEvent_t> event_pool;
@@ -87,7 +90,21 @@ struct pp_ctx {
     size_t scratch_bytes = 0;
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // NCCL communicator this ctx is a rank of (group.cu); null = single device
+    void *comm = nullptr;
+    int comm_rank = -1, comm_size = 1;
 };
+
+// every API entry: serialise on the ctx, select its device, pick the stream
+struct pp_guard {
+    std::lock_guard<std::mutex> lk;
+    explicit pp_guard(pp_ctx *ctx) : lk(ctx->mu) {
+        cudaSetDevice(ctx->device);
+        ctx->active_stream = ctx->stream;
+    }
+};
+void pp_comm_release(pp_ctx *ctx);                // group.cu: destroys ctx->comm if any
+void pp_world_free(pp_world_dev &w);              // api.cu
 
 int pp_fail(pp_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess);
 
@@ -107,6 +124,10 @@ struct pp_launch_scope {
 };
 
 int pp_scratch_reserve(pp_ctx *ctx, size_t bytes);
+int pp_tree_reserve(pp_ctx *ctx, size_t n_total, bool keep);
+int pp_tree_copy_in(pp_ctx *ctx, size_t first, size_t k, const double *x, const double *y, const double *yaw,
+                    const int32_t *parent, cudaMemcpyKind kind);
+int pp_tree_commit(pp_ctx *ctx, size_t first, size_t k, bool sync);
 
 // kernel-side view of pp_world_dev (passed by value)
 struct pp_world_view {

@@ -652,8 +652,8 @@ class RRT {  // src/rrt.rs:325-619
     }
     // Rounds of `batch` samples against one tree snapshot (the reference's four racy workers at width `batch`,
     // src/rrt.rs:600-609): one pp_rrt_extend_dubins call (NN -> Node::new yaw -> fused Dubins verify of the new
-    // edges; the parents' chains are verified already, that is the tree invariant), one batched append, one fused
-    // launch for the goal connections, check_finish_many for the nodes that see the goal; min_by length on the host.
+    // edges; the parents' chains are verified already, that is the tree invariant), one batched append,
+    // check_finish_many for the round's fresh nodes; min_by length on the host.
     std::optional<LineString> plan_rounds(size_t batch = 256) {
         std::optional<LineString> best;
         double best_len = std::numeric_limits<double>::infinity();
@@ -676,7 +676,7 @@ class RRT {  // src/rrt.rs:325-619
             std::vector<double> ax, ay, ayaw;
             std::vector<int32_t> apar;
             for (size_t k = 0; k < b; ++k) {
-                if (!ok[k]) continue;
+                if (!ok[k] || idx[k] == 0xFFFFFFFFu) continue;  // no nearest node: get_random_node's None
                 NodePtr n = std::make_shared<Node>(Point{px[k], py[k]}, nodes_[idx[k]]);
                 n->slot = (int64_t)(nodes_.size() + fresh.size());
                 fresh.push_back(n);
@@ -689,15 +689,9 @@ class RRT {  // src/rrt.rs:325-619
             detail::check(pp_tree_append(space_->ctx(), fresh.size(), ax.data(), ay.data(), ayaw.data(), apar.data()),
                           "tree_append");
             nodes_.insert(nodes_.end(), fresh.begin(), fresh.end());
-            const size_t f = fresh.size();
-            std::vector<double> gx(f, goal_.x), gy(f, goal_.y), gyaw(f, goal_yaw_);
-            std::vector<uint8_t> reach(f);
-            detail::check(pp_collide_dubins(space_->ctx(), f, gx.data(), gy.data(), gyaw.data(), ax.data(), ay.data(),
-                                            ayaw.data(), steer, step_size_, reach.data(), 0),
-                          "collide_dubins");
-            std::vector<NodePtr> visible;
-            for (size_t k = 0; k < f; ++k)
-                if (reach[k]) visible.push_back(fresh[k]);
+            // check_finish for every fresh node, as plan_one does (src/rrt.rs:591): the goal connects to the OPTIMIZED
+            // node, whose yaw differs from the fresh node's, so a blocked goal -> fresh edge decides nothing
+            const std::vector<NodePtr> &visible = fresh;
             for (std::optional<LineString> &line : check_finish_many(visible)) {
                 if (!line) continue;
                 const double len = line->euclidean_length();

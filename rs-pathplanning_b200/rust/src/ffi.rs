@@ -1,10 +1,15 @@
-//! extern "C" mirror of include/pathplanning_b200.h (ABI version 1) + the crate-level lazy context.
+//! extern "C" mirror of include/pathplanning_b200.h (ABI version 2): one context per Space (world + tree), one lazy
+//! crate-level context for the stateless Dubins calls, and the multi-GPU group.
 #![allow(non_camel_case_types, dead_code)]
 use lazy_static::lazy_static;
 use std::os::raw::{c_char, c_double, c_int, c_void};
 
 #[repr(C)]
 pub struct pp_ctx {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct pp_group {
     _private: [u8; 0],
 }
 
@@ -65,22 +70,61 @@ extern "C" {
     pub fn pp_rrt_extend_dubins(ctx: *mut pp_ctx, m: usize, qx: *const c_double, qy: *const c_double,
                                 radius: c_double, step: c_double, idx: *mut u32, yaw: *mut c_double, ok: *mut u8,
                                 nn_flags: c_int, collide_flags: c_int) -> c_int;
+
+    // one host process, several B200s: replicated tree / obstacles (ncclBroadcast), sliced batches
+    pub fn pp_group_create(devices: *const c_int, n_dev: c_int, out: *mut *mut pp_group) -> c_int;
+    pub fn pp_group_destroy(g: *mut pp_group);
+    pub fn pp_group_size(g: *mut pp_group) -> c_int;
+    pub fn pp_group_ctx(g: *mut pp_group, i: c_int) -> *mut pp_ctx;
+    pub fn pp_group_last_error(g: *mut pp_group) -> *const c_char;
+    pub fn pp_group_tree_upload(g: *mut pp_group, n: usize, x: *const c_double, y: *const c_double,
+                                yaw: *const c_double, parent: *const i32) -> c_int;
+    pub fn pp_group_tree_append(g: *mut pp_group, k: usize, x: *const c_double, y: *const c_double,
+                                yaw: *const c_double, parent: *const i32) -> c_int;
+    pub fn pp_group_obstacles_upload(g: *mut pp_group, bounds_x: *const c_double, bounds_y: *const c_double,
+                                     n_bounds: usize, ring_x: *const c_double, ring_y: *const c_double,
+                                     ring_off: *const u32, n_rings: usize) -> c_int;
+    pub fn pp_group_dubins_eval(g: *mut pp_group, n: usize, sx: *const c_double, sy: *const c_double,
+                                syaw: *const c_double, ex: *const c_double, ey: *const c_double,
+                                eyaw: *const c_double, radius_arr: *const c_double, radius: c_double,
+                                cost: *mut c_double, word: *mut u8, tpq: *mut c_double) -> c_int;
+    pub fn pp_group_collide_dubins(g: *mut pp_group, m: usize, sx: *const c_double, sy: *const c_double,
+                                   syaw: *const c_double, ex: *const c_double, ey: *const c_double,
+                                   eyaw: *const c_double, radius: c_double, step: c_double, ok: *mut u8,
+                                   flags: c_int) -> c_int;
+    pub fn pp_group_rrt_extend(g: *mut pp_group, m: usize, qx: *const c_double, qy: *const c_double, idx: *mut u32,
+                               yaw: *mut c_double, ok: *mut u8, nn_flags: c_int, collide_flags: c_int) -> c_int;
+    pub fn pp_group_rrt_extend_dubins(g: *mut pp_group, m: usize, qx: *const c_double, qy: *const c_double,
+                                      radius: c_double, step: c_double, idx: *mut u32, yaw: *mut c_double,
+                                      ok: *mut u8, nn_flags: c_int, collide_flags: c_int) -> c_int;
 }
 
-/// one context per process; pp_ctx is internally synchronised, so `&Ctx` may be shared by rayon workers
+/// an owned pp_ctx; internally synchronised, so `&Ctx` may be shared by rayon workers.  A context holds ONE
+/// obstacle set and ONE tree: every `rrt::Space` creates its own (`Ctx::new`), so planners never clobber each other.
 pub struct Ctx(pub *mut pp_ctx);
 unsafe impl Send for Ctx {}
 unsafe impl Sync for Ctx {}
 
-lazy_static! {
-    pub static ref CTX: Ctx = {
+impl Ctx {
+    pub fn new() -> std::sync::Arc<Ctx> {
         let dev = std::env::var("PP_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
         let mut p: *mut pp_ctx = std::ptr::null_mut();
         let rc = unsafe { pp_ctx_create(dev, &mut p) };
         // no CPU fallback: same failure style as the reference's expect()s (src/rrt.rs:64,67)
         assert!(rc == PP_OK, "pathplanning_b200: no sm_100 GPU context (status {})", rc);
-        Ctx(p)
-    };
+        std::sync::Arc::new(Ctx(p))
+    }
+}
+impl Drop for Ctx {
+    fn drop(&mut self) {
+        unsafe { pp_ctx_destroy(self.0) }
+    }
+}
+
+lazy_static! {
+    /// crate-level context of the STATELESS calls only (the `dubins` module, Dubins sampling of chains): they never
+    /// touch a tree or an obstacle set, so sharing it is harmless
+    pub static ref CTX: std::sync::Arc<Ctx> = Ctx::new();
 }
 
 pub fn check(rc: c_int, what: &str) {

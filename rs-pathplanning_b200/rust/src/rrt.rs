@@ -45,6 +45,9 @@ fn buffer_poly(poly: &Polygon<f64>, buffer: f64) -> Polygon<f64> {
 fn ring_soa(p: &Polygon<f64>) -> (Vec<f64>, Vec<f64>) { p.exterior().points_iter().map(|q| q.x_y()).unzip() }
 
 pub struct Space {
+    /// every Space owns its GPU context (one world + one tree), as an RRT owns its Space and its RTree in the
+    /// reference (src/rrt.rs:325-356): any number of Space / RRT pairs can live side by side
+    ctx: Arc<ffi::Ctx>,
     bounds: Polygon<f64>,
     robot: Robot,
     obstacles: Vec<Polygon<f64>>,
@@ -56,6 +59,7 @@ pub struct Space {
 
 impl Space {
     pub fn new(bounds: Polygon<f64>, robot: Robot, obstacle_list: Vec<Polygon<f64>>) -> Space {
+        let ctx = ffi::Ctx::new();
         let width = robot.get_width() / 2.0;
         let bounds = buffer_poly(&bounds, -width);
         let (bx, by) = ring_soa(&bounds);
@@ -77,12 +81,12 @@ impl Space {
         }
         ffi::check(
             unsafe {
-                ffi::pp_obstacles_upload(CTX.0, bx.as_ptr(), by.as_ptr(), bx.len(), ox.as_ptr(), oy.as_ptr(),
+                ffi::pp_obstacles_upload(ctx.0, bx.as_ptr(), by.as_ptr(), bx.len(), ox.as_ptr(), oy.as_ptr(),
                                          off.as_ptr(), obstacles.len())
             },
             "obstacles_upload",
         );
-        Space { bounds, robot, obstacles, minx, maxx, miny, maxy }
+        Space { ctx, bounds, robot, obstacles, minx, maxx, miny, maxy }
     }
 
     pub fn verify(&self, line: &LineString<f64>) -> bool {
@@ -90,7 +94,7 @@ impl Space {
         let off = [0u32, px.len() as u32];
         let mut ok = 0u8;
         ffi::check(
-            unsafe { ffi::pp_verify_polylines(CTX.0, 1, px.as_ptr(), py.as_ptr(), off.as_ptr(), &mut ok, 0) },
+            unsafe { ffi::pp_verify_polylines(self.ctx.0, 1, px.as_ptr(), py.as_ptr(), off.as_ptr(), &mut ok, 0) },
             "verify",
         );
         ok != 0
@@ -113,7 +117,7 @@ impl Space {
         let mut ok = vec![0u8; lines.len()];
         ffi::check(
             unsafe {
-                ffi::pp_verify_polylines(CTX.0, lines.len(), px.as_ptr(), py.as_ptr(), off.as_ptr(), ok.as_mut_ptr(), 0)
+                ffi::pp_verify_polylines(self.ctx.0, lines.len(), px.as_ptr(), py.as_ptr(), off.as_ptr(), ok.as_mut_ptr(), 0)
             },
             "verify_many",
         );
@@ -197,13 +201,13 @@ fn push_edge(e: &mut [Vec<f64>; 6], from: &Node, to: &Node) {
 }
 
 /// fused Dubins sample-and-verify of m independent edges: ok[i] = Space::verify(samples of edge i ++ [its end point])
-fn collide_dubins(e: &[Vec<f64>; 6], turn_radius: f64, step_size: f64) -> Vec<u8> {
+fn collide_dubins(ctx: &ffi::Ctx, e: &[Vec<f64>; 6], turn_radius: f64, step_size: f64) -> Vec<u8> {
     let m = e[0].len();
     let mut ok = vec![0u8; m];
     if m > 0 {
         ffi::check(
             unsafe {
-                ffi::pp_collide_dubins(CTX.0, m, e[0].as_ptr(), e[1].as_ptr(), e[2].as_ptr(), e[3].as_ptr(),
+                ffi::pp_collide_dubins(ctx.0, m, e[0].as_ptr(), e[1].as_ptr(), e[2].as_ptr(), e[3].as_ptr(),
                                        e[4].as_ptr(), e[5].as_ptr(), turn_radius, step_size, ok.as_mut_ptr(), 0)
             },
             "collide_dubins",
@@ -276,7 +280,7 @@ impl RRT {
         let root = Arc::new(Node::new_root(start.into(), start_yaw));
         *root.slot.lock().unwrap() = 0;
         let par = -1i32;
-        ffi::check(unsafe { ffi::pp_tree_upload(CTX.0, 1, &start.x, &start.y, &start_yaw, &par) }, "tree_upload");
+        ffi::check(unsafe { ffi::pp_tree_upload(space.ctx.0, 1, &start.x, &start.y, &start_yaw, &par) }, "tree_upload");
         RRT { goal, goal_yaw, max_iter, step_size, space, nodes: Arc::new(Mutex::new(vec![root])) }
     }
 
@@ -284,7 +288,7 @@ impl RRT {
         let (x, y) = point.x_y();
         let mut idx = 0xFFFF_FFFFu32;
         // the tree may grow between the query and the lookup (as under the reference's Mutex); indices stay valid
-        ffi::check(unsafe { ffi::pp_nn(CTX.0, 1, &x, &y, &mut idx, std::ptr::null_mut(), 0) }, "nn");
+        ffi::check(unsafe { ffi::pp_nn(self.space.ctx.0, 1, &x, &y, &mut idx, std::ptr::null_mut(), 0) }, "nn");
         if idx == 0xFFFF_FFFF { None } else { Some(self.nodes.lock().unwrap()[idx as usize].clone()) }
     }
 
@@ -302,7 +306,7 @@ impl RRT {
         if m == 0 {
             return self.space.verify(&vec![node.get_coord().x_y()].into());
         }
-        collide_dubins(&e, self.space.get_steer(), self.step_size).iter().all(|&v| v != 0)
+        collide_dubins(&self.space.ctx, &e, self.space.get_steer(), self.step_size).iter().all(|&v| v != 0)
     }
 
     pub fn check_finish(&self, node: Arc<Node>) -> Option<LineString<f64>> {
@@ -355,7 +359,7 @@ impl RRT {
                 push_edge(&mut e, v, &p); // chain[k] -> chain[k + 1]
             }
         }
-        let ok = collide_dubins(&e, self.space.get_steer(), self.step_size);
+        let ok = collide_dubins(&self.space.ctx, &e, self.space.get_steer(), self.step_size);
         let mut picks: Vec<Option<usize>> = Vec::with_capacity(nodes.len());
         for &(a, n) in spans.iter() {
             // .rev(): the valid candidate closest to the root wins; walking down from the root, the chain below
@@ -449,7 +453,7 @@ impl RRT {
                     let (x, y) = rnd_node.get_point().x_y();
                     let yaw = rnd_node.get_yaw();
                     let par = rnd_node.get_parent().map(|p| *p.slot.lock().unwrap() as i32).unwrap_or(-1);
-                    ffi::check(unsafe { ffi::pp_tree_append(CTX.0, 1, &x, &y, &yaw, &par) }, "tree_append");
+                    ffi::check(unsafe { ffi::pp_tree_append(self.space.ctx.0, 1, &x, &y, &yaw, &par) }, "tree_append");
                     nodes.push(rnd_node.clone());
                 }
                 if let Some(finish) = self.check_finish(rnd_node) {
@@ -477,7 +481,7 @@ impl RRT {
             let (mut idx, mut yaw, mut ok) = (vec![0u32; b], vec![0f64; b], vec![0u8; b]);
             ffi::check(
                 unsafe {
-                    ffi::pp_rrt_extend_dubins(CTX.0, b, px.as_ptr(), py.as_ptr(), steer, self.step_size,
+                    ffi::pp_rrt_extend_dubins(self.space.ctx.0, b, px.as_ptr(), py.as_ptr(), steer, self.step_size,
                                               idx.as_mut_ptr(), yaw.as_mut_ptr(), ok.as_mut_ptr(), 0, 0)
                 },
                 "rrt_extend_dubins",
@@ -500,7 +504,7 @@ impl RRT {
                 fpar.push(c.get_parent().map(|p| *p.slot.lock().unwrap() as i32).unwrap_or(-1));
             }
             ffi::check(
-                unsafe { ffi::pp_tree_append(CTX.0, fresh.len(), fx.as_ptr(), fy.as_ptr(), fyaw.as_ptr(), fpar.as_ptr()) },
+                unsafe { ffi::pp_tree_append(self.space.ctx.0, fresh.len(), fx.as_ptr(), fy.as_ptr(), fyaw.as_ptr(), fpar.as_ptr()) },
                 "tree_append",
             );
             for c in fresh.iter() {
@@ -508,15 +512,9 @@ impl RRT {
                 nodes.push(c.clone());
             }
             drop(nodes);
-            // goal -> node for every fresh node in one launch; only the nodes that see the goal are finalized
-            let goal_node = Node::new_root(self.goal.into(), self.goal_yaw);
-            let mut e: [Vec<f64>; 6] = Default::default();
-            for c in fresh.iter() {
-                push_edge(&mut e, &goal_node, c);
-            }
-            let g_ok = collide_dubins(&e, steer, self.step_size);
-            let reach: Vec<Arc<Node>> =
-                fresh.iter().zip(g_ok.iter()).filter(|p| *p.1 != 0).map(|p| p.0.clone()).collect();
+            // check_finish for every fresh node, as plan_one does (src/rrt.rs:591): the goal connects to the OPTIMIZED
+            // node, whose yaw differs from the fresh node's, so a blocked goal -> fresh edge decides nothing
+            let reach: Vec<Arc<Node>> = fresh.clone();
             for line in self.check_finish_many(&reach).into_iter().flatten() {
                 let len = line.euclidean_length();
                 if best.as_ref().map_or(true, |cur| len < cur.0) {

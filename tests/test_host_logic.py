@@ -47,14 +47,15 @@ def test_module_mirror_host_pieces(pp):
     assert r.Robot(1.0, 2.0, 0.8).get_steer() == 0.8
 
 
-def test_shard_range(pp):
-    from rs_pathplanning_b200 import sharding
-    for n, world in [(16, 1), (17, 2), (1 << 24, 8), (5, 8)]:
-        cuts = [sharding.shard_range(n, r, world) for r in range(world)]
+def test_slice_bounds(pp):
+    """pp_slice_bounds (the C-ABI's slicing rule, used by pp_group_* and by bench.py's ranks): contiguous, covering,
+    [g*n/G, (g+1)*n/G)"""
+    for n, world in [(16, 1), (17, 2), (1 << 24, 8), (5, 8), (0, 4), ((1 << 40) + 3, 7)]:
+        cuts = [pp.slice_bounds(n, world, r) for r in range(world)]
         assert cuts[0][0] == 0 and cuts[-1][1] == n
         assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
-    with pytest.raises(ValueError):
-        sharding.shard_range(10, 2, 2)
+        assert cuts == [((r * n) // world, ((r + 1) * n) // world) for r in range(world)]
+    assert pp.slice_bounds(10, 2, 5) == (5, 10)  # out-of-range part is clamped, never out of bounds
 
 
 def _free_port():
@@ -74,7 +75,6 @@ def _worker(rank, world, port, outdir):
     import __graft_entry__ as graft
     pp = graft.import_package()
     O = graft.import_oracle()
-    from rs_pathplanning_b200 import sharding
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     n_nodes, m_total = 3000, 4001
     # replicated tree: only rank 0 holds the data before the broadcast
@@ -83,15 +83,23 @@ def _worker(rank, world, port, outdir):
         tree = torch.from_numpy(np.stack([nx, ny, nyaw]))
     else:
         tree = torch.zeros((3, n_nodes), dtype=torch.float64)
-    sharding.replicate(tree, 0)
-    lo, hi = sharding.shard_range(m_total, rank, world)
+    dist.broadcast(tree, 0)  # on the GPU box: pp_tree_upload_bcast (ncclBroadcast inside the library)
+    # the launcher's channel also carries the 128-byte NCCL id from rank 0 to the others (pp_ctx_comm_init)
+    ident = [bytes(range(128)) if rank == 0 else None]
+    dist.broadcast_object_list(ident, 0)
+    assert ident[0] == bytes(range(128))
+    lo, hi = pp.slice_bounds(m_total, world, rank)
     qx = pp.synth.uniform(pp.synth.SEED_C4_Q, 0, hi - lo, 0.0, 100.0, first=lo)
     qy = pp.synth.uniform(pp.synth.SEED_C4_Q, 1, hi - lo, 0.0, 100.0, first=lo)
     # the GPU kernels cannot run here; the oracle stands in for the per-rank compute so that the host-side
     # slicing / replication / gathering logic is what is under test
     idx, _ = O.nn_brute(tree[0].numpy(), tree[1].numpy(), qx, qy)
-    t = sharding.max_over_ranks(10.0 + rank)
-    allidx = sharding.gather_to_rank0(idx)
+    tt = torch.tensor([10.0 + rank], dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)  # multi-GPU timings are the max over ranks
+    t = float(tt.item())
+    bucket = [None] * world if rank == 0 else None
+    dist.gather_object(idx, bucket, dst=0)
+    allidx = np.concatenate(bucket) if rank == 0 else None
     if rank == 0:
         np.save(os.path.join(outdir, "idx.npy"), allidx)
         np.save(os.path.join(outdir, "t.npy"), np.array([t]))

@@ -9,7 +9,8 @@ HEADER = os.path.join(ROOT, "include", "pathplanning_b200.h")
 RUST = os.path.join(ROOT, "rs-pathplanning_b200", "rust", "src")
 
 C_SCALARS = {"int": "c_int", "double": "c_double", "size_t": "usize", "uint8_t": "u8", "uint32_t": "u32",
-             "uint64_t": "u64", "int32_t": "i32", "void": "c_void", "char": "c_char", "pp_ctx": "pp_ctx"}
+             "uint64_t": "u64", "int32_t": "i32", "void": "c_void", "char": "c_char", "pp_ctx": "pp_ctx",
+             "pp_group": "pp_group"}
 
 
 def _split_args(s):
