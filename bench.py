@@ -7,8 +7,9 @@ One JSON line on stdout (rank 0).  Primary metric: batched Dubins pose-pair eval
 config C3 (2^24 pairs per GPU, radius 1.0, shortest-word selection + length only).  The same line carries
 the RRT extend-step (C4) and Dubins-edge verify (C5 slice) numbers under "workloads".
 N > 1 is launched by torch.distributed.run, one rank per GPU; the path shards with no data-path collective
-(weak scaling: every GPU takes its own 2^24-pair slice); the tree / obstacle buffers of the secondary
-workloads are replicated with one NCCL broadcast outside the timed region.
+(weak scaling: every GPU takes its own 2^24-pair slice; the "strong" block splits ONE 2^24-pair and ONE 2^22-edge
+batch over the ranks); tree / obstacle buffers are replicated by the library's own ncclBroadcast
+(pp_tree_upload_bcast, pp_obstacles_upload_bcast), and the 512-node tail broadcast is timed on its own.
 """
 from __future__ import annotations
 
@@ -27,14 +28,36 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
 N_PAIRS = 1 << 24          # C3, per GPU
+PASSES_PER_STEP = 64       # a step = 64 passes of the kernel over the 2^24-pair batch (inputs 768 MiB > L2, so a
+                           # pass never finds its data in cache): K steps then last >= 0.4 s and the clock samples,
+                           # the throttle flags and the driver's own clock around the run describe the timed region
 W_INSTR_PER_PAIR = 1100.0  # fixed yard-stick of SURVEY.md Appendix D (FP64-pipe thread-instructions per pair)
 BYTES_PER_PAIR = 57.0      # 48 B read + 8 B cost + 1 B word
-NCU_FP64_INSTR_PER_PAIR = 490.0  # DFMA + DADD + DMUL + DSETP executed per pair (ncu source page, same capture)
-NCU_DRAM_BYTES_PER_LAUNCH = 949.3e6  # measured once per kernel change by ncu (see profiles/r01_summary.md)
-NCU_NN_GRID_L2_BYTES = 25431908 * 32.0  # lts__t_sectors.sum x 32 B, pp_nn_grid_kernel on 2^20 queries / 2^20 nodes
 FP64_PEAK_NOMINAL = 148 * 64 * 1.965e9  # lanes * clock: used only if the live DFMA measurement fails
 C4_M, C4_NODES, C4_RINGS = 1 << 20, 1 << 20, 10_000
 C5_EDGES, C5_RINGS = 1 << 19, 100_000  # the per-GPU slice of config 5 (2^22 edges over 8 GPUs)
+C5_EDGES_TOTAL = 1 << 22
+# the workload both arms are measured on (the driver compares the two `config` objects)
+C3_CONFIG = {"workload": "c3_batched_dubins: 2^24 random pose pairs per GPU ('mixed' U[-2,2)^2 positions, U[-pi,pi) yaws, "
+                         "seed 0xD0B10003), radius 1.0, shortest-word selection + length only",
+             "pairs_per_gpu": N_PAIRS, "l2": "inputs (768 MiB) larger than L2, no flush needed",
+             "sharding": "contiguous slice per rank, no data-path collective"}
+
+
+def kernel_facts():
+    """per-kernel figures read from the committed ncu captures (tools/ncu_facts.py -> profiles/kernel_facts.json):
+    executed FP64-pipe instructions and DRAM bytes per launch.  Nothing here is a constant of this file."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_facts.json")))
+    except Exception:
+        return {}
+
+
+def fact(facts, prefix, key, default=None):
+    for name, f in facts.items():
+        if name.startswith(prefix) and f.get(key) is not None:
+            return f[key], f.get("source")
+    return default, None
 
 
 def log(*a):
@@ -101,44 +124,60 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def load_synth_standalone():
+    """the synthetic-input generator WITHOUT importing the product package (whose __init__ loads the CUDA library):
+    the reference arm must not map libpathplanning_b200.so at all"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pp_synth_standalone",
+                                                  os.path.join(ROOT, "rs-pathplanning_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def run_reference(args):
-    """the reference's CPU implementation of the path = the C restatement (oracle port; no rustc here),
-    all host threads, bounded sample per step"""
+    """the reference's CPU implementation of the path = the C restatement (oracle port; no rustc here) on all host
+    threads, on the SAME workload: every step is one pass over the full 2^24-pair batch"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     O = graft.import_oracle()
     O.build()
-    pp_synth = graft.import_package().synth
+    synth = load_synth_standalone()
+    assert "rs_pathplanning_b200" not in sys.modules
     threads = O.max_threads()
-    n = 1 << 21
-    sx, sy, syaw, ex, ey, eyaw = pp_synth.dubins_pairs(n)
-    for _ in range(max(args.warmup, 1)):
-        O.dubins_eval_batch(sx[: n // 8], sy[: n // 8], syaw[: n // 8], ex[: n // 8], ey[: n // 8], eyaw[: n // 8], 1.0,
-                            want_flags=False)
+    n = N_PAIRS
+    sx, sy, syaw, ex, ey, eyaw = synth.dubins_pairs(n)
+    cost, word = None, None
+    for _ in range(max(min(args.warmup, 2), 1)):
+        k = n // 8
+        O.dubins_eval_batch(sx[:k], sy[:k], syaw[:k], ex[:k], ey[:k], eyaw[:k], 1.0, want_flags=False)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.dubins_eval_batch(sx, sy, syaw, ex, ey, eyaw, 1.0, want_flags=False)
+        cost, word, _, _ = O.dubins_eval_batch(sx, sy, syaw, ex, ey, eyaw, 1.0, want_flags=False)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = f"{args.steps} steps x 2^21 pairs of the C3 'mixed' distribution (seed 0xD0B10003), OpenMP static partition"
+    sample = f"{args.steps} steps x the full 2^24-pair C3 batch (seed 0xD0B10003), OpenMP static partition over {threads} threads"
     line = {
         "impl": "reference", "metric": "dubins_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "c3_batched_dubins: 2^24 random pose pairs per GPU, radius 1.0, shortest-word selection + "
-                               "length only (reference arm: bounded 2^21-pair sample per step on the host cores)"},
+        "config": C3_CONFIG,
+        "step": {"passes_per_step": 1, "pairs_per_step": n},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "C restatement of src/dubins.rs (oracle/pp_oracle.c), not rustc output: no Rust toolchain in the image",
+        "word_hist": np.bincount(word, minlength=6)[:6].tolist(),
+        "note": "C restatement of src/dubins.rs (oracle/pp_oracle.c), not rustc output: no Rust toolchain in the image; "
+                "parity of this oracle is UNPINNED by the reference (it ships no tests)",
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ own arm
 def bind_to_gpu_numa(local):
-    """pin this rank's host threads (hence its first-touch pinned buffers) to the NUMA node its GPU hangs off:
-    with 8 ranks streaming 50 GB/s each, remote-socket staging halves the end-to-end rate"""
+    """pin this rank's host threads (hence its first-touch pinned buffers) to the NUMA node its GPU hangs off: with 8
+    ranks streaming 50 GB/s each, remote-socket staging halves the end-to-end rate.  Always returns a dict that says
+    what was done or WHY nothing could be done."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -148,20 +187,26 @@ def bind_to_gpu_numa(local):
         bus = bus.lower()
         if len(bus.split(":")[0]) == 8:  # nvml pads the domain to 8 hex digits, sysfs uses 4
             bus = bus[4:]
-        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")] \
+            if os.path.isdir("/sys/devices/system/node") else []
+        path = f"/sys/bus/pci/devices/{bus}/numa_node"
+        if not os.path.exists(path):
+            return {"bound": False, "reason": f"{path} does not exist", "host_numa_nodes": len(nodes)}
+        node = int(open(path).read().strip())
         if node < 0:
-            return None
+            return {"bound": False, "reason": "sysfs numa_node = -1 for the GPU's PCI device: the (virtualised) host "
+                    "exposes no GPU-to-node affinity", "host_numa_nodes": len(nodes)}
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
         cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return {"numa_node": node, "cpus": len(cpus)}
+        if not cpus:
+            return {"bound": False, "reason": f"no allowed CPU on node {node}", "host_numa_nodes": len(nodes)}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "numa_node": node, "cpus": len(cpus), "host_numa_nodes": len(nodes)}
     except Exception as e:  # pragma: no cover
-        return {"error": str(e)[:80]}
-    return None
+        return {"bound": False, "reason": f"{type(e).__name__}: {e}"[:120]}
 
 
 def time_steps(torch, dist, fn, steps, warmup, world):
@@ -199,12 +244,18 @@ def run_own(args):
     if world != args.gpus and world > 1:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}")
     torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa(local) if world > 1 else None
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = pp.Context(local)
+    if world > 1:
+        # the library's own communicator (ncclBroadcast of tree / tail / obstacles inside the C-ABI): rank 0 makes the
+        # id, the launcher's channel (torch.distributed) hands the 128 bytes to the other ranks
+        ident = [pp.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, 0)
+        ctx.comm_init(ident[0], world, rank)
     # a dedicated non-default stream shared by torch (events, copies) and the library's launches, so that
     # torch.cuda.Event brackets exactly our kernels (the legacy default stream's handle 0 means "own stream")
     stream = torch.cuda.Stream(device=dev)
@@ -213,6 +264,7 @@ def run_own(args):
     peaks = measured_peaks()
     hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    facts = kernel_facts()
 
     # ---- FP64 pipe peak, measured live
     try:
@@ -230,57 +282,76 @@ def run_own(args):
     d_word = torch.empty(n, dtype=torch.uint8, device=dev)
     log(f"[rank {rank}] inputs ready in {time.time() - t_gen:.1f}s")
 
-    def step():
+    def one_pass():
         ctx.dubins_eval_dev(n, *d_in, 1.0, d_cost, d_word)
+
+    def step():
+        for _ in range(PASSES_PER_STEP):
+            one_pass()
 
     sampler = ClockSampler(local) if rank == 0 else None
     ctx.timing_enable(True)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    # ~1 s of identical untimed steps directly before the timed region: the 100 ms nvidia-smi samples then
-    # describe the clocks under this load even when K steps last only a few milliseconds
-    t_load = time.time()
-    while time.time() - t_load < (0.0 if args.profile else 1.0):
-        for _ in range(20):
-            step()
-        torch.cuda.synchronize()
     ctx.timing_reset()
     l0 = ctx.launch_count
     ms, t0, t1 = time_steps(torch, dist, step, args.steps, 0, world)
     launches = ctx.launch_count - l0
     k_ms, k_n = ctx.timing_get("dubins_eval")
     ctx.timing_enable(False)
-    clocks = sampler.stop(t_load + 0.3, t1) if sampler else None
+    clocks = sampler.stop(t0, t1) if sampler else None
     if clocks is not None:
-        clocks["window"] = "~1 s of identical untimed steps immediately before the timed region + the timed region"
-    value = world * n * args.steps / (ms * 1e-3)
+        clocks["window"] = f"the timed region itself ({(t1 - t0):.2f} s of wall clock)"
+    value = world * n * PASSES_PER_STEP * args.steps / (ms * 1e-3)
     k_avg_ms = k_ms / max(k_n, 1)
     pairs_per_s_kernel = n / (k_avg_ms * 1e-3)
 
     # sanity of what was computed (never a fallback): word histogram on rank 0
     hist = torch.bincount(d_word.to(torch.int64), minlength=256)[:6].tolist()
 
-    # ---- e2e through the C-ABI with pinned HOST buffers (H2D + kernel + D2H inside the timed region)
+    # ---- e2e through the C-ABI with HOST buffers (H2D + kernel + D2H inside the timed region): pinned buffers of the
+    # library (pp_host_alloc), and the plain pageable arrays a caller holding Vec<f64> / numpy memory passes
     e2e_steps = max(1, min(args.steps, 3))
+    d_cost_host, d_word_host = d_cost.cpu().numpy(), d_word.cpu().numpy()
+
+    def e2e_leg(arrays, out):
+        ctx.dubins_eval(*arrays, radius=1.0, want_tpq=False, out=out)  # warm-up
+        if world > 1:
+            dist.barrier()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.dubins_eval(*arrays, radius=1.0, want_tpq=False, out=out)
+        t = torch.tensor([time.perf_counter() - te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        same = bool(np.array_equal(out[0], d_cost_host) and np.array_equal(out[1], d_word_host))
+        return world * n * e2e_steps / float(t.item()), same
+
     pins = [pp.PinnedArray(n, np.float64) for _ in range(6)]
     for p, a in zip(pins, host):
         p.array[:] = a
     pcost, pword = pp.PinnedArray(n, np.float64), pp.PinnedArray(n, np.uint8)
-    ctx.dubins_eval(*[p.array for p in pins], radius=1.0, want_tpq=False, out=(pcost.array, pword.array, None))  # warm-up
+    e2e_value, same = e2e_leg([p.array for p in pins], (pcost.array, pword.array, None))
+    del pins, pcost, pword
+    pg_cost, pg_word = np.empty(n, np.float64), np.empty(n, np.uint8)
+    e2e_pageable, same_pg = e2e_leg(list(host), (pg_cost, pg_word, None))
+    del pg_cost, pg_word
+    e2e_launches = 2 * 16 * (e2e_steps + 1)
+    # copy-only ceilings of THIS box, same bytes, no kernel (all ranks at once: the host side is shared)
     if world > 1:
         dist.barrier()
-    te = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.dubins_eval(*[p.array for p in pins], radius=1.0, want_tpq=False, out=(pcost.array, pword.array, None))
-    e2e_s = time.perf_counter() - te
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(e2e_t.item())
-    same = bool(np.array_equal(pcost.array, d_cost.cpu().numpy()) and np.array_equal(pword.array, d_word.cpu().numpy()))
-    e2e_launches = 16 * (e2e_steps + 1)
-    del pins, host
+    copy_ms = {k: ctx.measure_copy(48 * n, 9 * n, pinned=(k == "pinned")) for k in ("pinned", "pageable")}
+    for k in copy_ms:
+        t = torch.tensor([copy_ms[k]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_ms[k] = float(t.item())
+    ceil_pinned = world * n / (copy_ms["pinned"] * 1e-3)
+    ceil_pageable = world * n / (copy_ms["pageable"] * 1e-3)
+    del host
+
+    strong = strong_block(args, torch, dist, pp, ctx, dev, rank, world)
 
     workloads = {}
     if not args.skip_secondary:
@@ -291,63 +362,176 @@ def run_own(args):
             d.copy_(torch.from_numpy(a))
         del far
         for _ in range(3):
-            step()
+            one_pass()
         far_steps = max(1, min(args.steps, 10))
         l0 = ctx.launch_count
-        far_ms, _, _ = time_steps(torch, dist, step, far_steps, 0, world)
+        far_ms, _, _ = time_steps(torch, dist, one_pass, far_steps, 0, world)
         far_hist = torch.bincount(d_word.to(torch.int64), minlength=256)[:6].tolist()
         workloads["dubins_far"] = {
             "metric": "dubins_pairs_per_s", "value": world * n * far_steps / (far_ms * 1e-3), "unit": "pairs/s",
             "ms_per_step": far_ms / far_steps, "steps": far_steps, "gpu_launches": ctx.launch_count - l0,
             "config": {"workload": "c3 'far': 2^24 pose pairs per GPU, positions U[-50,50)^2, yaws U[-pi,pi), radius 1.0",
                        "word_hist_rank0": far_hist}}
-        workloads.update(secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak))
+        del d_in
+        workloads.update(secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak, facts))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu_baseline = cpu_baseline_leg(pp)
 
     if rank == 0:
-        achieved = pairs_per_s_kernel * W_INSTR_PER_PAIR / 1e9
+        # executed FP64-pipe work per pair: from the committed ncu capture of this kernel (profiles/kernel_facts.json),
+        # not a constant of this file; `frac` = live pairs/s x that / the live DFMA peak = the pipe utilisation
+        ex_instr, ex_src = fact(facts, "pp_dubins_eval_kernel", "fp64_thread_instr_per_unit")
+        traffic, tr_src = fact(facts, "pp_dubins_eval_kernel", "dram_bytes")
+        busy_ncu, _ = fact(facts, "pp_dubins_eval_kernel", "fp64_pipe_pct_active")
+        achieved = pairs_per_s_kernel * ex_instr / 1e9 if ex_instr else None
         line = {
             "metric": "dubins_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c3_batched_dubins: 2^24 random pose pairs per GPU ('mixed' U[-2,2)^2 positions, "
-                                   "U[-pi,pi) yaws, seed 0xD0B10003), radius 1.0, shortest-word selection + length only",
-                       "pairs_per_gpu": n, "l2": "inputs (768 MiB) larger than L2, no flush needed",
-                       "sharding": "contiguous slice per rank, no data-path collective", "word_hist_rank0": hist},
+            "config": C3_CONFIG,
+            "step": {"passes_per_step": PASSES_PER_STEP, "pairs_per_step": n * PASSES_PER_STEP, "word_hist_rank0": hist,
+                     "timed_region_s": ms * 1e-3,
+                     "why": "one pass over the 2^24-pair batch lasts 0.6 ms; a step repeats it so that the timed region is "
+                            ">= 0.4 s (inputs exceed L2: no pass finds its data cached)"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 9 * n,
                     "steps": e2e_steps, "matches_device_run": same,
-                    "how": "pp_dubins_eval on pinned host buffers: 16 chunks over 3 streams, copies inside the timed region",
+                    "how": "pp_dubins_eval on pinned host buffers (pp_host_alloc): 16 chunks over 3 streams, copies inside "
+                           "the timed region",
+                    "copy_ceiling": {"value": ceil_pinned, "unit": "pairs/s", "ms": copy_ms["pinned"],
+                                     "what": "the same 805 MB up + 151 MB down per rank, both directions at once from pinned "
+                                             "memory, all ranks together, NO kernel (pp_measure_copy, best of 3)"},
+                    "frac_of_copy_ceiling": e2e_value / ceil_pinned,
                     "numa_binding_rank0": numa},
-            "gpu_launches": launches + e2e_launches + sum(w.get("gpu_launches", 0) for w in workloads.values()),
+            "e2e_pageable": {"value": e2e_pageable, "unit": "pairs/s", "h2d_bytes_per_step": 48 * n,
+                             "d2h_bytes_per_step": 9 * n, "steps": e2e_steps, "matches_device_run": same_pg,
+                             "how": "the same call on ordinary pageable arrays (what a Rust caller holding Vec<f64> passes): "
+                                    "the driver stages every copy through its own pinned bounce buffers",
+                             "copy_ceiling": {"value": ceil_pageable, "unit": "pairs/s", "ms": copy_ms["pageable"]},
+                             "frac_of_copy_ceiling": e2e_pageable / ceil_pageable},
+            "gpu_launches": launches + e2e_launches + sum(w.get("gpu_launches", 0) for w in workloads.values())
+            + strong.get("gpu_launches", 0),
             "gpu_launches_primary_timed_region": launches,
             "clocks": clocks,
             "roofline": {
                 "kernel": "pp_dubins_eval_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e9,
-                "unit": "Ginstr/s", "frac": achieved * 1e9 / fp64_peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, dram__bytes_read.sum + "
-                "dram__bytes_write.sum per launch of 2^24 pairs (profiles/r01_dubins_eval_final4_raw.csv); algorithmic 956.3e6",
-                "fp64_pipe_busy_ncu": 0.728, "fp64_instr_per_pair_ncu": NCU_FP64_INSTR_PER_PAIR,
-                # `frac` follows the contract (SURVEY 8d yard-stick W = 1100 per pair) and exceeds 1 because the
-                # kernel executes only ~490 FP64-pipe instructions per pair (ncu source page); with the executed count the same
-                # timing gives the pipe utilisation ncu reports
-                "frac_of_executed_fp64_work": pairs_per_s_kernel * NCU_FP64_INSTR_PER_PAIR / fp64_peak,
-                "per_unit": f"W = {W_INSTR_PER_PAIR:.0f} FP64-pipe thread-instructions per pair (fixed yard-stick, SURVEY App. D)",
+                "unit": "Ginstr/s", "frac": (achieved * 1e9 / fp64_peak) if achieved else None,
+                "per_unit": f"{ex_instr:.0f} executed FP64-pipe thread-instructions per pair, from {ex_src}" if ex_instr else None,
+                "fp64_pipe_busy_ncu": busy_ncu / 100.0 if busy_ncu else None,
+                "traffic": traffic, "traffic_source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per "
+                f"launch of 2^24 pairs ({tr_src}); algorithmic {BYTES_PER_PAIR * n:.4g}",
+                # the SURVEY 8d yard-stick (W = 1100 instructions per pair, fixed before any kernel existed) is 2.2x the
+                # work this kernel executes, so the fraction against it exceeds 1; kept for continuity only
+                "yardstick_frac": pairs_per_s_kernel * W_INSTR_PER_PAIR / fp64_peak,
+                "yardstick_per_unit": f"W = {W_INSTR_PER_PAIR:.0f} FP64-pipe thread-instructions per pair (SURVEY App. D)",
                 "peak_source": fp64_src, "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n,
                 "hbm_view": {"bound": "hbm", "achieved": pairs_per_s_kernel * BYTES_PER_PAIR / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": pairs_per_s_kernel * BYTES_PER_PAIR / 1e9 / hbm_peak,
                              "per_unit": "57 B per pair (48 read + 9 written)", "peak_source": hbm_src},
             },
             "cpu_baseline": cpu_baseline,
+            "strong": strong,
             "workloads": workloads,
+            "parity": "oracle port, UNPINNED by the reference (it ships no tests and cannot be compiled here)",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def strong_block(args, torch, dist, pp, ctx, dev, rank, world):
+    """fixed-TOTAL work split over the ranks (north_star: "16M pairs (1/2/4/8 B200)", "4M edges sharded across 8"):
+    C3 = ONE 2^24-pair batch, C5 = ONE 2^22-edge batch; rank r takes the contiguous slice [r*n/W, (r+1)*n/W)
+    (pp_slice_bounds).  Device-resident times are CUDA events on the launching stream, max over ranks; the end-to-end
+    C3 figure goes through the host entry point with pinned buffers.  Also the latency of the only collective on the
+    path: a 512-node pp_tree_append_bcast (H2D on the root + ncclBroadcast of the tail + the finishing kernels)."""
+    out = {"scaling": "strong", "n_gpus": world}
+    steps = max(1, min(args.steps, 10))
+    l_start = ctx.launch_count
+    # ---- C3, 2^24 pairs in total
+    lo, hi = pp.slice_bounds(N_PAIRS, world, rank)
+    cnt = hi - lo
+    host = pp.synth.dubins_pairs(cnt, "mixed", first=lo)
+    d_in = [torch.from_numpy(a).to(dev) for a in host]
+    d_cost = torch.empty(cnt, dtype=torch.float64, device=dev)
+    d_word = torch.empty(cnt, dtype=torch.uint8, device=dev)
+    fn = lambda: ctx.dubins_eval_dev(cnt, *d_in, 1.0, d_cost, d_word)  # noqa: E731
+    ms, _, _ = time_steps(torch, dist, fn, steps * 8, 3, world)
+    pins = [pp.PinnedArray(cnt, np.float64) for _ in range(6)]
+    for p_, a in zip(pins, host):
+        p_.array[:] = a
+    pc, pw = pp.PinnedArray(cnt, np.float64), pp.PinnedArray(cnt, np.uint8)
+    arrays, outs = [p_.array for p_ in pins], (pc.array, pw.array, None)
+    ctx.dubins_eval(*arrays, radius=1.0, want_tpq=False, out=outs)
+    if world > 1:
+        dist.barrier()
+    te = time.perf_counter()
+    for _ in range(3):
+        ctx.dubins_eval(*arrays, radius=1.0, want_tpq=False, out=outs)
+    t = torch.tensor([time.perf_counter() - te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # checksum of the gathered result (the same for every device count: pure slicing)
+    chk = torch.tensor([float(np.sum(pc.array)), float(np.sum(pw.array.astype(np.float64)))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+    out["c3"] = {"metric": "dubins_pairs_per_s", "total_pairs": N_PAIRS, "value": N_PAIRS * steps * 8 / (ms * 1e-3),
+                 "unit": "pairs/s", "ms_per_batch": ms / (steps * 8),
+                 "e2e": {"value": N_PAIRS * 3 / float(t.item()), "unit": "pairs/s", "ms_per_batch": float(t.item()) / 3 * 1e3},
+                 "checksum": {"sum_cost": float(chk[0].item()), "sum_word": float(chk[1].item())}}
+    del pins, pc, pw, d_in, d_cost, d_word, host
+    # ---- C5, 2^22 Dubins edges in total vs 100 k rings (replicated by the library's broadcast)
+    e_lo, e_hi = pp.slice_bounds(C5_EDGES_TOTAL, world, rank)
+    e = e_hi - e_lo
+    if rank == 0:
+        bounds5, rings5 = pp.synth.circle_world(C5_RINGS, rmin=0.5, rmax=1.5)
+        ctx.obstacles_upload_bcast(0, bounds5, rings5)
+    else:
+        ctx.obstacles_upload_bcast(0)
+    edges = [torch.from_numpy(a).to(dev) for a in pp.synth.dubins_edges(e, first=e_lo)]
+    ok5 = torch.empty(e, dtype=torch.uint8, device=dev)
+    fn = lambda: ctx.collide_dubins_dev(e, *edges, 1.0, 0.05, ok5)  # noqa: E731
+    ms, _, _ = time_steps(torch, dist, fn, steps, 2, world)
+    free = ok5.sum().to(torch.float64)
+    if world > 1:
+        dist.all_reduce(free, op=dist.ReduceOp.SUM)
+    out["c5"] = {"metric": "dubins_edges_verified_per_s", "total_edges": C5_EDGES_TOTAL,
+                 "value": C5_EDGES_TOTAL * steps / (ms * 1e-3), "unit": "edges/s", "ms_per_batch": ms / steps,
+                 "free_edges": int(free.item())}
+    del edges, ok5
+    # ---- the collective: 512-node append, tail broadcast
+    rng = np.random.default_rng(3)
+    base = 1 << 16
+    bx, by = rng.uniform(0, 1000, base), rng.uniform(0, 1000, base)
+    if rank == 0:
+        ctx.tree_upload_bcast(0, base, bx, by)
+    else:
+        ctx.tree_upload_bcast(0, base)
+    k, reps = 512, 40
+    tx, ty = rng.uniform(0, 1000, k), rng.uniform(0, 1000, k)
+    for _ in range(3):
+        ctx.tree_append_bcast(0, k, tx, ty) if rank == 0 else ctx.tree_append_bcast(0, k)
+    if world > 1:
+        dist.barrier()
+    te = time.perf_counter()
+    for _ in range(reps):
+        ctx.tree_append_bcast(0, k, tx, ty) if rank == 0 else ctx.tree_append_bcast(0, k)
+    t = torch.tensor([time.perf_counter() - te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sizes = torch.tensor([ctx.tree_size], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(sizes, op=dist.ReduceOp.MIN)
+    out["tree_append_512"] = {"ms": float(t.item()) / reps * 1e3, "reps": reps, "bytes_broadcast": k * 28,
+                              "tree_size_all_ranks": int(sizes.item()),
+                              "what": "pp_tree_append_bcast of 512 nodes: H2D on the root, one fused ncclBroadcast of the "
+                                      "tail (x, y, yaw, parent) over NVLink, fp32 copies + padding kernels, stream sync; "
+                                      "wall clock, max over ranks (N = 1: no collective)"}
+    out["gpu_launches"] = ctx.launch_count - l_start
+    return out
 
 
 def cpu_baseline_leg(pp):
@@ -402,23 +586,22 @@ def cpu_baseline_leg(pp):
             "note": "C restatement of src/dubins.rs (oracle/pp_oracle.c, gcc -O3 -ffp-contract=off -fno-fast-math), not rustc output"}
 
 
-def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak):
+def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak, facts):
     """C4 (RRT extend step: NN + straight-edge verify) and the per-GPU slice of C5 (Dubins-edge verify)"""
     out = {}
     steps = max(1, min(args.steps, 10))      # the millisecond-scale workloads
     slow_steps = max(1, min(args.steps, 2))  # the two deliberately slow yard-stick scans (0.36 / 0.48 s per step)
-    # ---- C4: replicated tree + obstacles (rank 0 generates, one NCCL broadcast), queries sharded
+    # ---- C4: tree + obstacles replicated INSIDE the library (rank 0 holds them, pp_tree_upload_bcast /
+    # pp_obstacles_upload_bcast = ncclBroadcast over NVLink, outside the timed region), queries sharded
     m = C4_M
     if rank == 0:
         _, _, nx, ny, nyaw = pp.synth.extend_inputs(1, C4_NODES)
-        tree = torch.from_numpy(np.stack([nx, ny, nyaw])).to(dev)
+        bounds, rings = pp.synth.circle_world(C4_RINGS)
+        ctx.tree_upload_bcast(0, C4_NODES, nx, ny, nyaw)
+        ctx.obstacles_upload_bcast(0, bounds, rings)
     else:
-        tree = torch.empty((3, C4_NODES), dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.broadcast(tree, 0)  # NVLink/NVSwitch; the only collective on the path, outside the timed region
-    ctx.tree_upload_dev(C4_NODES, tree[0], tree[1], tree[2])
-    bounds, rings = pp.synth.circle_world(C4_RINGS)
-    ctx.obstacles_upload(bounds, rings)
+        ctx.tree_upload_bcast(0, C4_NODES)
+        ctx.obstacles_upload_bcast(0)
     qx = torch.from_numpy(pp.synth.uniform(pp.synth.SEED_C4_Q, 0, m, 0.0, 1000.0, first=rank * m)).to(dev)
     qy = torch.from_numpy(pp.synth.uniform(pp.synth.SEED_C4_Q, 1, m, 0.0, 1000.0, first=rank * m)).to(dev)
     idx = torch.empty(m, dtype=torch.int32, device=dev)
@@ -474,9 +657,9 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
                                       "latency-bound gather, not a stream",
                           # what actually bounds it (ncu --set full, profiles/r01_rrt_kernels_final6_raw.csv): 25.4 M L2
                           # sectors per launch of 2^20 queries, l1tex throughput 78 %, lts throughput 60 %
-                          "l2_view": {"l2_bytes_per_launch_ncu": NCU_NN_GRID_L2_BYTES, "unit": "GB/s",
-                                      "achieved": NCU_NN_GRID_L2_BYTES / nn_s / 1e9, "l1tex_throughput_ncu": 0.777,
-                                      "lts_throughput_ncu": 0.602}}),
+                          "l2_view": (lambda sec, src: {"l2_bytes_per_launch_ncu": sec * 32.0 if sec else None, "unit": "GB/s",
+                                                        "achieved": sec * 32.0 / nn_s / 1e9 if sec else None,
+                                                        "source": src})(*fact(facts, "pp_nn_grid_kernel", "l2_sectors"))}),
         }
         if kname == "nn_grid":
             out[name]["nn_grid_build_ms_after_upload"] = grid_build_ms
@@ -607,7 +790,9 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak)
         "ms_per_step": ms / steps, "fill_kernel_ms": f_ms / max(f_n, 1), "gpu_launches": ctx.launch_count - l0,
         "config": {"workload": f"{ns} Dubins paths/GPU (c5 edge distribution), step 0.05: count + scan + fill of {total} samples"},
         "roofline": {"kernel": "pp_dubins_fill_kernel", "bound": "hbm", "achieved": total * 24.0 / f_s / 1e9, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": total * 24.0 / f_s / 1e9 / hbm_peak, "traffic": None,
+                     "unit": "GB/s", "frac": total * 24.0 / f_s / 1e9 / hbm_peak,
+                     "traffic": fact(facts, "pp_dubins_fill_kernel", "dram_bytes")[0],
+                     "traffic_source": fact(facts, "pp_dubins_fill_kernel", "dram_bytes")[1],
                      "per_unit": "24 B written per sample (+112 B plan record per path)"},
     }
     # ---- C2 (functional, host-driven): the examples/rrt shape -- 100 x 100 world, 50 create_circle obstacles, 10 k

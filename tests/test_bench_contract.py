@@ -16,18 +16,29 @@ def _run(args, env=None, timeout=600):
 
 
 def test_reference_arm_prints_one_contract_line():
-    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"])
+    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "1"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "dubins_pairs_per_s" and d["unit"] == "pairs/s"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f64"
-    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 1e4 and d["ms_per_step"] > 0
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 1e4 and d["ms_per_step"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "2^21 pairs" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "2^24-pair" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_never_loads_the_product_library():
+    """hygiene: the reference arm must not map libpathplanning_b200.so -- with the library path pointing
+    nowhere the product package cannot even be imported, and the arm must still run; both arms print the same `config`"""
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"], env={"PP_B200_LIB": "/nonexistent/libpp.so"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.C3_CONFIG and d["step"]["pairs_per_step"] == 1 << 24
 
 
 def test_reference_arm_other_ranks_exit_quietly():
