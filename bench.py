@@ -611,14 +611,15 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
     grid_build_ms = None
     # "extend" is the call a user makes (default flags: the library picks the exact grid search for a tree this size);
     # the *_scan* rows force the tiled brute-force kernels of the north-star design; all rows must agree bit for bit
-    for name, nnf, cf, kname in [("extend_scan", 8, 8, "nn_scan"), ("extend", 0, 0, "nn_grid"),
+    for name, nnf, cf, kname in [("extend_scan", 8, 8, "nn_scan"), ("extend", 0, 0, "extend_fused"),
+                                 ("extend_split", 0, 16, "nn_grid"),
                                  ("extend_scan_plain_f64", 1, 8, "nn_scan_f64"),
                                  ("extend_scan_unsorted", 4, 4, "nn_scan_unsorted")]:
         ctx.timing_enable(True)
         fn = lambda: ctx.rrt_extend_dev(m, qx, qy, idx, yaw, ok, nn_flags=nnf, collide_flags=cf)  # noqa: E731
         fn()
         torch.cuda.synchronize()
-        if kname == "nn_grid" and grid_build_ms is None:
+        if kname == "extend_fused" and grid_build_ms is None:
             b_ms, b_n = ctx.timing_get("nn_grid_build")  # the first grid call after the upload built the node grid
             grid_build_ms = b_ms / max(b_n, 1)
         ctx.timing_reset()
@@ -626,7 +627,8 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
         ksteps = slow_steps if nnf in (1, 4) else steps
         ms, _, _ = time_steps(torch, dist, fn, ksteps, 0, world)
         nn_ms, nn_n = ctx.timing_get(kname)
-        c_ms, c_n = ctx.timing_get({0: "collide_segments_grid", 8: "collide_segments", 4: "collide_segments_unsorted"}[cf])
+        c_ms, c_n = ctx.timing_get({0: "extend_sort", 16: "collide_segments_grid", 8: "collide_segments",
+                                    4: "collide_segments_unsorted"}[cf])
         ctx.timing_enable(False)
         if ref_idx is None:
             ref_idx, ref_ok = idx.clone(), ok.clone()
@@ -638,7 +640,8 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
             "ms_per_step": ms / ksteps, "steps": ksteps, "gpu_launches": ctx.launch_count - l0,
             "config": {"workload": f"c4: {m} queries/GPU vs {C4_NODES}-node tree, straight edge vs {C4_RINGS} create_circle rings",
                        "free_fraction_rank0": float(ok.float().mean().item())},
-            "nn_kernel_ms": nn_ms / max(nn_n, 1), "collide_kernel_ms": c_ms / max(c_n, 1),
+            **({"fused_kernel_ms": nn_ms / max(nn_n, 1), "sort_kernels_ms": c_ms / max(c_n, 1)} if kname == "extend_fused"
+               else {"nn_kernel_ms": nn_ms / max(nn_n, 1), "collide_kernel_ms": c_ms / max(c_n, 1)}),
             "matches_scan": agree,
             "roofline": ({"kernel": kname, "bound": "fp64", "achieved": pair_evals * 6.0 / nn_s / 1e9, "peak": fp64_peak / 1e9,
                           "unit": "Ginstr/s", "frac": pair_evals * 6.0 / nn_s / fp64_peak,
@@ -650,18 +653,20 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
                           # kernel streams only the 8 B fp32 copies)
                           "streamed_view": {"bytes_per_launch": m / 512.0 * C4_NODES * (8.0 if kname == "nn_scan" else 20.0),
                                             "achieved": m / 512.0 * C4_NODES * (8.0 if kname == "nn_scan" else 20.0) / nn_s / 1e9,
-                                            "unit": "GB/s"}} if kname != "nn_grid" else
+                                            "unit": "GB/s"}} if kname not in ("nn_grid", "extend_fused") else
                          {"kernel": kname, "bound": "hbm", "achieved": 36.0 * 2 ** 20 / nn_s / 1e9, "peak": hbm_peak,
                           "unit": "GB/s", "frac": 36.0 * 2 ** 20 / nn_s / 1e9 / hbm_peak,
-                          "per_unit": "36 MiB algorithmic bytes per launch (queries + nodes + indices); the search is a "
-                                      "latency-bound gather, not a stream",
+                          "per_unit": ("36 MiB (queries + nodes + indices) + 9 MiB (yaw + ok) algorithmic bytes per fused launch"
+                                       if kname == "extend_fused" else "36 MiB algorithmic bytes per launch (queries + nodes + "
+                                       "indices)") + "; the search is a latency-bound gather, not a stream",
                           # what actually bounds it (ncu --set full, profiles/r01_rrt_kernels_final6_raw.csv): 25.4 M L2
                           # sectors per launch of 2^20 queries, l1tex throughput 78 %, lts throughput 60 %
                           "l2_view": (lambda sec, src: {"l2_bytes_per_launch_ncu": sec * 32.0 if sec else None, "unit": "GB/s",
                                                         "achieved": sec * 32.0 / nn_s / 1e9 if sec else None,
-                                                        "source": src})(*fact(facts, "pp_nn_grid_kernel", "l2_sectors"))}),
+                                                        "source": src})(*fact(facts, "pp_rrt_extend_fused_kernel" if kname == "extend_fused"
+                                                                              else "pp_nn_grid_kernel", "l2_sectors"))}),
         }
-        if kname == "nn_grid":
+        if kname == "extend_fused":
             out[name]["nn_grid_build_ms_after_upload"] = grid_build_ms
             # the same step end to end through the host C-ABI call (pp_rrt_extend on pinned host buffers: 16 B in and
             # 13 B out per query cross PCIe inside the timed region); wall clock, max over ranks
@@ -692,7 +697,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
     ctx.timing_reset()
     l0 = ctx.launch_count
     ms, _, _ = time_steps(torch, dist, fn, steps, 0, world)
-    parts = {k: ctx.timing_get(k) for k in ("nn_grid", "dubins_plan", "collide_dubins")}
+    parts = {k: ctx.timing_get(k) for k in ("nn_grid", "extend_gather", "dubins_plan", "collide_dubins")}
     ctx.timing_enable(False)
     out["extend_dubins"] = {
         "metric": "rrt_extend_steps_per_s", "value": world * m * steps / (ms * 1e-3), "unit": "steps/s",
@@ -834,9 +839,12 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--skip-secondary", action="store_true", help="only the primary C3 metric")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--profile", action="store_true", help="for ncu runs: no 1 s clock-sampling load phase")
+    ap.add_argument("--profile", action="store_true", help="for ncu runs: one pass per step (a number from such a run is never a bench value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    if args.profile:  # under ncu every launch is replayed ~40 times: one pass per step is enough for a capture
+        global PASSES_PER_STEP
+        PASSES_PER_STEP = 1
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -61,8 +61,10 @@ enum pp_collide_flags {
     PP_COLLIDE_NO_CULL = 1,  /* exhaustive segment-pair loop exactly as geo's, no AABB rejection */
     PP_COLLIDE_USE_GRID = 2, /* the obstacle grid, explicitly */
     PP_COLLIDE_UNSORTED = 4, /* tiled AABB scan with one edge per thread in the caller's order (no binning) */
-    PP_COLLIDE_SCAN = 8      /* tiled scan of ALL ring boxes through shared memory (TMA tiles), edges binned by start
+    PP_COLLIDE_SCAN = 8,     /* tiled scan of ALL ring boxes through shared memory (TMA tiles), edges binned by start
                                 point, 32 boxes per instruction against the warp's union box, hit flags by ballot */
+    PP_COLLIDE_SPLIT = 16    /* pp_rrt_extend only: keep NN and verify as two launches (the default fuses them into one
+                                cell-coherent kernel whenever both halves take their grid route; same bits) */
 };
 
 /* flags for pp_nn */

@@ -109,7 +109,7 @@ def lib():
     L.ppo_verify_margin.restype = C.c_int
     L.ppo_verify_margin.argtypes = [wp, _dp, _dp, sz, _dp]
     L.ppo_verify_dubins_edges_flags.restype = None
-    L.ppo_verify_dubins_edges_flags.argtypes = [wp, sz] + [_dp] * 6 + [d, d, d, _u8p, _u32p, _dp, C.c_int]
+    L.ppo_verify_dubins_edges_flags.argtypes = [wp, sz] + [_dp] * 6 + [d, d, d, _u8p, _u32p, _dp, C.c_int, C.c_int]
     L.ppo_optimize.restype = C.c_long
     L.ppo_optimize.argtypes = [wp, sz, _dp, _dp, _dp, _i32p, C.c_uint32, d, d, d, _dp, _dp, _dp, sz, _u32p,
                                C.POINTER(C.c_long)]
@@ -307,7 +307,8 @@ class OracleWorld:
         v = lib().ppo_verify_margin(C.byref(self.w), _p(lx), _p(ly), lx.size, C.byref(m))
         return bool(v), m.value
 
-    def verify_dubins_edges_flags(self, sx, sy, syaw, ex, ey, eyaw, radius, step, graze_tol=GRAZE_TOL, nthreads=0):
+    def verify_dubins_edges_flags(self, sx, sy, syaw, ex, ey, eyaw, radius, step, graze_tol=GRAZE_TOL, culled=False,
+                                  nthreads=0):
         """(ok, flags, margins): verdicts with the classification flags of the parity harness"""
         sx, sy, syaw, ex, ey, eyaw = map(_f64, (sx, sy, syaw, ex, ey, eyaw))
         ok = np.empty(sx.size, np.uint8)
@@ -315,7 +316,7 @@ class OracleWorld:
         margins = np.empty(sx.size, np.float64)
         lib().ppo_verify_dubins_edges_flags(C.byref(self.w), sx.size, _p(sx), _p(sy), _p(syaw), _p(ex), _p(ey),
                                             _p(eyaw), float(radius), float(step), float(graze_tol), _p(ok, _u8p),
-                                            _p(flags, _u32p), _p(margins), int(nthreads))
+                                            _p(flags, _u32p), _p(margins), int(culled), int(nthreads))
         return ok, flags, margins
 
     def verify_segments(self, ax, ay, bx, by, culled=False, nthreads=0):

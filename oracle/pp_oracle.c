@@ -890,21 +890,38 @@ static double dist_point_ring(const double *rx, const double *ry, size_t n, doub
  * Not part of the reference; only used to CLASSIFY verdict differences between two implementations whose
  * sample coordinates agree to a tolerance (margin < tolerance => "near graze"). */
 #define PPO_MARGIN_SUB 4
+static int verify_margin(const ppo_world *w, const double *lx, const double *ly, size_t n, double *margin, int culled);
 int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, size_t n, double *margin) {
-    int verdict = ppo_verify(w, lx, ly, n);
+    return verify_margin(w, lx, ly, n, margin, 0);
+}
+/* culled != 0: the verdict comes from ppo_verify_culled (same answer up to the near-parallel noise class, and
+ * O(rings) instead of O(ring segments x line segments) -- for worlds of 1e5 rings) */
+static int verify_margin(const ppo_world *w, const double *lx, const double *ly, size_t n, double *margin, int culled) {
+    int verdict = culled ? ppo_verify_culled(w, lx, ly, n) : ppo_verify(w, lx, ly, n);
     double m;
+    /* box of the whole line: only rings near it can matter (their boxes are computed once per call) */
+    aabb_t lb = {INFINITY, INFINITY, -INFINITY, -INFINITY};
+    for (size_t j = 0; j < n; ++j) {
+        if (lx[j] < lb.minx) lb.minx = lx[j];
+        if (lx[j] > lb.maxx) lb.maxx = lx[j];
+        if (ly[j] < lb.miny) lb.miny = ly[j];
+        if (ly[j] > lb.maxy) lb.maxy = ly[j];
+    }
     if (verdict) {
+        /* the bounds ring first: its distance bounds how far away an obstacle ring can still matter */
         m = INFINITY;
-        for (size_t r = 0; r <= w->n_rings; ++r) { /* r == n_rings: the bounds ring */
+        for (size_t pass = 0; pass <= w->n_rings; ++pass) {
             const double *rx, *ry;
             size_t rn;
-            if (r == w->n_rings) {
+            if (pass == 0) {
                 rx = w->bx, ry = w->by, rn = w->nb;
             } else {
+                size_t r = pass - 1;
                 rx = w->ox + w->ring_off[r], ry = w->oy + w->ring_off[r], rn = w->ring_off[r + 1] - w->ring_off[r];
             }
             if (rn == 0) continue;
             aabb_t b = ring_aabb(rx, ry, rn);
+            if (lb.maxx < b.minx - m || lb.minx > b.maxx + m || lb.maxy < b.miny - m || lb.miny > b.maxy + m) continue;
             for (size_t j = 0; j < n; ++j) {
                 size_t j1 = (j + 1 < n) ? j + 1 : j; /* last vertex: degenerate segment */
                 double sminx = lx[j] < lx[j1] ? lx[j] : lx[j1], smaxx = lx[j] > lx[j1] ? lx[j] : lx[j1];
@@ -922,6 +939,18 @@ int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, si
         }
     } else {
         m = 0.0;
+        /* obstacle rings whose box meets the line's box: a probe point can only be inside one of those */
+        size_t n_cand = 0;
+        uint32_t *cand = (uint32_t *)malloc((w->n_rings ? w->n_rings : 1) * sizeof(uint32_t));
+        aabb_t *cbox = (aabb_t *)malloc((w->n_rings ? w->n_rings : 1) * sizeof(aabb_t));
+        for (size_t r = 0; r < w->n_rings && cand && cbox; ++r) {
+            size_t rn = w->ring_off[r + 1] - w->ring_off[r];
+            if (rn < 3) continue;
+            aabb_t b = ring_aabb(w->ox + w->ring_off[r], w->oy + w->ring_off[r], rn);
+            if (lb.maxx < b.minx || lb.minx > b.maxx || lb.maxy < b.miny || lb.miny > b.maxy) continue;
+            cbox[n_cand] = b;
+            cand[n_cand++] = (uint32_t)r;
+        }
         for (size_t j = 0; j < n; ++j) {
             size_t j1 = (j + 1 < n) ? j + 1 : j;
             int subs = (j1 == j) ? 1 : PPO_MARGIN_SUB + 1;
@@ -936,12 +965,12 @@ int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, si
                     double v = w->nb ? dist_point_ring(w->bx, w->by, w->nb, qx, qy) : INFINITY;
                     if (v > m) m = v;
                 }
-                for (size_t r = 0; r < w->n_rings; ++r) {
+                for (size_t c = 0; c < n_cand; ++c) {
+                    const aabb_t b = cbox[c];
+                    if (qx < b.minx || qx > b.maxx || qy < b.miny || qy > b.maxy) continue;
+                    size_t r = cand[c];
                     const double *rx = w->ox + w->ring_off[r], *ry = w->oy + w->ring_off[r];
                     size_t rn = w->ring_off[r + 1] - w->ring_off[r];
-                    if (rn < 3) continue;
-                    aabb_t b = ring_aabb(rx, ry, rn);
-                    if (qx < b.minx || qx > b.maxx || qy < b.miny || qy > b.maxy) continue;
                     if (ppo_point_position(rx, ry, rn, qx, qy) == 1) {
                         double v = dist_point_ring(rx, ry, rn, qx, qy);
                         if (v > m) m = v;
@@ -949,6 +978,8 @@ int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, si
                 }
             }
         }
+        free(cand);
+        free(cbox);
     }
     if (margin) *margin = m;
     return verdict;
@@ -973,7 +1004,7 @@ static uint32_t decision_flags(uint32_t path_flags, double margin, double scale,
 void ppo_verify_dubins_edges_flags(const ppo_world *w, size_t m, const double *sx, const double *sy,
                                    const double *syaw, const double *ex, const double *ey, const double *eyaw,
                                    double radius, double step, double graze_tol, uint8_t *ok, uint32_t *flags,
-                                   double *margins, int nthreads) {
+                                   double *margins, int culled, int nthreads) {
     int nt = resolve_threads(nthreads);
     (void)nt;
 #pragma omp parallel num_threads(nt)
@@ -1013,7 +1044,7 @@ void ppo_verify_dubins_edges_flags(const ppo_world *w, size_t m, const double *s
                 if (fabs(lx[k]) > scale) scale = fabs(lx[k]);
                 if (fabs(ly[k]) > scale) scale = fabs(ly[k]);
             }
-            ok[i] = (uint8_t)ppo_verify_margin(w, lx, ly, (size_t)n, &mg);
+            ok[i] = (uint8_t)verify_margin(w, lx, ly, (size_t)n, &mg, culled);
             flags[i] = decision_flags(f, mg, scale, graze_tol, radius, step);
             if (margins) margins[i] = mg;
         }

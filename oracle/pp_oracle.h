@@ -148,7 +148,7 @@ int ppo_verify_margin(const ppo_world *w, const double *lx, const double *ly, si
 void ppo_verify_dubins_edges_flags(const ppo_world *w, size_t m, const double *sx, const double *sy,
                                    const double *syaw, const double *ex, const double *ey, const double *eyaw,
                                    double radius, double step, double graze_tol, uint8_t *ok, uint32_t *flags,
-                                   double *margins, int nthreads);
+                                   double *margins, int culled, int nthreads);
 
 /* RRT::optimize (src/rrt.rs:463-487, RECURSION_LIMIT :14) of tree node `node` over a flat tree.  Writes the chain
  * of the returned node (new node ... root) as poses and returns its length; 0 = None; -2 cap too small; -3 error.

@@ -39,6 +39,8 @@ int pp_launch_verify_polylines(pp_ctx *, size_t, const double *, const double *,
 int pp_launch_collide_dubins(pp_ctx *, size_t, const void *, const void *, const double *, const double *, uint8_t *,
                              int, cudaStream_t);
 int pp_launch_fp64_peak(pp_ctx *, int, double *, cudaStream_t, unsigned *, unsigned *);
+int pp_launch_rrt_extend_fused(pp_ctx *, size_t, const double *, const double *, uint32_t *, double *, uint8_t *,
+                               cudaStream_t);
 int pp_launch_extend_gather(pp_ctx *, size_t, const double *, const double *, const uint32_t *, double *, double *,
                             double *, double *, cudaStream_t);
 
@@ -1130,6 +1132,18 @@ int pp_collide_dubins(pp_ctx *ctx, size_t m, const double *sx, const double *sy,
     return PP_OK;
 }
 
+// one extend step on device pointers: the fused kernel when both halves take their default (grid) route -- the library's
+// own choice or PP_NN_GRID / PP_COLLIDE_USE_GRID -- otherwise the NN kernel followed by the verify kernel the flags name
+static int pp_extend_step(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *yaw,
+                          uint8_t *ok, int nn_flags, int collide_flags, cudaStream_t s) {
+    const bool fused = (nn_flags & PP_NN_GRID) && !(nn_flags & (PP_NN_SCAN | PP_NN_PLAIN_F64 | PP_NN_UNSORTED)) &&
+                       !(collide_flags & (PP_COLLIDE_NO_CULL | PP_COLLIDE_UNSORTED | PP_COLLIDE_SCAN | PP_COLLIDE_SPLIT));
+    if (fused) return pp_launch_rrt_extend_fused(ctx, m, qx, qy, idx, yaw, ok, s);
+    int rc = pp_launch_nn(ctx, m, qx, qy, idx, nullptr, nn_flags, s);
+    if (rc) return rc;
+    return pp_launch_collide_segments(ctx, m, qx, qy, nullptr, nullptr, idx, yaw, ok, collide_flags, s);
+}
+
 int pp_rrt_extend_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *yaw,
                       uint8_t *ok, int nn_flags, int collide_flags) {
     if (!ctx || (m && (!qx || !qy || !idx || !ok))) return PP_ERR_INVALID;
@@ -1139,9 +1153,7 @@ int pp_rrt_extend_dev(pp_ctx *ctx, size_t m, const double *qx, const double *qy,
     if (ctx->tree.n == 0) return pp_fail(ctx, PP_ERR_STATE, "tree is empty");
     int rc = pp_nn_prepare(ctx, m, &nn_flags);
     if (rc) return rc;
-    rc = pp_launch_nn(ctx, m, qx, qy, idx, nullptr, nn_flags, ctx->stream);
-    if (rc) return rc;
-    return pp_launch_collide_segments(ctx, m, qx, qy, nullptr, nullptr, idx, yaw, ok, collide_flags, ctx->stream);
+    return pp_extend_step(ctx, m, qx, qy, idx, yaw, ok, nn_flags, collide_flags, ctx->stream);
 }
 
 int pp_rrt_extend(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *yaw, uint8_t *ok,
@@ -1161,10 +1173,7 @@ int pp_rrt_extend(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uin
     double *q = dq.as<double>();
     PP_CUDA(ctx, cudaMemcpyAsync(q, qx, m * 8, cudaMemcpyHostToDevice, s));
     PP_CUDA(ctx, cudaMemcpyAsync(q + m, qy, m * 8, cudaMemcpyHostToDevice, s));
-    rc = pp_launch_nn(ctx, m, q, q + m, di.as<uint32_t>(), nullptr, nn_flags, s);
-    if (rc) return rc;
-    rc = pp_launch_collide_segments(ctx, m, q, q + m, nullptr, nullptr, di.as<uint32_t>(), dy.as<double>(),
-                                    dok.as<uint8_t>(), collide_flags, s);
+    rc = pp_extend_step(ctx, m, q, q + m, di.as<uint32_t>(), dy.as<double>(), dok.as<uint8_t>(), nn_flags, collide_flags, s);
     if (rc) return rc;
     PP_CUDA(ctx, cudaMemcpyAsync(idx, di.p, m * 4, cudaMemcpyDeviceToHost, s));
     if (yaw) PP_CUDA(ctx, cudaMemcpyAsync(yaw, dy.p, m * 8, cudaMemcpyDeviceToHost, s));

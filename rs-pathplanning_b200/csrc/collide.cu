@@ -21,6 +21,7 @@
 //     answer is noise; PP_COLLIDE_NO_CULL gives the exhaustive loop).
 #include "dubins_device.cuh"
 #include "geo_predicates.cuh"
+#include "nn_grid.cuh"
 #include "pp_common.cuh"
 
 pp_world_view pp_make_world_view(const pp_world_dev &w);  // api.cu
@@ -272,32 +273,10 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
 #ifndef PP_SEGGRID_MIN_BLOCKS
 #define PP_SEGGRID_MIN_BLOCKS 6  // 80 registers: 0.186 ms per 2^20 C4 edges (0.211 at 90 registers, 0.189 at 64)
 #endif
-__global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
-    pp_collide_segments_grid_kernel(pp_world_view w, size_t m, const double *__restrict__ ax,
-                                    const double *__restrict__ ay, const double *__restrict__ bx,
-                                    const double *__restrict__ by, const uint32_t *__restrict__ gather_idx,
-                                    const double *__restrict__ node_x, const double *__restrict__ node_y,
-                                    double *__restrict__ yaw_out, uint8_t *__restrict__ ok) {
-    const size_t i = (size_t)blockIdx.x * PP_SEG_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool live = i < m;
-    double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    if (live) {
-        x0 = ax[i];
-        y0 = ay[i];
-        if (gather_idx) {  // extend step: b = tree node nearest to the sample a (src/rrt.rs:406-411)
-            // pp_nn answers 0xFFFFFFFF for a query without a nearest node (NaN / Inf coordinates, d2 overflow):
-            // the reference's get_random_node returns None there, here the step reports ok = 0 and yaw = NaN
-            const uint32_t g = gather_idx[i];
-            const bool none = g == 0xFFFFFFFFu;
-            x1 = none ? CUDART_NAN : node_x[g];
-            y1 = none ? CUDART_NAN : node_y[g];
-            if (yaw_out) yaw_out[i] = none ? CUDART_NAN : atan2(y1 - y0, x1 - x0);  // compute_yaw, src/rrt.rs:267-271
-        } else {
-            x1 = bx[i];
-            y1 = by[i];
-        }
-    }
+// Space::verify of one straight edge per lane through the obstacle grid; ALL 32 lanes of the warp call together
+// (ballots and shuffles inside), lanes without an edge pass live = false
+__device__ __forceinline__ bool pp_verify_segment_grid(const pp_world_view &w, bool live, double x0, double y0, double x1,
+                                                       double y1, int lane) {
     // bounds.contains(line): both points strictly inside (src/rrt.rs:125)
     const bool good = live && pp_bounds_contains(w, x0, y0) && pp_bounds_contains(w, x1, y1);
     bool hit = false;
@@ -392,7 +371,142 @@ __global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
             } while (pend != 0u);
         }
     }
-    if (live) ok[i] = (good && !hit) ? 1 : 0;
+    return good && !hit;
+}
+
+__global__ void __launch_bounds__(PP_SEG_THREADS, PP_SEGGRID_MIN_BLOCKS)
+    pp_collide_segments_grid_kernel(pp_world_view w, size_t m, const double *__restrict__ ax,
+                                    const double *__restrict__ ay, const double *__restrict__ bx,
+                                    const double *__restrict__ by, const uint32_t *__restrict__ gather_idx,
+                                    const double *__restrict__ node_x, const double *__restrict__ node_y,
+                                    double *__restrict__ yaw_out, uint8_t *__restrict__ ok) {
+    const size_t i = (size_t)blockIdx.x * PP_SEG_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = i < m;
+    double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (live) {
+        x0 = ax[i];
+        y0 = ay[i];
+        if (gather_idx) {  // extend step: b = tree node nearest to the sample a (src/rrt.rs:406-411)
+            // pp_nn answers 0xFFFFFFFF for a query without a nearest node (NaN / Inf coordinates, d2 overflow):
+            // the reference's get_random_node returns None there, here the step reports ok = 0 and yaw = NaN
+            const uint32_t g = gather_idx[i];
+            const bool none = g == 0xFFFFFFFFu;
+            x1 = none ? CUDART_NAN : node_x[g];
+            y1 = none ? CUDART_NAN : node_y[g];
+            if (yaw_out) yaw_out[i] = none ? CUDART_NAN : atan2(y1 - y0, x1 - x0);  // compute_yaw, src/rrt.rs:267-271
+        } else {
+            x1 = bx[i];
+            y1 = by[i];
+        }
+    }
+    const bool free_edge = pp_verify_segment_grid(w, live, x0, y0, x1, y1, lane);
+    if (live) ok[i] = free_edge ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused, cell-coherent extend step (src/rrt.rs:406-426 with straight edges): ONE launch does
+//   nearest neighbour (exact grid search) -> Node::new's yaw (compute_yaw) -> Space::verify of the edge sample -> node.
+// The queries are first binned by the node-grid block they fall into (pp_extend_bin / scan / scatter below: a
+// counting sort whose rank comes out of the histogram's own atomicAdd), so the 32 queries of a warp lie in ONE
+// 4 x 4 block of node cells: their 3 x 3 neighbourhoods overlap almost entirely, the cell runs they read are the
+// same cache lines, their edges fall into the same obstacle cell, and the ring walk / narrow phase work on the same
+// rings.  No idx / yaw round trip through memory between the two halves, and the edge's far end comes out of the NN
+// scan's own registers instead of a second gather.  Per query the arithmetic is that of pp_nn_grid_kernel and
+// pp_collide_segments_grid_kernel, so idx, yaw and ok are the same bits; only the order of the work changes.
+// ------------------------------------------------------------------------------------------------
+#define PP_EXT_BIN_SHIFT_MIN 2  // 4 x 4 node cells per bin (~32 queries per bin when queries ~ nodes)
+#define PP_EXT_MAX_BINS 65536u
+
+struct pp_extend_bins {
+    int shift, bx, by;  // bins of (1 << shift)^2 node cells, bx x by of them
+};
+
+__device__ __forceinline__ uint32_t pp_extend_bin_of(const pp_nn_grid_view &g, const pp_extend_bins &b, double x, double y) {
+    const double fx = floor((x - g.gminx) * g.ginv), fy = floor((y - g.gminy) * g.ginv);
+    const int cx = (fx >= (double)g.gx) ? g.gx - 1 : ((fx > 0.0) ? (int)fx : 0);  // NaN -> 0, as the search does
+    const int cy = (fy >= (double)g.gy) ? g.gy - 1 : ((fy > 0.0) ? (int)fy : 0);
+    return (uint32_t)(cy >> b.shift) * (uint32_t)b.bx + (uint32_t)(cx >> b.shift);
+}
+
+// histogram of the bins; the value the atomicAdd returns is the query's rank inside its bin
+__global__ void __launch_bounds__(256)
+    pp_extend_bin_kernel(pp_nn_grid_view g, pp_extend_bins b, const double *__restrict__ qx, const double *__restrict__ qy,
+                         uint32_t m, uint32_t *__restrict__ hist, uint32_t *__restrict__ bin_of, uint32_t *__restrict__ rank) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t bin = pp_extend_bin_of(g, b, qx[j], qy[j]);
+    bin_of[j] = bin;
+    rank[j] = atomicAdd(&hist[bin], 1u);
+}
+
+// exclusive scan of up to 65 536 bin counts in ONE block (64 values per thread), in place
+__global__ void __launch_bounds__(1024) pp_extend_scan_kernel(uint32_t *__restrict__ hist, uint32_t nb) {
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per = (nb + 1023u) / 1024u;
+    const uint32_t first = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < per; ++k)
+        if (first + k < nb) sum += hist[first + k];
+    uint32_t inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t wv = warp_sums[lane];
+        uint32_t winc = wv;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_sums[lane] = winc - wv;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + inc - sum;
+    for (uint32_t k = 0; k < per; ++k)
+        if (first + k < nb) {
+            const uint32_t v = hist[first + k];
+            hist[first + k] = run;
+            run += v;
+        }
+}
+
+__global__ void __launch_bounds__(256)
+    pp_extend_scatter_kernel(uint32_t m, const uint32_t *__restrict__ start, const uint32_t *__restrict__ bin_of,
+                             const uint32_t *__restrict__ rank, uint32_t *__restrict__ perm) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j < m) perm[__ldg(start + bin_of[j]) + rank[j]] = j;
+}
+
+#ifndef PP_EXTEND_MIN_BLOCKS
+#define PP_EXTEND_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(PP_SEG_THREADS, PP_EXTEND_MIN_BLOCKS)
+    pp_rrt_extend_fused_kernel(pp_nn_grid_view g, pp_world_view w, uint32_t m, const uint32_t *__restrict__ perm,
+                               const double *__restrict__ qx, const double *__restrict__ qy, uint32_t *__restrict__ idx_out,
+                               double *__restrict__ yaw_out, uint8_t *__restrict__ ok) {
+    const uint32_t t = blockIdx.x * PP_SEG_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = t < m;
+    uint32_t j = 0, bi = 0xFFFFFFFFu;
+    double x0 = 0, y0 = 0, x1 = 0, y1 = 0, best;
+    if (live) {
+        j = perm ? __ldg(perm + t) : t;
+        x0 = qx[j];
+        y0 = qy[j];
+        pp_nn_grid_search(g, x0, y0, best, bi, x1, y1);  // RRT::get_nearest_node, src/rrt.rs:378-391
+        idx_out[j] = bi;
+        const bool none = bi == 0xFFFFFFFFu;  // no nearest node: get_random_node's None -> ok = 0, yaw = NaN
+        if (none) x1 = y1 = CUDART_NAN;
+        if (yaw_out) yaw_out[j] = none ? CUDART_NAN : atan2(y1 - y0, x1 - x0);  // compute_yaw, src/rrt.rs:267-271
+    }
+    __syncwarp();
+    const bool free_edge = pp_verify_segment_grid(w, live, x0, y0, x1, y1, lane);
+    if (live) ok[j] = free_edge ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -782,6 +896,47 @@ int pp_launch_collide_segments(pp_ctx *ctx, size_t m, const double *ax, const do
         pp_collide_segments_bucketed_kernel<<<grid_b, PP_SEG_THREADS, 0, stream>>>(w, m, ax, ay, bx, by, gather_idx, nx,
                                                                                    ny, yaw_out, perm, ok);
     }
+    PP_CUDA(ctx, cudaGetLastError());
+    return PP_OK;
+}
+
+// fused extend step (NN + yaw + verify in one launch, queries binned by node-grid block).  The caller has made the
+// node grid usable (pp_nn_prepare).  Queries below PP_EXT_SORT_MIN keep their order (the three binning launches would
+// cost more than they save).
+#define PP_EXT_SORT_MIN 8192
+int pp_launch_rrt_extend_fused(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *yaw,
+                               uint8_t *ok, cudaStream_t stream) {
+    if (m == 0) return PP_OK;
+    if (m >= 0xFFFFFFF0ull) return pp_fail(ctx, PP_ERR_INVALID, "too many queries for one extend call");
+    const pp_nn_grid_view g = pp_nn_make_grid_view(ctx->tree);
+    const pp_world_view w = pp_make_world_view(ctx->world);
+    uint32_t *perm = nullptr;
+    if (m >= PP_EXT_SORT_MIN && g.grid_n > 0) {
+        pp_extend_bins b;
+        b.shift = PP_EXT_BIN_SHIFT_MIN;
+        for (;;) {
+            b.bx = ((g.gx - 1) >> b.shift) + 1;
+            b.by = ((g.gy - 1) >> b.shift) + 1;
+            if ((uint64_t)b.bx * (uint64_t)b.by <= PP_EXT_MAX_BINS) break;
+            ++b.shift;
+        }
+        const uint32_t nb = (uint32_t)b.bx * (uint32_t)b.by;
+        const size_t hist_words = ((size_t)nb + 64) & ~(size_t)63;
+        int rc = pp_scratch_reserve(ctx, (hist_words + 3 * m) * 4);
+        if (rc) return rc;
+        uint32_t *hist = (uint32_t *)ctx->scratch, *bin_of = hist + hist_words, *rank = bin_of + m;
+        perm = rank + m;
+        pp_launch_scope scope(ctx, "extend_sort", 3);
+        PP_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4, stream));
+        const unsigned g1 = (unsigned)((m + 255) / 256);
+        pp_extend_bin_kernel<<<g1, 256, 0, stream>>>(g, b, qx, qy, (uint32_t)m, hist, bin_of, rank);
+        pp_extend_scan_kernel<<<1, 1024, 0, stream>>>(hist, nb);
+        pp_extend_scatter_kernel<<<g1, 256, 0, stream>>>((uint32_t)m, hist, bin_of, rank, perm);
+        PP_CUDA(ctx, cudaGetLastError());
+    }
+    pp_launch_scope scope(ctx, "extend_fused");
+    const unsigned grid = (unsigned)((m + PP_SEG_THREADS - 1) / PP_SEG_THREADS);
+    pp_rrt_extend_fused_kernel<<<grid, PP_SEG_THREADS, 0, stream>>>(g, w, (uint32_t)m, perm, qx, qy, idx, yaw, ok);
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;
 }

@@ -16,6 +16,7 @@
 //                       split the nodes of one query, per-thread running minimum, warp-shuffle
 //                       argmin with lowest-index tie-break, last CTA reduces the partials.
 //   pp_nn_grid_kernel   exact ring-expanding search over a uniform grid of the nodes.
+#include "nn_grid.cuh"
 #include "pp_common.cuh"
 
 #define PP_NN_TILE 1024   // nodes per tile (tree arrays are padded to this with +inf sentinels)
@@ -241,95 +242,14 @@ __global__ void __launch_bounds__(PP_NN_WIDE_THREADS)
 // node in a cell at Chebyshev distance >= r is farther than (r-1)*cell from the query, so the search
 // stops once best < ((r-1)*cell*(1-2^-30))^2.  Same d2 arithmetic, ties to the lowest index.
 // ---------------------------------------------------------------------------------------------
-// The grid describes the nodes [0, grid_n); nodes appended since (the TAIL [grid_n, n_nodes), src/rrt.rs:586-589
-// inserts one node per iteration) are not filed into cells but compared one by one BEFORE the cell search -- every
-// lane of a warp reads the same tail node (one broadcast load), and the tighter `best` shortens the ring walk.
-// Tail ids are larger than every grid id and the cell scan takes ties to the lower id, so the lexicographic
-// (d2, id) minimum -- hence the lowest-index tie-break -- is unchanged.  The host rebuilds the grid when the tail
-// outgrows its budget (pp_nn_grid_policy).
-struct pp_nn_grid_view {
-    uint32_t n_nodes, grid_n;
-    const uint32_t *cell_start, *cell_items;
-    const double2 *cell_xy;
-    const double *node_x, *node_y;
-    int gx, gy;
-    double gminx, gminy, gcell, ginv;
-};
-
-__device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, double x, double y, double &best_out,
-                                                  uint32_t &bi_out) {
-    double best = CUDART_INF;
-    uint32_t bi = 0xFFFFFFFFu;
-    for (uint32_t i = g.grid_n; i < g.n_nodes; ++i) {  // the tail, in index order, strict compare (as the scans)
-        const double dx = __ldg(g.node_x + i) - x, dy = __ldg(g.node_y + i) - y;
-        const double v = dx * dx + dy * dy;
-        if (v < best) {
-            best = v;
-            bi = i;
-        }
-    }
-    // candidates k0 <= k < k1 of the cell-sorted arrays: same d2 arithmetic as the scans, (d2, id) lexicographic
-    // minimum; the id is fetched only when a candidate ties or improves
-    auto scan = [&](uint32_t k0, uint32_t k1) {
-        for (uint32_t k = k0; k < k1; ++k) {
-            const double2 p = __ldg(g.cell_xy + k);
-            const double dx = p.x - x, dy = p.y - y;
-            const double v = dx * dx + dy * dy;
-            if (v <= best) {
-                const uint32_t i = __ldg(g.cell_items + k);
-                // a tie only counts against a node already held: d2 = +inf (a query or node at 1e300, +-inf) ties
-                // with the initial best and must leave "no node", as the strict compare of the scans does
-                if (v < best || (i < bi && bi != 0xFFFFFFFFu)) {
-                    best = v;
-                    bi = i;
-                }
-            }
-        }
-    };
-    if (g.grid_n > 0) {
-        const int gx = g.gx, gy = g.gy;
-        double fx = floor((x - g.gminx) * g.ginv), fy = floor((y - g.gminy) * g.ginv);
-        int cx = (fx >= (double)gx) ? gx - 1 : ((fx > 0.0) ? (int)fx : 0);  // NaN -> 0
-        int cy = (fy >= (double)gy) ? gy - 1 : ((fy > 0.0) ? (int)fy : 0);
-        // rings 0 and 1 together: the 3 x 3 block is three runs of the cell-sorted arrays (a row of cells is
-        // contiguous), i.e. six offset loads instead of eighteen
-        {
-            const int xa = max(cx - 1, 0), xb = min(cx + 1, gx - 1);
-            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gy - 1); ++yy) {
-                const uint32_t *row = g.cell_start + (size_t)yy * gx;
-                scan(__ldg(row + xa), __ldg(row + xb + 1));
-            }
-        }
-        const int maxr = max(gx, gy);
-        for (int r = 2; r <= maxr; ++r) {
-            if (bi != 0xFFFFFFFFu) {
-                double lim = (double)(r - 1) * g.gcell * (1.0 - 0x1p-30);
-                if (best < lim * lim) break;
-            }
-            const int y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
-            for (int yy = max(y0, 0); yy <= min(y1, gy - 1); ++yy) {
-                const uint32_t *row = g.cell_start + (size_t)yy * gx;
-                if (yy == y0 || yy == y1) {  // full row of the ring: one run
-                    scan(__ldg(row + max(x0, 0)), __ldg(row + min(x1, gx - 1) + 1));
-                } else {  // the two end cells
-                    if (x0 >= 0) scan(__ldg(row + x0), __ldg(row + x0 + 1));
-                    if (x1 < gx) scan(__ldg(row + x1), __ldg(row + x1 + 1));
-                }
-            }
-        }
-    }
-    best_out = best;
-    bi_out = bi;
-}
-
 __global__ void __launch_bounds__(128)
     pp_nn_grid_kernel(pp_nn_grid_view g, const double *__restrict__ qx, const double *__restrict__ qy, size_t m,
                       uint32_t *__restrict__ idx_out, double *__restrict__ d2_out) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
-    double best;
+    double best, bx, by;
     uint32_t bi;
-    pp_nn_grid_search(g, qx[j], qy[j], best, bi);
+    pp_nn_grid_search(g, qx[j], qy[j], best, bi, bx, by);
     idx_out[j] = bi;
     if (d2_out) d2_out[j] = best;
 }
@@ -641,7 +561,7 @@ int pp_build_bucket_perm(pp_ctx *ctx, size_t m, const double *kx, const double *
     return PP_OK;
 }
 
-static pp_nn_grid_view pp_nn_make_grid_view(const pp_tree_dev &t) {
+pp_nn_grid_view pp_nn_make_grid_view(const pp_tree_dev &t) {
     pp_nn_grid_view g;
     g.n_nodes = (uint32_t)t.n;
     g.grid_n = (t.grid_n == (size_t)-1 || t.grid_n > t.n) ? 0u : (uint32_t)t.grid_n;

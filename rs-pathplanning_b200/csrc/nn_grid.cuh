@@ -1,0 +1,97 @@
+// nn_grid.cuh -- the exact uniform-grid nearest-neighbour search as a device function, shared by the stand-alone
+// NN kernel (nn.cu) and the fused extend kernel (collide.cu).
+#pragma once
+#include "pp_common.cuh"
+
+// The grid describes the nodes [0, grid_n); nodes appended since (the TAIL [grid_n, n_nodes), src/rrt.rs:586-589
+// inserts one node per iteration) are not filed into cells but compared one by one BEFORE the cell search -- every
+// lane of a warp reads the same tail node (one broadcast load), and the tighter `best` shortens the ring walk.
+// Tail ids are larger than every grid id and the cell scan takes ties to the lower id, so the lexicographic
+// (d2, id) minimum -- hence the lowest-index tie-break -- is unchanged.  The host rebuilds the grid when the tail
+// outgrows its budget (pp_nn_grid_policy).
+struct pp_nn_grid_view {
+    uint32_t n_nodes, grid_n;
+    const uint32_t *cell_start, *cell_items;
+    const double2 *cell_xy;
+    const double *node_x, *node_y;
+    int gx, gy;
+    double gminx, gminy, gcell, ginv;
+};
+
+// (bx_out, by_out): coordinates of the winner (undefined when bi_out == 0xFFFFFFFF) -- the extend step needs them
+// for the edge and gets them from the scan instead of a second gather
+__device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, double x, double y, double &best_out,
+                                                  uint32_t &bi_out, double &bx_out, double &by_out) {
+    double best = CUDART_INF, bx = 0.0, by = 0.0;
+    uint32_t bi = 0xFFFFFFFFu;
+    for (uint32_t i = g.grid_n; i < g.n_nodes; ++i) {  // the tail, in index order, strict compare (as the scans)
+        const double nx = __ldg(g.node_x + i), ny = __ldg(g.node_y + i);
+        const double dx = nx - x, dy = ny - y;
+        const double v = dx * dx + dy * dy;
+        if (v < best) {
+            best = v;
+            bi = i;
+            bx = nx;
+            by = ny;
+        }
+    }
+    // candidates k0 <= k < k1 of the cell-sorted arrays: same d2 arithmetic as the scans, (d2, id) lexicographic
+    // minimum; the id is fetched only when a candidate ties or improves
+    auto scan = [&](uint32_t k0, uint32_t k1) {
+        for (uint32_t k = k0; k < k1; ++k) {
+            const double2 p = __ldg(g.cell_xy + k);
+            const double dx = p.x - x, dy = p.y - y;
+            const double v = dx * dx + dy * dy;
+            if (v <= best) {
+                const uint32_t i = __ldg(g.cell_items + k);
+                // a tie only counts against a node already held: d2 = +inf (a query or node at 1e300, +-inf) ties
+                // with the initial best and must leave "no node", as the strict compare of the scans does
+                if (v < best || (i < bi && bi != 0xFFFFFFFFu)) {
+                    best = v;
+                    bi = i;
+                    bx = p.x;
+                    by = p.y;
+                }
+            }
+        }
+    };
+    if (g.grid_n > 0) {
+        const int gx = g.gx, gy = g.gy;
+        double fx = floor((x - g.gminx) * g.ginv), fy = floor((y - g.gminy) * g.ginv);
+        int cx = (fx >= (double)gx) ? gx - 1 : ((fx > 0.0) ? (int)fx : 0);  // NaN -> 0
+        int cy = (fy >= (double)gy) ? gy - 1 : ((fy > 0.0) ? (int)fy : 0);
+        // rings 0 and 1 together: the 3 x 3 block is three runs of the cell-sorted arrays (a row of cells is
+        // contiguous), i.e. six offset loads instead of eighteen
+        {
+            const int xa = max(cx - 1, 0), xb = min(cx + 1, gx - 1);
+            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gy - 1); ++yy) {
+                const uint32_t *row = g.cell_start + (size_t)yy * gx;
+                scan(__ldg(row + xa), __ldg(row + xb + 1));
+            }
+        }
+        const int maxr = max(gx, gy);
+        for (int r = 2; r <= maxr; ++r) {
+            if (bi != 0xFFFFFFFFu) {
+                double lim = (double)(r - 1) * g.gcell * (1.0 - 0x1p-30);
+                if (best < lim * lim) break;
+            }
+            const int y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
+            for (int yy = max(y0, 0); yy <= min(y1, gy - 1); ++yy) {
+                const uint32_t *row = g.cell_start + (size_t)yy * gx;
+                if (yy == y0 || yy == y1) {  // full row of the ring: one run
+                    scan(__ldg(row + max(x0, 0)), __ldg(row + min(x1, gx - 1) + 1));
+                } else {  // the two end cells
+                    if (x0 >= 0) scan(__ldg(row + x0), __ldg(row + x0 + 1));
+                    if (x1 < gx) scan(__ldg(row + x1), __ldg(row + x1 + 1));
+                }
+            }
+        }
+    }
+    best_out = best;
+    bi_out = bi;
+    bx_out = bx;
+    by_out = by;
+}
+
+pp_nn_grid_view pp_nn_make_grid_view(const pp_tree_dev &t);  // nn.cu (host)
+

@@ -370,7 +370,8 @@ def test_extend_step(ctx, O, pp):
     oidx, _ = O.nn_brute(nx, ny, qx, qy)
     want = W.verify_segments(qx, qy, nx[oidx], ny[oidx])
     wyaw = np.arctan2(ny[oidx] - qy, nx[oidx] - qx)
-    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_PLAIN, DEFAULT), (NN_SCAN, SCAN)]:
+    # (default, default) and (grid, grid) run the fused cell-coherent kernel; 16 = PP_COLLIDE_SPLIT keeps two launches
+    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_DEFAULT, 16), (NN_PLAIN, DEFAULT), (NN_SCAN, SCAN)]:
         idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=nnf, collide_flags=cf)
         assert np.array_equal(idx, oidx) and np.array_equal(ok, want)
         assert np.abs(yaw - wyaw).max() < 1e-12
