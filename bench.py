@@ -711,7 +711,8 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
     bounds2, rings2 = pp.synth.circle_world(C4_RINGS, shift=5000.0)
     ctx.obstacles_upload(bounds2, rings2)
     for name, cf, kname, what in [("collide_scan_nohit", 8, "collide_segments", "tiled fp32 box scan over all 10k rings"),
-                                  ("collide_grid_nohit", 0, "collide_segments_grid", "uniform obstacle grid, the default")]:
+                                  ("collide_grid_nohit", 16, "collide_segments_grid",
+                                   "uniform obstacle grid as its own launch (PP_COLLIDE_SPLIT)")]:
         fn = lambda: ctx.rrt_extend_dev(m, qx, qy, idx, yaw, ok, nn_flags=2, collide_flags=cf)  # noqa: E731
         ctx.timing_enable(True)
         fn()
@@ -720,7 +721,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
         ms, _, _ = time_steps(torch, dist, fn, steps, 0, world)
         c_ms, c_n = ctx.timing_get(kname)
         ctx.timing_enable(False)
-        out[name] = {"collide_kernel_ms": c_ms / max(c_n, 1), "edges_per_s": m / (c_ms / max(c_n, 1) * 1e-3),
+        out[name] = {"collide_kernel_ms": c_ms / max(c_n, 1), "edges_per_s": m / max(c_ms / max(c_n, 1) * 1e-3, 1e-12),
                      "free_fraction_rank0": float(ok.float().mean().item()),
                      "config": {"workload": f"c4 edges vs the no-hit ring set ({what})"}}
     # ---- C5 slice: Dubins edges sampled at 0.05 and verified against 100k rings

@@ -316,12 +316,18 @@ int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double 
 // ------------------------------------------------------------------------------------------------
 #define PP_FILL_THREADS 128
 
+#ifndef PP_FILL_TMA
+#define PP_FILL_TMA 1  // 1: staging rows leave through the TMA engine (cp.async.bulk shared -> global); 0: 16-byte vector stores
+#endif
+#define PP_FILL_ROW 100  // doubles per staging row: 96 (32 samples) + 1 (alignment shift) + padding to a 16-byte multiple
+
 __global__ void __launch_bounds__(PP_FILL_THREADS)
     pp_dubins_fill_kernel(size_t n, const pp_dubins_plan *__restrict__ plans, const uint64_t *__restrict__ offsets,
                           double *__restrict__ out) {
-    __shared__ __align__(16) double fill_stage[PP_FILL_THREADS / 32][96];
+    // two staging rows per warp: while the TMA engine drains one, the warp interpolates into the other
+    __shared__ __align__(16) double fill_stage[PP_FILL_THREADS / 32][2][PP_FILL_ROW];
     const int lane = threadIdx.x & 31;
-    double *stage = fill_stage[threadIdx.x >> 5];
+    uint32_t chunk = 0;  // running chunk counter of this warp: selects the staging row
     const size_t warps_total = (size_t)gridDim.x * (PP_FILL_THREADS / 32);
     for (size_t path = (size_t)blockIdx.x * (PP_FILL_THREADS / 32) + (threadIdx.x >> 5); path < n;
          path += warps_total) {
@@ -348,6 +354,18 @@ __global__ void __launch_bounds__(PP_FILL_THREADS)
                 const uint32_t k0 = base + j0;
                 if (k0 >= pl.count) break;  // the trim rule may cut the tail (Q6/Q7); warp-uniform
                 const uint32_t cnt = min(min(32u, ns - j0), pl.count - k0);
+                // The 3*cnt doubles of this step are contiguous in `out` (a full step = 768 B).  The row is staged
+                // in shared memory SHIFTED by the parity of its first global element, so that the 16-byte aligned
+                // part of the destination is 16-byte aligned in shared memory too.
+                double *d0 = dst + 3 * (size_t)k0;
+                const uint32_t D = 3 * cnt;
+                const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(d0) >> 3) & 1u);
+                double *stage = fill_stage[threadIdx.x >> 5][chunk & 1u] + head;
+                ++chunk;
+#if PP_FILL_TMA
+                if (lane == 0) pp_bulk_wait_read<1>();  // the copy issued two chunks ago has let go of this row
+                __syncwarp();
+#endif
                 if ((uint32_t)lane < cnt) {
                     double x, y, yaw;
                     pp_interpolate(mode, pd0 + (double)(j0 + lane) * d, ox, oy, oyaw, so, co, pl.rinv, &x, &y, &yaw);
@@ -362,15 +380,21 @@ __global__ void __launch_bounds__(PP_FILL_THREADS)
                     stage[3 * lane + 1] = y;
                     stage[3 * lane + 2] = yaw;
                 }
+                const uint32_t nvec = (D - head) >> 1;  // 16-byte units after the (optional) 8-byte head
+#if PP_FILL_TMA
+                // Per-lane (x,y,yaw) stores touched 24 sectors per warp instruction (L1 store-sector bound), 16-byte
+                // vector stores from the staging row still cost 2 LSU instructions per lane.  One bulk copy per row
+                // hands the whole 768 bytes to the TMA engine: no LSU / L1 store traffic at all.
+                pp_fence_proxy_async();  // this lane's staging writes -> visible to the async proxy
                 __syncwarp();
-                // Per-lane (x,y,yaw) stores would touch 24 sectors per warp instruction (ncu: 3x the ideal
-                // sector count, L1 79 % busy, lg_throttle the top stall).  The 3*cnt doubles of this step are
-                // contiguous in `out`: one scalar store to reach 16-byte alignment if needed, then 16-byte
-                // vector stores straight from the staging row (a full step = 768 B = 48 vectors).
-                double *d0 = dst + 3 * (size_t)k0;
-                const uint32_t D = 3 * cnt;
-                const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(d0) >> 3) & 1u);
-                const uint32_t nvec = (D - head) >> 1;
+                if (lane == 0) {
+                    if (head) d0[0] = stage[0];
+                    if (nvec) pp_bulk_s2g(d0 + head, stage + head, nvec * 16u);
+                    pp_bulk_commit();
+                    if ((D - head) & 1u) d0[D - 1] = stage[D - 1];
+                }
+#else
+                __syncwarp();
                 if (lane == 0 && head) d0[0] = stage[0];
 #pragma unroll
                 for (uint32_t v = lane; v < 64; v += 32) {
@@ -381,6 +405,7 @@ __global__ void __launch_bounds__(PP_FILL_THREADS)
                 }
                 if (lane == 0 && ((D - head) & 1u)) d0[D - 1] = stage[D - 1];
                 __syncwarp();
+#endif
             }
             base += ns;
             if (seg < 2) {  // next origin = this segment's end point (src/dubins.rs:258-271, read back at :230)
@@ -393,6 +418,9 @@ __global__ void __launch_bounds__(PP_FILL_THREADS)
             }
         }
     }
+#if PP_FILL_TMA
+    if (lane == 0) pp_bulk_wait<0>();  // every bulk store of this warp has landed before the CTA retires
+#endif
 }
 
 int pp_launch_dubins_fill(pp_ctx *ctx, size_t n, const void *plans, const uint64_t *offsets, double *out,

@@ -185,4 +185,21 @@ __device__ __forceinline__ void pp_bulk_g2s(void *smem_dst, const void *gmem_src
                  "l"(gmem_src), "r"(bytes), "r"(pp_smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk copy (TMA engine; completion through bulk async-groups); bytes % 16 == 0, both addresses
+// 16-byte aligned.  The data must have been made visible to the async proxy (pp_fence_proxy_async) by its writers.
+__device__ __forceinline__ void pp_bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(pp_smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pp_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source (the staging row is free again)
+template <int N>
+__device__ __forceinline__ void pp_bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void pp_bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 #endif
