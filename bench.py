@@ -668,6 +668,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
         }
         if kname == "extend_fused":
             out[name]["nn_grid_build_ms_after_upload"] = grid_build_ms
+        if kname == "extend_fused" and not args.profile:
             # the same step end to end through the host C-ABI call (pp_rrt_extend on pinned host buffers: 16 B in and
             # 13 B out per query cross PCIe inside the timed region); wall clock, max over ranks
             hq = [pp.PinnedArray(m, np.float64) for _ in range(2)]

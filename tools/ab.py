@@ -20,11 +20,14 @@ CSRC = os.path.join(ROOT, "rs-pathplanning_b200", "csrc")
 OUT = os.path.join(ROOT, "build_ab")
 
 ROWS = [  # (label, path into the bench JSON line, scale, unit)
-    ("eval 2^24 pairs", ("ms_per_step",), 1.0, "ms"),
+    ("eval 2^24 pairs (kernel avg)", ("roofline", "kernel_ms_avg"), 1.0, "ms"),
     ("eval far", ("workloads", "dubins_far", "ms_per_step"), 1.0, "ms"),
     ("extend (default)", ("workloads", "extend", "ms_per_step"), 1.0, "ms"),
-    ("  nn_grid", ("workloads", "extend", "nn_kernel_ms"), 1.0, "ms"),
-    ("  collide grid", ("workloads", "extend", "collide_kernel_ms"), 1.0, "ms"),
+    ("  fused kernel", ("workloads", "extend", "fused_kernel_ms"), 1.0, "ms"),
+    ("  binning (3 launches)", ("workloads", "extend", "sort_kernels_ms"), 1.0, "ms"),
+    ("extend (split)", ("workloads", "extend_split", "ms_per_step"), 1.0, "ms"),
+    ("  nn_grid", ("workloads", "extend_split", "nn_kernel_ms"), 1.0, "ms"),
+    ("  collide grid", ("workloads", "extend_split", "collide_kernel_ms"), 1.0, "ms"),
     ("extend_scan", ("workloads", "extend_scan", "ms_per_step"), 1.0, "ms"),
     ("extend_dubins", ("workloads", "extend_dubins", "ms_per_step"), 1.0, "ms"),
     ("c5 slice", ("workloads", "dubins_rrt", "ms_per_step"), 1.0, "ms"),
