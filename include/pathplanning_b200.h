@@ -114,12 +114,18 @@ int pp_host_free(void *p);
 int pp_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi_2_pi);
 
 /* all six words for explicit (alpha, beta, d): src/dubins.rs:27-153 (lsl, rsr, lsr, rsl, rlr, lrl).
- * tpq: n*6*3 doubles (NaN where infeasible); feasible: n*6 bytes. */
+ * tpq: n*6*3 doubles (NaN where infeasible); feasible: n*6 bytes.
+ * Domain: alpha, beta in [0, 2*pi] and 0 <= d < 1e5 -- what the reference's own caller passes (both angles come out of
+ * mod2pi, src/dubins.rs:336-338); values outside are refused with PP_ERR_INVALID (NaN is accepted: infeasible). */
 int pp_dubins_words(pp_ctx *ctx, size_t n, const double *alpha, const double *beta, const double *d, double *tpq,
                     uint8_t *feasible);
 
 /* dubins_path_planning's evaluation half (src/dubins.rs:401-408 + 326-363): frame change, six words,
- * strict-< in-order minimum.  radius_arr may be NULL -> scalar `radius` (DubinsConfig.turn_radius).
+ * strict-< in-order minimum.  The frame change computes theta = atan2(dy, dx) - syaw (a few ulp from the reference's
+ * rotate-then-atan2), and the kernels' sincos / atan2 / acos are within 1.5 ulp of glibc's: for a pair whose alpha,
+ * t or q sits within ~1e-9 of a mod2pi wrap (RRT edges always have alpha at the 0 / 2*pi wrap), whose two best words
+ * tie to 1e-9, or whose word is within 1e-9 of infeasible, the chosen word -- hence the sample count -- may differ
+ * from the reference's; everywhere else word, cost and samples agree to 1e-9 relative.  radius_arr may be NULL -> scalar `radius` (DubinsConfig.turn_radius).
  * cost is radius-normalised as in the reference (src/dubins.rs:395); word = pp_word or PP_WORD_NONE
  * (reference returns None, src/dubins.rs:397; cost = +inf).  tpq (n*3) may be NULL. */
 int pp_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,

@@ -719,6 +719,63 @@ static double aabb_pad(const aabb_t *b) {
     return m * 0x1p-40 + 0x1p-1000;
 }
 
+/* circle filter, the second cull of the culled loop (same expressions as geo_predicates.cuh: pp_make_ring_circle /
+ * pp_circle_class): per ring a centre, an inflated outer radius^2 no ring point exceeds and a deflated inner radius^2
+ * whose disc lies inside the polygon.  class 0: the segment stays outside the outer circle (ring skipped); class 1:
+ * both end points inside the inner circle (blocked); class 2: the exact geo predicates decide. */
+typedef struct {
+    double cx, cy, rout2, rin2;
+} circle_t;
+
+static circle_t ring_circle(const double *rx, const double *ry, size_t n, const aabb_t *b, double pad) {
+    circle_t c;
+    c.cx = c.cy = 0.0;
+    c.rout2 = INFINITY;
+    c.rin2 = 0.0;
+    int finite = 1;
+    for (size_t i = 0; i < n; ++i)
+        if (!isfinite(rx[i]) || !isfinite(ry[i])) finite = 0;
+    if (!finite || n < 3) return c;
+    c.cx = 0.5 * (b->minx + b->maxx);
+    c.cy = 0.5 * (b->miny + b->maxy);
+    double rout = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        double d = hypot(rx[i] - c.cx, ry[i] - c.cy);
+        if (d > rout) rout = d;
+    }
+    double ro = rout * (1.0 + 1.0e-6) + pad;
+    c.rout2 = ro * ro;
+    if (ppo_point_position(rx, ry, n, c.cx, c.cy) == 1) {
+        double rin = INFINITY;
+        for (size_t i = 0; i + 1 < n; ++i) {
+            double x0 = rx[i], y0 = ry[i], dx = rx[i + 1] - x0, dy = ry[i + 1] - y0;
+            double l2 = dx * dx + dy * dy;
+            double t = (l2 > 0.0) ? ((c.cx - x0) * dx + (c.cy - y0) * dy) / l2 : 0.0;
+            t = (t > 0.0) ? ((t < 1.0) ? t : 1.0) : 0.0;
+            double d = hypot(c.cx - (x0 + t * dx), c.cy - (y0 + t * dy));
+            if (d < rin) rin = d;
+        }
+        double ri = rin * (1.0 - 1.0e-6) - pad;
+        if (ri > 0.0 && ri < INFINITY) c.rin2 = ri * ri;
+    }
+    return c;
+}
+
+static int circle_class(const circle_t *c, double ax, double ay, double bx, double by) {
+    double acx = c->cx - ax, acy = c->cy - ay;
+    double a2 = acx * acx + acy * acy;
+    double bcx = c->cx - bx, bcy = c->cy - by;
+    double b2 = bcx * bcx + bcy * bcy;
+    if (a2 < c->rin2 && b2 < c->rin2) return 1;
+    if (!(a2 > c->rout2) || !(b2 > c->rout2)) return 2;
+    if (!(a2 < 1.0e6 * c->rout2) || !(b2 < 1.0e6 * c->rout2)) return 2;
+    double abx = bx - ax, aby = by - ay;
+    double e = acx * abx + acy * aby;
+    double f = abx * abx + aby * aby;
+    if (!(e > 0.0) || !(e < f)) return 0;
+    return (a2 * f - e * e > c->rout2 * f) ? 0 : 2;
+}
+
 int ppo_verify_culled(const ppo_world *w, const double *lx, const double *ly, size_t n) {
     for (size_t k = 0; k < n; ++k)
         if (!poly_contains_point(w->bx, w->by, w->nb, lx[k], ly[k])) return 0;
@@ -727,16 +784,32 @@ int ppo_verify_culled(const ppo_world *w, const double *lx, const double *ly, si
         size_t rn = w->ring_off[r + 1] - w->ring_off[r];
         aabb_t b = ring_aabb(rx, ry, rn);
         double pad = aabb_pad(&b);
+        /* quick reject of the whole line against the ring's padded box before the ring's circle is set up */
+        int near = 0;
+        for (size_t k = 0; k < n && !near; ++k) {
+            size_t k1 = (k + 1 < n) ? k + 1 : k;
+            double sminx = lx[k] < lx[k1] ? lx[k] : lx[k1], smaxx = lx[k] > lx[k1] ? lx[k] : lx[k1];
+            double sminy = ly[k] < ly[k1] ? ly[k] : ly[k1], smaxy = ly[k] > ly[k1] ? ly[k] : ly[k1];
+            if (!(smaxx < b.minx - pad || sminx > b.maxx + pad || smaxy < b.miny - pad || sminy > b.maxy + pad)) near = 1;
+        }
+        if (!near && n > 0) continue;
+        circle_t c = ring_circle(rx, ry, rn, &b, rn ? pad : 0.0);
         for (size_t j = 0; j + 1 < n; ++j) {
             double sminx = lx[j] < lx[j + 1] ? lx[j] : lx[j + 1], smaxx = lx[j] > lx[j + 1] ? lx[j] : lx[j + 1];
             double sminy = ly[j] < ly[j + 1] ? ly[j] : ly[j + 1], smaxy = ly[j] > ly[j + 1] ? ly[j] : ly[j + 1];
             if (smaxx < b.minx - pad || sminx > b.maxx + pad || smaxy < b.miny - pad || sminy > b.maxy + pad)
                 continue;
+            int cls = circle_class(&c, lx[j], ly[j], lx[j + 1], ly[j + 1]);
+            if (cls == 0) continue;
+            if (cls == 1) return 0;
             if (ppo_lines_intersect(rx, ry, rn, lx + j, ly + j, 2)) return 0;
         }
         for (size_t k = 0; k < n; ++k) {
             double x = lx[k], y = ly[k];
             if (x < b.minx - pad || x > b.maxx + pad || y < b.miny - pad || y > b.maxy + pad) continue;
+            int cls = circle_class(&c, x, y, x, y);
+            if (cls == 0) continue;
+            if (cls == 1) return 0;
             if (poly_contains_point(rx, ry, rn, x, y)) return 0;
         }
     }

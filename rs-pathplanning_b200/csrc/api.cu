@@ -177,6 +177,7 @@ void pp_world_free(pp_world_dev &w) {
     cudaFree(w.oy);
     cudaFree(w.meta);
     cudaFree(w.aabb32);
+    cudaFree(w.circ);
     cudaFree(w.cell_start);
     cudaFree(w.cell_items);
     w = pp_world_dev();
@@ -351,6 +352,14 @@ int pp_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi_2_pi) 
 int pp_dubins_words(pp_ctx *ctx, size_t n, const double *alpha, const double *beta, const double *d, double *tpq,
                     uint8_t *feasible) {
     if (!ctx || (n && (!alpha || !beta || !d || !tpq || !feasible))) return PP_ERR_INVALID;
+    // domain of the word formulas as the reference calls them (src/dubins.rs:336-338: alpha and beta come out of mod2pi,
+    // d = hypot * c): the kernels' range reductions are specialised to it, so anything else is refused, not guessed
+    for (size_t i = 0; i < n; ++i) {
+        const bool ok = alpha[i] >= 0.0 && alpha[i] <= 6.283185307179586 && beta[i] >= 0.0 && beta[i] <= 6.283185307179586 &&
+                        d[i] >= 0.0 && d[i] < 1.0e5;
+        if (!ok && !(std::isnan(alpha[i]) || std::isnan(beta[i]) || std::isnan(d[i])))  // NaN in -> infeasible out (Q5)
+            return pp_fail(ctx, PP_ERR_INVALID, "pp_dubins_words: alpha, beta must lie in [0, 2*pi] and d in [0, 1e5)");
+    }
     pp_guard g(ctx);
     cudaStream_t s = ctx->stream;
     PP_TMP(ctx, da, s, n * 8);
@@ -783,6 +792,7 @@ int pp_obstacles_upload(pp_ctx *ctx, const double *bounds_x, const double *bound
     // ---- obstacle rings
     std::vector<double> ox, oy;
     std::vector<pp_ring_meta> meta(n_rings);
+    std::vector<pp_ring_circle> circ(n_rings);
     for (size_t r = 0; r < n_rings; ++r) {
         if (ring_off[r + 1] < ring_off[r]) return pp_fail(ctx, PP_ERR_INVALID, "ring_off must be non-decreasing");
         std::vector<double> rx(ring_x + ring_off[r], ring_x + ring_off[r + 1]),
@@ -811,6 +821,8 @@ int pp_obstacles_upload(pp_ctx *ctx, const double *bounds_x, const double *bound
         } else {
             m.pad = pp_aabb_pad(m.minx, m.miny, m.maxx, m.maxy);
         }
+        circ[r] = pp_make_ring_circle(rx.data(), ry.data(), (uint32_t)rx.size(), m.minx, m.miny, m.maxx, m.maxy, m.pad,
+                                      finite && !rx.empty());
         ox.insert(ox.end(), rx.begin(), rx.end());
         oy.insert(oy.end(), ry.begin(), ry.end());
     }
@@ -905,6 +917,7 @@ int pp_obstacles_upload(pp_ctx *ctx, const double *bounds_x, const double *bound
     if ((rc = pp_upload_vec(ctx, &w.oy, oy))) return rc;
     if ((rc = pp_upload_vec(ctx, &w.meta, meta))) return rc;
     if ((rc = pp_upload_vec(ctx, &w.aabb32, aabb32))) return rc;
+    if ((rc = pp_upload_vec(ctx, &w.circ, circ))) return rc;
     if ((rc = pp_upload_vec(ctx, &w.cell_start, cstart))) return rc;
     if ((rc = pp_upload_vec(ctx, &w.cell_items, citems))) return rc;
     w.nb = nb;
@@ -945,6 +958,7 @@ pp_world_view pp_make_world_view(const pp_world_dev &w) {
     v.meta = w.meta;
     v.n_rings = w.n_rings;
     v.aabb32 = w.aabb32;
+    v.circ = w.circ;
     v.n_aabb_tiles = w.n_aabb_tiles;
     v.cell_start = w.cell_start;
     v.cell_items = w.cell_items;

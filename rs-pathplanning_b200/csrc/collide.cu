@@ -50,6 +50,19 @@ __device__ __forceinline__ bool pp_outside_padded(const pp_ring_meta &m, double 
     return (x < m.minx - m.pad) || (x > m.maxx + m.pad) || (y < m.miny - m.pad) || (y > m.maxy + m.pad);
 }
 
+// circle filter of ring r for the segment a-b (geo_predicates.cuh: pp_circle_class): 0 skip the ring, 1 blocked, 2 exact
+__device__ __forceinline__ int pp_ring_circle_class(const pp_world_view &w, uint32_t r, double ax, double ay, double bx,
+                                                    double by) {
+    const double2 lo = __ldg(reinterpret_cast<const double2 *>(w.circ + r));
+    const double2 hi = __ldg(reinterpret_cast<const double2 *>(w.circ + r) + 1);
+    pp_ring_circle c;
+    c.cx = lo.x;
+    c.cy = lo.y;
+    c.rout2 = hi.x;
+    c.rin2 = hi.y;
+    return pp_circle_class(c, ax, ay, bx, by);
+}
+
 // ---- warp-cooperative narrow phase.  The warp is split into four groups of eight lanes; a group works on one
 // pending (line segment, ring) candidate and its lane `sub` takes ring segments sub, sub + 8, ...: the rings of
 // this domain have 4-20 segments, so whole-warp passes would leave three quarters of the lanes idle.  All 32
@@ -241,6 +254,12 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
                             const bool sgx = x1 < x0, sgy = y1 < y0;
                             const bool seg_in = !((sgx ? x0 : x1) < mt.minx - mt.pad || (sgx ? x1 : x0) > mt.maxx + mt.pad ||
                                                   (sgy ? y0 : y1) < mt.miny - mt.pad || (sgy ? y1 : y0) > mt.maxy + mt.pad);
+                            const int cls = pp_ring_circle_class(w, t * PP_AABB_TILE + r, x0, y0, x1, y1);  // circle filter
+                            if (cls == 0) continue;
+                            if (cls == 1) {
+                                hit = true;
+                                break;
+                            }
                             if ((seg_in && pp_ring_hits_segment(rx, ry, mt.count, x0, y0, x1, y1)) ||
                                 (!pp_outside_padded(mt, x0, y0) && pp_point_position(rx, ry, mt.count, x0, y0) == 1) ||
                                 (!pp_outside_padded(mt, x1, y1) && pp_point_position(rx, ry, mt.count, x1, y1) == 1)) {
@@ -317,8 +336,18 @@ __device__ __forceinline__ bool pp_verify_segment_grid(const pp_world_view &w, b
                     ++kcur;
                     const float4 bb = __ldg(w.aabb32 + r);
                     if (!(q32x1 < bb.x || q32x0 > bb.z || q32y1 < bb.y || q32y0 > bb.w)) {
-                        ring = r;
-                        break;
+                        // circle filter: most box candidates are decided here, per lane, without the warp-wide
+                        // exact predicates (edge outside the ring's outer circle, or both ends inside its inner one)
+                        const int cls = pp_ring_circle_class(w, r, x0, y0, x1, y1);
+                        if (cls == 1) {
+                            hit = true;
+                            more = false;
+                            break;
+                        }
+                        if (cls == 2) {
+                            ring = r;
+                            break;
+                        }
                     }
                 } else {  // next row of cells: one contiguous run of ids
                     if (cy > cy1) {
@@ -440,15 +469,27 @@ __global__ void __launch_bounds__(256)
     rank[j] = atomicAdd(&hist[bin], 1u);
 }
 
-// exclusive scan of up to 65 536 bin counts in ONE block (64 values per thread), in place
-__global__ void __launch_bounds__(1024) pp_extend_scan_kernel(uint32_t *__restrict__ hist, uint32_t nb) {
+// exclusive scan of up to 65 536 bin counts in ONE block, in place: a thread owns 64 consecutive counts, fetched with
+// sixteen independent 16-byte loads into registers (the first version walked them one dependent load at a time: ~25 us)
+#define PP_EXT_SCAN_PER 64
+__global__ void __launch_bounds__(1024) pp_extend_scan_kernel(uint32_t *__restrict__ hist) {
     __shared__ uint32_t warp_sums[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t per = (nb + 1023u) / 1024u;
-    const uint32_t first = threadIdx.x * per;
-    uint32_t sum = 0;
-    for (uint32_t k = 0; k < per; ++k)
-        if (first + k < nb) sum += hist[first + k];
+    uint4 *mine = reinterpret_cast<uint4 *>(hist + (size_t)threadIdx.x * PP_EXT_SCAN_PER);
+    // two halves of 32 counts: eight independent 16-byte loads in flight at a time (all sixteen would not fit the
+    // 64 registers a 1 024-thread block leaves per thread)
+    uint32_t half[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = mine[8 * h + k];
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
+        half[h] = s;
+    }
+    const uint32_t sum = half[0] + half[1];
     uint32_t inc = sum;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -467,12 +508,25 @@ __global__ void __launch_bounds__(1024) pp_extend_scan_kernel(uint32_t *__restri
     }
     __syncthreads();
     uint32_t run = warp_sums[warp] + inc - sum;
-    for (uint32_t k = 0; k < per; ++k)
-        if (first + k < nb) {
-            const uint32_t v = hist[first + k];
-            hist[first + k] = run;
-            run += v;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = mine[8 * h + k];  // second read: this thread's own lines, L1-resident
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint4 o;
+            o.x = run;
+            run += v[k].x;
+            o.y = run;
+            run += v[k].y;
+            o.z = run;
+            run += v[k].z;
+            o.w = run;
+            run += v[k].w;
+            mine[8 * h + k] = o;
         }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -621,6 +675,12 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
                             const bool seg_in =
                                 !((sgx ? x0[e] : x1[e]) < mt.minx - mt.pad || (sgx ? x1[e] : x0[e]) > mt.maxx + mt.pad ||
                                   (sgy ? y0[e] : y1[e]) < mt.miny - mt.pad || (sgy ? y1[e] : y0[e]) > mt.maxy + mt.pad);
+                            const int cls = pp_ring_circle_class(w, ring, x0[e], y0[e], x1[e], y1[e]);  // circle filter
+                            if (cls == 0) continue;
+                            if (cls == 1) {
+                                hit[e] = true;
+                                continue;
+                            }
                             if ((seg_in && pp_ring_hits_segment(rx, ry, mt.count, x0[e], y0[e], x1[e], y1[e])) ||
                                 (!pp_outside_padded(mt, x0[e], y0[e]) &&
                                  pp_point_position(rx, ry, mt.count, x0[e], y0[e]) == 1) ||
@@ -807,6 +867,7 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 cy = cy1 + 1;
             }
             // the ids of a ROW of cells are one contiguous run of cell_items: the walk goes row by row
+            bool inner = false;
             for (;;) {
                 uint32_t ring = 0xFFFFFFFFu;
                 while (more) {
@@ -815,8 +876,17 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                         ++kcur;
                         const float4 bb = __ldg(w.aabb32 + r);
                         if (!(q32x1 < bb.x || q32x0 > bb.z || q32y1 < bb.y || q32y0 > bb.w)) {
-                            ring = r;
-                            break;
+                            // circle filter on this lane's segment (its vertex alone for the last point)
+                            const int cls = pp_ring_circle_class(w, r, x, y, xe, ye);
+                            if (cls == 1) {  // both ends inside the ring's inner circle: the polyline is blocked
+                                inner = true;
+                                more = false;
+                                break;
+                            }
+                            if (cls == 2) {
+                                ring = r;
+                                break;
+                            }
                         }
                     } else {
                         if (cy > cy1) {
@@ -828,6 +898,10 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                         kend = __ldg(row + cx1 + 1);
                         ++cy;
                     }
+                }
+                if (__ballot_sync(0xffffffffu, inner) != 0u) {
+                    bad = true;
+                    break;
                 }
                 uint32_t pend = __ballot_sync(0xffffffffu, ring != 0xFFFFFFFFu);
                 if (pend == 0u) break;
@@ -921,16 +995,16 @@ int pp_launch_rrt_extend_fused(pp_ctx *ctx, size_t m, const double *qx, const do
             ++b.shift;
         }
         const uint32_t nb = (uint32_t)b.bx * (uint32_t)b.by;
-        const size_t hist_words = ((size_t)nb + 64) & ~(size_t)63;
+        const size_t hist_words = 1024 * PP_EXT_SCAN_PER;  // the scan block always covers 65 536 slots (zero beyond nb)
         int rc = pp_scratch_reserve(ctx, (hist_words + 3 * m) * 4);
         if (rc) return rc;
         uint32_t *hist = (uint32_t *)ctx->scratch, *bin_of = hist + hist_words, *rank = bin_of + m;
         perm = rank + m;
         pp_launch_scope scope(ctx, "extend_sort", 3);
-        PP_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4, stream));
+        PP_CUDA(ctx, cudaMemsetAsync(hist, 0, hist_words * 4, stream));
         const unsigned g1 = (unsigned)((m + 255) / 256);
         pp_extend_bin_kernel<<<g1, 256, 0, stream>>>(g, b, qx, qy, (uint32_t)m, hist, bin_of, rank);
-        pp_extend_scan_kernel<<<1, 1024, 0, stream>>>(hist, nb);
+        pp_extend_scan_kernel<<<1, 1024, 0, stream>>>(hist);
         pp_extend_scatter_kernel<<<g1, 256, 0, stream>>>((uint32_t)m, hist, bin_of, rank, perm);
         PP_CUDA(ctx, cudaGetLastError());
     }

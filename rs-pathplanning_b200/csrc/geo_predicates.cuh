@@ -119,3 +119,73 @@ PP_HD double pp_aabb_pad(double minx, double miny, double maxx, double maxy) {
     if (fabs(maxy) > m) m = fabs(maxy);
     return m * 0x1p-40 + 0x1p-1000;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Circle filter (second, exact-by-margin broad phase).  Per ring: a centre c, the square of an OUTER radius that
+// every ring point stays inside (inflated by 1e-6 relative + the box pad) and the square of an INNER radius whose
+// disc lies inside the polygon (deflated likewise; 0 when the centre is not inside the ring).  For a line segment
+// a-b (a == b: a single vertex):
+//   class 0  the whole segment stays outside the outer circle: no ring point is within reach, the polygon neither
+//            meets the segment nor contains a point of it -> the ring is skipped without the exact predicates;
+//   class 1  both end points lie inside the inner circle: the polygon contains them -> Space::verify fails;
+//   class 2  undecided -> the exact geo predicates run (and are the answer).
+// The margins (1e-6 relative) exceed every rounding error of the tests below and of geo's own formulas by orders of
+// magnitude, so classes 0 / 1 agree with what the exact predicates would say -- except, as with the box cull, for
+// line segments on the extension of a ring segment and parallel to it to ~2^-45 rad, where geo's parameter test is
+// rounding noise (tests/test_oracle_geo.py).  The oracle's culled loop applies the same rule
+// with the same arithmetic (the checker restates it as circle_class).
+// ------------------------------------------------------------------------------------------------------------------
+struct pp_ring_circle {
+    double cx, cy, rout2, rin2;
+};
+
+PP_HD int pp_circle_class(const pp_ring_circle &c, double ax, double ay, double bx, double by) {
+    const double acx = c.cx - ax, acy = c.cy - ay;
+    const double a2 = acx * acx + acy * acy;
+    const double bcx = c.cx - bx, bcy = c.cy - by;
+    const double b2 = bcx * bcx + bcy * bcy;
+    if (a2 < c.rin2 && b2 < c.rin2) return 1;
+    if (!(a2 > c.rout2) || !(b2 > c.rout2)) return 2;  // an end point within reach of the ring (or NaN)
+    // far end points make the cancellation below too coarse for the margin (and may overflow): leave it to the predicates
+    if (!(a2 < 1.0e6 * c.rout2) || !(b2 < 1.0e6 * c.rout2)) return 2;
+    const double abx = bx - ax, aby = by - ay;
+    const double e = acx * abx + acy * aby;  // (c - a) . (b - a)
+    const double f = abx * abx + aby * aby;
+    if (!(e > 0.0) || !(e < f)) return 0;  // the closest point of the segment is an end point, and both are outside
+    // closest point in the interior: |c - a|^2 - e^2 / f > rout2, multiplied through by f > 0
+    return (a2 * f - e * e > c.rout2 * f) ? 0 : 2;
+}
+
+// host-side set-up of one ring's circle (n points, closed ring); the CPU checker restates the same expressions
+inline pp_ring_circle pp_make_ring_circle(const double *rx, const double *ry, uint32_t n, double minx, double miny,
+                                          double maxx, double maxy, double pad, bool finite) {
+    pp_ring_circle c;
+    c.cx = c.cy = 0.0;
+    c.rout2 = INFINITY;  // never class 0 / 1: always undecided
+    c.rin2 = 0.0;
+    if (!finite || n < 3) return c;
+    c.cx = 0.5 * (minx + maxx);
+    c.cy = 0.5 * (miny + maxy);
+    double rout = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const double d = hypot(rx[i] - c.cx, ry[i] - c.cy);
+        if (d > rout) rout = d;
+    }
+    const double ro = rout * (1.0 + 1.0e-6) + pad;
+    c.rout2 = ro * ro;
+    if (pp_point_position(rx, ry, n, c.cx, c.cy) == 1) {
+        double rin = INFINITY;
+        for (uint32_t i = 0; i + 1 < n; ++i) {
+            const double x0 = rx[i], y0 = ry[i], dx = rx[i + 1] - x0, dy = ry[i + 1] - y0;
+            const double l2 = dx * dx + dy * dy;
+            double t = (l2 > 0.0) ? ((c.cx - x0) * dx + (c.cy - y0) * dy) / l2 : 0.0;
+            t = (t > 0.0) ? ((t < 1.0) ? t : 1.0) : 0.0;
+            const double d = hypot(c.cx - (x0 + t * dx), c.cy - (y0 + t * dy));
+            if (d < rin) rin = d;
+        }
+        const double ri = rin * (1.0 - 1.0e-6) - pad;
+        if (ri > 0.0 && ri < INFINITY) c.rin2 = ri * ri;
+    }
+    return c;
+}

@@ -19,11 +19,17 @@ struct pp_nn_grid_view {
 };
 
 // (bx_out, by_out): coordinates of the winner (undefined when bi_out == 0xFFFFFFFF) -- the extend step needs them
-// for the edge and gets them from the scan instead of a second gather
+// for the edge and gets them from the scan instead of a second gather.
+// Latency structure (ncu r02: 63 % of this function's samples were load-scoreboard stalls): the six row offsets of
+// the 3 x 3 block are loaded before any of them is used, the coordinate loop runs one load ahead, and a candidate's
+// node id is NOT fetched inside the loop -- the winner is tracked by its position in the cell arrays and its id is
+// read once at the end; only an exact tie of two distances (rare) needs ids early.
 __device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, double x, double y, double &best_out,
                                                   uint32_t &bi_out, double &bx_out, double &by_out) {
     double best = CUDART_INF, bx = 0.0, by = 0.0;
-    uint32_t bi = 0xFFFFFFFFu;
+    uint32_t bi = 0xFFFFFFFFu;  // id of the winner when known (src == 1)
+    uint32_t bk = 0;            // position of the winner in the cell arrays (src == 2)
+    int src = 0;                // 0: no node yet, 1: id known (tail node or resolved tie), 2: position known
     for (uint32_t i = g.grid_n; i < g.n_nodes; ++i) {  // the tail, in index order, strict compare (as the scans)
         const double nx = __ldg(g.node_x + i), ny = __ldg(g.node_y + i);
         const double dx = nx - x, dy = ny - y;
@@ -33,25 +39,35 @@ __device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, doub
             bi = i;
             bx = nx;
             by = ny;
+            src = 1;
         }
     }
-    // candidates k0 <= k < k1 of the cell-sorted arrays: same d2 arithmetic as the scans, (d2, id) lexicographic
-    // minimum; the id is fetched only when a candidate ties or improves
+    // candidates k0 <= k < k1 of the cell-sorted arrays: same d2 arithmetic as the scans, (d2, id) lexicographic minimum
     auto scan = [&](uint32_t k0, uint32_t k1) {
+        if (k0 >= k1) return;
+        double2 p = __ldg(g.cell_xy + k0);
         for (uint32_t k = k0; k < k1; ++k) {
-            const double2 p = __ldg(g.cell_xy + k);
-            const double dx = p.x - x, dy = p.y - y;
+            const double2 q = p;
+            if (k + 1 < k1) p = __ldg(g.cell_xy + k + 1);  // one load ahead of the arithmetic
+            const double dx = q.x - x, dy = q.y - y;
             const double v = dx * dx + dy * dy;
-            if (v <= best) {
+            if (v < best) {
+                best = v;
+                bk = k;
+                bx = q.x;
+                by = q.y;
+                src = 2;
+            } else if (v == best && src != 0) {
+                // exact tie: the lower id wins.  (d2 = +inf -- a query or node at 1e300, +-inf -- ties with the initial
+                // best and must leave "no node", as the strict compare of the scans does: src == 0 skips it.)
                 const uint32_t i = __ldg(g.cell_items + k);
-                // a tie only counts against a node already held: d2 = +inf (a query or node at 1e300, +-inf) ties
-                // with the initial best and must leave "no node", as the strict compare of the scans does
-                if (v < best || (i < bi && bi != 0xFFFFFFFFu)) {
-                    best = v;
-                    bi = i;
-                    bx = p.x;
-                    by = p.y;
+                const uint32_t cur = (src == 1) ? bi : __ldg(g.cell_items + bk);
+                if (i < cur) {
+                    bx = q.x;
+                    by = q.y;
                 }
+                bi = (i < cur) ? i : cur;
+                src = 1;
             }
         }
     };
@@ -61,17 +77,25 @@ __device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, doub
         int cx = (fx >= (double)gx) ? gx - 1 : ((fx > 0.0) ? (int)fx : 0);  // NaN -> 0
         int cy = (fy >= (double)gy) ? gy - 1 : ((fy > 0.0) ? (int)fy : 0);
         // rings 0 and 1 together: the 3 x 3 block is three runs of the cell-sorted arrays (a row of cells is
-        // contiguous), i.e. six offset loads instead of eighteen
+        // contiguous); all six offsets are requested before the first run is walked
         {
             const int xa = max(cx - 1, 0), xb = min(cx + 1, gx - 1);
-            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gy - 1); ++yy) {
+            const int ya = max(cy - 1, 0), yb = min(cy + 1, gy - 1);
+            uint32_t r0[3], r1[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int yy = min(ya + t, yb);
                 const uint32_t *row = g.cell_start + (size_t)yy * gx;
-                scan(__ldg(row + xa), __ldg(row + xb + 1));
+                r0[t] = __ldg(row + xa);
+                r1[t] = __ldg(row + xb + 1);
             }
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                if (ya + t <= yb) scan(r0[t], r1[t]);
         }
         const int maxr = max(gx, gy);
         for (int r = 2; r <= maxr; ++r) {
-            if (bi != 0xFFFFFFFFu) {
+            if (src != 0) {
                 double lim = (double)(r - 1) * g.gcell * (1.0 - 0x1p-30);
                 if (best < lim * lim) break;
             }
@@ -87,8 +111,9 @@ __device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, doub
             }
         }
     }
+    if (src == 2) bi = __ldg(g.cell_items + bk);
     best_out = best;
-    bi_out = bi;
+    bi_out = (src == 0) ? 0xFFFFFFFFu : bi;
     bx_out = bx;
     by_out = by;
 }

@@ -33,6 +33,8 @@ struct pp_tree_dev {
     size_t cell_cap = 0, item_cap = 0;
 };
 
+struct pp_ring_circle;  // geo_predicates.cuh
+
 struct pp_ring_meta {  // per obstacle ring
     double minx, miny, maxx, maxy;  // exact AABB of the ring's points
     double pad;                     // conservative rounding pad (see collide.cu)
@@ -50,6 +52,7 @@ struct pp_world_dev {
     uint32_t n_pts = 0, n_rings = 0;
     pp_ring_meta *meta = nullptr;
     float4 *aabb32 = nullptr;  // outward-rounded padded AABBs (minx, miny, maxx, maxy) for the fp32 broad phase
+    struct pp_ring_circle *circ = nullptr;  // per ring: centre, inflated outer / deflated inner radius^2 (geo_predicates.cuh)
     uint32_t n_aabb_tiles = 0;
     // byte grid classifying cells of the bounds' AABB: 0 outside, 1 inside, 2 needs the exact test
     uint8_t *bcls = nullptr;
@@ -140,6 +143,7 @@ struct pp_world_view {
     const pp_ring_meta *meta;
     uint32_t n_rings;
     const float4 *aabb32;
+    const struct pp_ring_circle *circ;
     uint32_t n_aabb_tiles;
     const uint32_t *cell_start, *cell_items;
     int gx, gy;

@@ -183,6 +183,12 @@ def test_eval_edge_cases(ctx, O):
     assert c.size == 0 and w.size == 0
     with pytest.raises(Exception):
         ctx.dubins_eval([0.0], [0.0], [0.0], [1.0], [0.0], [0.0], radius=0.0)
+    # the word formulas' domain is the reference's own call pattern (alpha, beta out of mod2pi): anything else is refused
+    for a, b, dd in [(7.0, 0.0, 1.0), (0.0, -0.1, 1.0), (1.0, 1.0, -1.0), (1.0, 1.0, 2e5)]:
+        with pytest.raises(Exception):
+            ctx.dubins_words([a], [b], [dd])
+    t6, f6 = ctx.dubins_words([nan], [1.0], [1.0])
+    assert not f6.any()
 
 
 @pytest.mark.parametrize("radius,step,dist", [(1.0, 0.1, "mixed"), (0.5, 0.01, "mixed"), (1.0, 0.05, "far"), (2.0, 0.3, "far")])
