@@ -611,15 +611,15 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
     grid_build_ms = None
     # "extend" is the call a user makes (default flags: the library picks the exact grid search for a tree this size);
     # the *_scan* rows force the tiled brute-force kernels of the north-star design; all rows must agree bit for bit
-    for name, nnf, cf, kname in [("extend_scan", 8, 8, "nn_scan"), ("extend", 0, 0, "extend_fused"),
-                                 ("extend_split", 0, 16, "nn_grid"),
+    for name, nnf, cf, kname in [("extend_scan", 8, 8, "nn_scan"), ("extend", 0, 0, "nn_grid"),
+                                 ("extend_fused", 0, 16, "extend_fused"),
                                  ("extend_scan_plain_f64", 1, 8, "nn_scan_f64"),
                                  ("extend_scan_unsorted", 4, 4, "nn_scan_unsorted")]:
         ctx.timing_enable(True)
         fn = lambda: ctx.rrt_extend_dev(m, qx, qy, idx, yaw, ok, nn_flags=nnf, collide_flags=cf)  # noqa: E731
         fn()
         torch.cuda.synchronize()
-        if kname == "extend_fused" and grid_build_ms is None:
+        if kname == "nn_grid" and grid_build_ms is None:
             b_ms, b_n = ctx.timing_get("nn_grid_build")  # the first grid call after the upload built the node grid
             grid_build_ms = b_ms / max(b_n, 1)
         ctx.timing_reset()
@@ -627,7 +627,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
         ksteps = slow_steps if nnf in (1, 4) else steps
         ms, _, _ = time_steps(torch, dist, fn, ksteps, 0, world)
         nn_ms, nn_n = ctx.timing_get(kname)
-        c_ms, c_n = ctx.timing_get({0: "extend_sort", 16: "collide_segments_grid", 8: "collide_segments",
+        c_ms, c_n = ctx.timing_get({16: "extend_sort", 0: "collide_segments_grid", 8: "collide_segments",
                                     4: "collide_segments_unsorted"}[cf])
         ctx.timing_enable(False)
         if ref_idx is None:
@@ -666,9 +666,9 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
                                                         "source": src})(*fact(facts, "pp_rrt_extend_fused_kernel" if kname == "extend_fused"
                                                                               else "pp_nn_grid_kernel", "l2_sectors"))}),
         }
-        if kname == "extend_fused":
+        if kname == "nn_grid":
             out[name]["nn_grid_build_ms_after_upload"] = grid_build_ms
-        if kname == "extend_fused" and not args.profile:
+        if kname == "nn_grid" and not args.profile:
             # the same step end to end through the host C-ABI call (pp_rrt_extend on pinned host buffers: 16 B in and
             # 13 B out per query cross PCIe inside the timed region); wall clock, max over ranks
             hq = [pp.PinnedArray(m, np.float64) for _ in range(2)]
@@ -712,8 +712,7 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
     bounds2, rings2 = pp.synth.circle_world(C4_RINGS, shift=5000.0)
     ctx.obstacles_upload(bounds2, rings2)
     for name, cf, kname, what in [("collide_scan_nohit", 8, "collide_segments", "tiled fp32 box scan over all 10k rings"),
-                                  ("collide_grid_nohit", 16, "collide_segments_grid",
-                                   "uniform obstacle grid as its own launch (PP_COLLIDE_SPLIT)")]:
+                                  ("collide_grid_nohit", 0, "collide_segments_grid", "uniform obstacle grid, the default")]:
         fn = lambda: ctx.rrt_extend_dev(m, qx, qy, idx, yaw, ok, nn_flags=2, collide_flags=cf)  # noqa: E731
         ctx.timing_enable(True)
         fn()

@@ -63,8 +63,9 @@ enum pp_collide_flags {
     PP_COLLIDE_UNSORTED = 4, /* tiled AABB scan with one edge per thread in the caller's order (no binning) */
     PP_COLLIDE_SCAN = 8,     /* tiled scan of ALL ring boxes through shared memory (TMA tiles), edges binned by start
                                 point, 32 boxes per instruction against the warp's union box, hit flags by ballot */
-    PP_COLLIDE_SPLIT = 16    /* pp_rrt_extend only: keep NN and verify as two launches (the default fuses them into one
-                                cell-coherent kernel whenever both halves take their grid route; same bits) */
+    PP_COLLIDE_FUSED = 16    /* pp_rrt_extend only: NN + yaw + verify in ONE cell-coherent launch, the queries binned by
+                                node-grid block first (three small launches).  Same bits as the default pair of
+                                launches; pays off when the binning is amortised, see DESIGN.md section 3 */
 };
 
 /* flags for pp_nn */

@@ -19,7 +19,7 @@ PP_OK, PP_ERR_INVALID, PP_ERR_NO_DEVICE, PP_ERR_CUDA, PP_ERR_NOMEM, PP_ERR_STATE
 COMM_ID_BYTES = 128
 WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
 WORD_NONE = 0xFF
-COLLIDE_DEFAULT, COLLIDE_NO_CULL, COLLIDE_USE_GRID, COLLIDE_UNSORTED, COLLIDE_SCAN, COLLIDE_SPLIT = 0, 1, 2, 4, 8, 16
+COLLIDE_DEFAULT, COLLIDE_NO_CULL, COLLIDE_USE_GRID, COLLIDE_UNSORTED, COLLIDE_SCAN, COLLIDE_FUSED = 0, 1, 2, 4, 8, 16
 NN_DEFAULT, NN_PLAIN_F64, NN_GRID, NN_UNSORTED, NN_SCAN = 0, 1, 2, 4, 8
 PLAN_BYTES = 112
 

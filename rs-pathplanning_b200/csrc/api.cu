@@ -1146,12 +1146,13 @@ int pp_collide_dubins(pp_ctx *ctx, size_t m, const double *sx, const double *sy,
     return PP_OK;
 }
 
-// one extend step on device pointers: the fused kernel when both halves take their default (grid) route -- the library's
-// own choice or PP_NN_GRID / PP_COLLIDE_USE_GRID -- otherwise the NN kernel followed by the verify kernel the flags name
+// one extend step on device pointers: the NN kernel followed by the verify kernel the flags name; with
+// PP_COLLIDE_FUSED (and both halves on their grid route) the binned, fused kernel instead
 static int pp_extend_step(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uint32_t *idx, double *yaw,
                           uint8_t *ok, int nn_flags, int collide_flags, cudaStream_t s) {
-    const bool fused = (nn_flags & PP_NN_GRID) && !(nn_flags & (PP_NN_SCAN | PP_NN_PLAIN_F64 | PP_NN_UNSORTED)) &&
-                       !(collide_flags & (PP_COLLIDE_NO_CULL | PP_COLLIDE_UNSORTED | PP_COLLIDE_SCAN | PP_COLLIDE_SPLIT));
+    const bool fused = (collide_flags & PP_COLLIDE_FUSED) && (nn_flags & PP_NN_GRID) &&
+                       !(nn_flags & (PP_NN_SCAN | PP_NN_PLAIN_F64 | PP_NN_UNSORTED)) &&
+                       !(collide_flags & (PP_COLLIDE_NO_CULL | PP_COLLIDE_UNSORTED | PP_COLLIDE_SCAN));
     if (fused) return pp_launch_rrt_extend_fused(ctx, m, qx, qy, idx, yaw, ok, s);
     int rc = pp_launch_nn(ctx, m, qx, qy, idx, nullptr, nn_flags, s);
     if (rc) return rc;

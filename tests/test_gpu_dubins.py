@@ -187,8 +187,8 @@ def test_eval_edge_cases(ctx, O):
     for a, b, dd in [(7.0, 0.0, 1.0), (0.0, -0.1, 1.0), (1.0, 1.0, -1.0), (1.0, 1.0, 2e5)]:
         with pytest.raises(Exception):
             ctx.dubins_words([a], [b], [dd])
-    t6, f6 = ctx.dubins_words([nan], [1.0], [1.0])
-    assert not f6.any()
+    t6, f6 = ctx.dubins_words([nan], [1.0], [1.0])  # NaN passes the `p_squared < 0` / `|tmp| > 1` tests: Some(NaN) (Q5)
+    assert np.isnan(t6).all()
 
 
 @pytest.mark.parametrize("radius,step,dist", [(1.0, 0.1, "mixed"), (0.5, 0.01, "mixed"), (1.0, 0.05, "far"), (2.0, 0.3, "far")])

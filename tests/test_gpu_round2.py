@@ -10,7 +10,7 @@ from conftest import check_dubins_verdicts, exactly_free, near_parallel_edges
 pytestmark = pytest.mark.gpu
 
 NN_DEFAULT, NN_PLAIN, NN_GRID, NN_UNSORTED, NN_SCAN = 0, 1, 2, 4, 8
-DEFAULT, NO_CULL, USE_GRID, UNSORTED, SCAN, SPLIT = 0, 1, 2, 4, 8, 16
+DEFAULT, NO_CULL, USE_GRID, UNSORTED, SCAN, FUSED = 0, 1, 2, 4, 8, 16
 
 
 def test_c4_full_size_default_equals_exhaustive_loop(ctx, pp, O):
@@ -86,7 +86,7 @@ def test_extend_with_unanswerable_queries(ctx, pp, O):
     """pp_nn answers 0xFFFFFFFF for NaN / Inf queries (get_random_node would return None, src/rrt.rs:408-411): the
     extend steps must report ok = 0 and yaw = NaN for them instead of reading node[0xFFFFFFFF], and leave the context
     usable (no sticky CUDA error)"""
-    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(12_000, 6000, world=100.0)  # > 8 192: the binned fused path
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(12_000, 6000, world=100.0)  # > 8 192: PP_COLLIDE_FUSED bins the queries
     bounds, rings = pp.synth.circle_world(100, world=100.0)
     ctx.tree_upload(nx, ny, nyaw)
     ctx.obstacles_upload(bounds, rings)
@@ -101,7 +101,7 @@ def test_extend_with_unanswerable_queries(ctx, pp, O):
     good = ~none
     want = np.zeros(qx.size, np.uint8)
     want[good] = W.verify_segments(qx[good], qy[good], nx[oidx[good]], ny[oidx[good]])
-    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_DEFAULT, SPLIT), (NN_SCAN, SCAN), (NN_PLAIN, UNSORTED),
+    for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_DEFAULT, FUSED), (NN_SCAN, SCAN), (NN_PLAIN, UNSORTED),
                     (NN_DEFAULT, NO_CULL)]:
         idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=nnf, collide_flags=cf)
         assert np.array_equal(idx, oidx), (nnf, cf)
@@ -112,7 +112,7 @@ def test_extend_with_unanswerable_queries(ctx, pp, O):
     wyaw = np.arctan2(ny[oidx[good]] - qy[good], nx[oidx[good]] - qx[good])
     check_dubins_verdicts(O, W, ok[good], qx[good], qy[good], wyaw, nx[oidx[good]], ny[oidx[good]], nyaw[oidx[good]],
                           0.8, 0.1)
-    few = ctx.rrt_extend(qx[:3000], qy[:3000])  # < 8 192 queries: the fused kernel in the caller's order
+    few = ctx.rrt_extend(qx[:3000], qy[:3000], collide_flags=FUSED)  # < 8 192 queries: the fused kernel in the caller's order
     assert np.array_equal(few[0], oidx[:3000]) and np.array_equal(few[2], want[:3000])
     one = ctx.rrt_extend([nan], [0.0])  # scalar call
     assert one[0][0] == 0xFFFFFFFF and one[2][0] == 0 and math.isnan(one[1][0])

@@ -370,7 +370,7 @@ def test_extend_step(ctx, O, pp):
     oidx, _ = O.nn_brute(nx, ny, qx, qy)
     want = W.verify_segments(qx, qy, nx[oidx], ny[oidx])
     wyaw = np.arctan2(ny[oidx] - qy, nx[oidx] - qx)
-    # (default, default) and (grid, grid) run the fused cell-coherent kernel; 16 = PP_COLLIDE_SPLIT keeps two launches
+    # 16 = PP_COLLIDE_FUSED: queries binned by node-grid block, then NN + yaw + verify in one cell-coherent launch
     for nnf, cf in [(NN_DEFAULT, DEFAULT), (NN_GRID, USE_GRID), (NN_DEFAULT, 16), (NN_PLAIN, DEFAULT), (NN_SCAN, SCAN)]:
         idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=nnf, collide_flags=cf)
         assert np.array_equal(idx, oidx) and np.array_equal(ok, want)

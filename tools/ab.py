@@ -23,11 +23,11 @@ ROWS = [  # (label, path into the bench JSON line, scale, unit)
     ("eval 2^24 pairs (kernel avg)", ("roofline", "kernel_ms_avg"), 1.0, "ms"),
     ("eval far", ("workloads", "dubins_far", "ms_per_step"), 1.0, "ms"),
     ("extend (default)", ("workloads", "extend", "ms_per_step"), 1.0, "ms"),
-    ("  fused kernel", ("workloads", "extend", "fused_kernel_ms"), 1.0, "ms"),
-    ("  binning (3 launches)", ("workloads", "extend", "sort_kernels_ms"), 1.0, "ms"),
-    ("extend (split)", ("workloads", "extend_split", "ms_per_step"), 1.0, "ms"),
-    ("  nn_grid", ("workloads", "extend_split", "nn_kernel_ms"), 1.0, "ms"),
-    ("  collide grid", ("workloads", "extend_split", "collide_kernel_ms"), 1.0, "ms"),
+    ("  nn_grid", ("workloads", "extend", "nn_kernel_ms"), 1.0, "ms"),
+    ("  collide grid", ("workloads", "extend", "collide_kernel_ms"), 1.0, "ms"),
+    ("extend (PP_COLLIDE_FUSED)", ("workloads", "extend_fused", "ms_per_step"), 1.0, "ms"),
+    ("  fused kernel", ("workloads", "extend_fused", "fused_kernel_ms"), 1.0, "ms"),
+    ("  binning (3 launches)", ("workloads", "extend_fused", "sort_kernels_ms"), 1.0, "ms"),
     ("extend_scan", ("workloads", "extend_scan", "ms_per_step"), 1.0, "ms"),
     ("extend_dubins", ("workloads", "extend_dubins", "ms_per_step"), 1.0, "ms"),
     ("c5 slice", ("workloads", "dubins_rrt", "ms_per_step"), 1.0, "ms"),
