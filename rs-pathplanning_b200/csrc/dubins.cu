@@ -469,18 +469,14 @@ __global__ void __launch_bounds__(PP_FILL_THREADS)
 #endif
 }
 #else
-#ifndef PP_FILL_SPL
-#define PP_FILL_SPL 2  // samples per lane and warp iteration: 2 = rows of 64 samples (1 536 B), two independent
-                       // interpolations in flight per lane; 1 = the round-1 kernel (rows of 32)
-#endif
-#ifndef PP_FILL_MIN_BLOCKS
-#define PP_FILL_MIN_BLOCKS 6
-#endif
-#define PP_FILL_CHUNK (32 * PP_FILL_SPL)
-__global__ void __launch_bounds__(PP_FILL_THREADS, PP_FILL_MIN_BLOCKS)
+// Variants measured on 5.1e7 samples (2^16 C5 paths) and NOT adopted (round 2, profiles/r02_summary.md): rows leaving
+// through the TMA engine (cp.async.bulk shared -> global, two rows per warp; PP_FILL_TMA=1 above) 0.378 ms; rows of
+// 64 samples with two interpolations in flight per lane 0.366 ms; this kernel under __launch_bounds__(128, 6) 0.418 ms;
+// this kernel as it stands 0.280 ms = 4.4 TB/s (a pure store stream, torch fill_, reaches 7.26 TB/s on the same box).
+__global__ void __launch_bounds__(PP_FILL_THREADS)
     pp_dubins_fill_kernel(size_t n, const pp_dubins_plan *__restrict__ plans, const uint64_t *__restrict__ offsets,
                           double *__restrict__ out) {
-    __shared__ __align__(16) double fill_stage[PP_FILL_THREADS / 32][3 * PP_FILL_CHUNK];
+    __shared__ __align__(16) double fill_stage[PP_FILL_THREADS / 32][96];
     const int lane = threadIdx.x & 31;
     double *stage = fill_stage[threadIdx.x >> 5];
     const size_t warps_total = (size_t)gridDim.x * (PP_FILL_THREADS / 32);
@@ -505,40 +501,36 @@ __global__ void __launch_bounds__(PP_FILL_THREADS, PP_FILL_MIN_BLOCKS)
             const double len = pl.len[seg], pd0 = pl.pd0[seg];
             const double d = (len > 0.0) ? pl.step : -pl.step;
             const uint32_t ns = pl.n[seg];
-            for (uint32_t j0 = 0; j0 < ns; j0 += PP_FILL_CHUNK) {
+            for (uint32_t j0 = 0; j0 < ns; j0 += 32) {
                 const uint32_t k0 = base + j0;
                 if (k0 >= pl.count) break;  // the trim rule may cut the tail (Q6/Q7); warp-uniform
-                const uint32_t cnt = min(min((uint32_t)PP_FILL_CHUNK, ns - j0), pl.count - k0);
-#pragma unroll
-                for (int u = 0; u < PP_FILL_SPL; ++u) {
-                    const uint32_t s_ = (uint32_t)lane + 32u * u;
-                    if (s_ < cnt) {
-                        double x, y, yaw;
-                        pp_interpolate(mode, pd0 + (double)(j0 + s_) * d, ox, oy, oyaw, so, co, pl.rinv, &x, &y, &yaw);
-                        if (!pl.from_origin) {  // src/dubins.rs:412-422
-                            const double xw = (cs * x + (-ss) * y) + pl.sx;
-                            const double yw = (ss * x + cs * y) + pl.sy;
-                            x = xw;
-                            y = yw;
-                            yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
-                        }
-                        stage[3 * s_ + 0] = x;  // stride of 3 doubles: conflict-free
-                        stage[3 * s_ + 1] = y;
-                        stage[3 * s_ + 2] = yaw;
+                const uint32_t cnt = min(min(32u, ns - j0), pl.count - k0);
+                if ((uint32_t)lane < cnt) {
+                    double x, y, yaw;
+                    pp_interpolate(mode, pd0 + (double)(j0 + lane) * d, ox, oy, oyaw, so, co, pl.rinv, &x, &y, &yaw);
+                    if (!pl.from_origin) {  // src/dubins.rs:412-422
+                        const double xw = (cs * x + (-ss) * y) + pl.sx;
+                        const double yw = (ss * x + cs * y) + pl.sy;
+                        x = xw;
+                        y = yw;
+                        yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
                     }
+                    stage[3 * lane + 0] = x;  // stride of 3 doubles: conflict-free
+                    stage[3 * lane + 1] = y;
+                    stage[3 * lane + 2] = yaw;
                 }
                 __syncwarp();
                 // Per-lane (x,y,yaw) stores would touch 24 sectors per warp instruction (ncu: 3x the ideal
                 // sector count, L1 79 % busy, lg_throttle the top stall).  The 3*cnt doubles of this step are
                 // contiguous in `out`: one scalar store to reach 16-byte alignment if needed, then 16-byte
-                // vector stores straight from the staging row (a full step = 768 B per 32 samples).
+                // vector stores straight from the staging row (a full step = 768 B = 48 vectors).
                 double *d0 = dst + 3 * (size_t)k0;
                 const uint32_t D = 3 * cnt;
                 const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(d0) >> 3) & 1u);
                 const uint32_t nvec = (D - head) >> 1;
                 if (lane == 0 && head) d0[0] = stage[0];
 #pragma unroll
-                for (uint32_t v = lane; v < 48 * PP_FILL_SPL + 16; v += 32) {
+                for (uint32_t v = lane; v < 64; v += 32) {
                     if (v < nvec) {
                         const uint32_t e = head + 2 * v;
                         *reinterpret_cast<double2 *>(d0 + e) = make_double2(stage[e], stage[e + 1]);

@@ -55,3 +55,11 @@ def test_example_rrt_on_reference_world_format(ctx, tmp_path):
     assert int(re.search(r"tree nodes: (\d+)", out).group(1)) > 50
     if "Path generated!" in out:
         assert "verify(path) = 1" in out
+
+
+def test_example_group_drives_every_device_from_one_process(ctx):
+    """a compiled host using pp_group: replication by broadcast (upload + 512-node append), sliced extend steps,
+    byte-identical to one context for 1, 2, 4 ... devices (1 on a single-GPU box)"""
+    out = subprocess.run([_bin("example_group"), str(1 << 16)], capture_output=True, text=True, check=True).stdout
+    assert "group ok" in out and "DIFFERS" not in out
+    assert "group of 1 device(s): extend byte-identical, extend_dubins byte-identical" in out
