@@ -1,8 +1,7 @@
 #!/bin/bash
 # ncu evidence for one round (run under gpurun, 1 GPU).  Usage: bash profiles/capture.sh r02 [all]
 # Every ncu run is preceded by the same command line without ncu (B200_PROFILING.md).  The reports are exported to
-# CSV on the box (raw page + CUDA/SASS source page) and the .ncu-rep files are deleted when large: gpurun copies back
-# at most 64 MiB.
+# CSV on the box (raw page + CUDA/SASS source page) and large .ncu-rep files are deleted: gpurun copies back <= 64 MiB.
 set -u
 R=${1:-r02}
 mkdir -p gpurun_out
@@ -16,27 +15,25 @@ $CMD2 > gpurun_out/${R}_plain2.json 2> gpurun_out/${R}_plain2.err &&
 ncu --set full --clock-control none --import-source on -k regex:pp_dubins_eval_kernel -s 3 -c 1 \
     -o gpurun_out/${R}_dubins_eval $CMD2 > gpurun_out/${R}_dubins_eval_run.log 2>&1
 echo "dubins_eval capture rc=$?"
+cap() {  # name, kernel regex, launch-skip, launch-count
+  ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/${R}_$1 $CMD \
+      > gpurun_out/${R}_$1_run.log 2>&1
+  echo "$1 capture rc=$?"
+  ncu -i gpurun_out/${R}_$1.ncu-rep --page raw --csv > gpurun_out/${R}_$1_raw.csv 2>/dev/null
+  ncu -i gpurun_out/${R}_$1.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${R}_$1_source.csv 2>/dev/null
+}
 if [ "${2:-}" = "all" ]; then
-  $CMD > /dev/null 2>&1 &&
-  ncu --set full --clock-control none --import-source on \
-      -k regex:"pp_rrt_extend_fused_kernel|pp_extend_bin_kernel|pp_extend_scatter_kernel|pp_verify_polylines_kernel|pp_dubins_fill_kernel" \
-      -c 16 -o gpurun_out/${R}_rrt $CMD > gpurun_out/${R}_rrt_run.log 2>&1
-  echo "rrt capture rc=$?"
+  $CMD > /dev/null 2>&1
+  # the extend step: default pair of launches (first instances), then the binned fused kernel and its binning
+  cap extend "pp_nn_grid_kernel|pp_collide_segments_grid_kernel|pp_rrt_extend_fused_kernel|pp_extend_bin_kernel|pp_extend_scan_kernel|pp_extend_scatter_kernel" 0 8
+  # verify kernel: instances in bench order are strong-C5 x3, extend_dubins x2, C5 slice x2, C5 no-hit x2
+  cap verify_c5 "pp_verify_polylines_kernel" 5 1
+  cap verify_nohit "pp_verify_polylines_kernel" 7 1
+  cap verify_extend "pp_verify_polylines_kernel" 3 1
+  cap fill "pp_dubins_fill_kernel|pp_dubins_plan_kernel" 0 2
 fi
-for f in gpurun_out/${R}_dubins_eval.ncu-rep gpurun_out/${R}_rrt.ncu-rep; do
-  [ -f "$f" ] || continue
-  ncu -i "$f" --page raw --csv > "${f%.ncu-rep}_raw.csv" 2>/dev/null
-done
-[ -f gpurun_out/${R}_dubins_eval.ncu-rep ] && ncu -i gpurun_out/${R}_dubins_eval.ncu-rep --page source --csv \
-    --print-source cuda,sass > gpurun_out/${R}_dubins_eval_source.csv 2>/dev/null
-if [ -f gpurun_out/${R}_rrt.ncu-rep ]; then
-  for k in pp_rrt_extend_fused_kernel pp_verify_polylines_kernel pp_dubins_fill_kernel; do
-    ncu -i gpurun_out/${R}_rrt.ncu-rep --page source --csv --print-source cuda,sass -k regex:$k -c 1 \
-        > gpurun_out/${R}_${k}_source.csv 2>/dev/null
-  done
-  # the no-hit C5 launch of the verify kernel is the last of its six instances
-  ncu -i gpurun_out/${R}_rrt.ncu-rep --page source --csv --print-source cuda,sass -k regex:pp_verify_polylines_kernel -s 5 -c 1 \
-      > gpurun_out/${R}_pp_verify_polylines_kernel_nohit_source.csv 2>/dev/null
-fi
-find gpurun_out -name "*.ncu-rep" -size +20M -delete
-du -sh gpurun_out; ls -la gpurun_out | tail -20
+ncu -i gpurun_out/${R}_dubins_eval.ncu-rep --page raw --csv > gpurun_out/${R}_dubins_eval_raw.csv 2>/dev/null
+ncu -i gpurun_out/${R}_dubins_eval.ncu-rep --page source --csv --print-source cuda,sass \
+    > gpurun_out/${R}_dubins_eval_source.csv 2>/dev/null
+find gpurun_out -name "*.ncu-rep" -size +8M -delete
+du -sh gpurun_out; ls -la gpurun_out | tail -30
