@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
 N_PAIRS = 1 << 24          # C3, per GPU
-PASSES_PER_STEP = 64       # a step = 64 passes of the kernel over the 2^24-pair batch (inputs 768 MiB > L2, so a
-                           # pass never finds its data in cache): K steps then last >= 0.4 s and the clock samples,
+PASSES_PER_STEP = 128      # a step = 128 passes of the kernel over the 2^24-pair batch (inputs 768 MiB > L2, so a
+                           # pass never finds its data in cache): K = 10 steps then last 0.8 s and the clock samples,
                            # the throttle flags and the driver's own clock around the run describe the timed region
 W_INSTR_PER_PAIR = 1100.0  # fixed yard-stick of SURVEY.md Appendix D (FP64-pipe thread-instructions per pair)
 BYTES_PER_PAIR = 57.0      # 48 B read + 8 B cost + 1 B word
@@ -394,7 +394,7 @@ def run_own(args):
             "step": {"passes_per_step": PASSES_PER_STEP, "pairs_per_step": n * PASSES_PER_STEP, "word_hist_rank0": hist,
                      "timed_region_s": ms * 1e-3,
                      "why": "one pass over the 2^24-pair batch lasts 0.6 ms; a step repeats it so that the timed region is "
-                            ">= 0.4 s (inputs exceed L2: no pass finds its data cached)"},
+                            ">= 0.5 s (inputs exceed L2: no pass finds its data cached)"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 9 * n,
                     "steps": e2e_steps, "matches_device_run": same,
                     "how": "pp_dubins_eval on pinned host buffers (pp_host_alloc): 16 chunks over 3 streams, copies inside "

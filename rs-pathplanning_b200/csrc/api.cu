@@ -180,6 +180,7 @@ void pp_world_free(pp_world_dev &w) {
     cudaFree(w.circ);
     cudaFree(w.cell_start);
     cudaFree(w.cell_items);
+    cudaFree(w.cell_box);
     w = pp_world_dev();
 }
 
@@ -920,6 +921,12 @@ int pp_obstacles_upload(pp_ctx *ctx, const double *bounds_x, const double *bound
     if ((rc = pp_upload_vec(ctx, &w.circ, circ))) return rc;
     if ((rc = pp_upload_vec(ctx, &w.cell_start, cstart))) return rc;
     if ((rc = pp_upload_vec(ctx, &w.cell_items, citems))) return rc;
+    {
+        // the ring boxes once more, in cell order: the walk reads box k and item k side by side instead of item -> box
+        std::vector<float4> cbox(citems.size());
+        for (size_t k = 0; k < cstart.back(); ++k) cbox[k] = aabb32[citems[k]];
+        if ((rc = pp_upload_vec(ctx, &w.cell_box, cbox))) return rc;
+    }
     w.nb = nb;
     w.bgx = bgx;
     w.bgy = bgy;
@@ -962,6 +969,7 @@ pp_world_view pp_make_world_view(const pp_world_dev &w) {
     v.n_aabb_tiles = w.n_aabb_tiles;
     v.cell_start = w.cell_start;
     v.cell_items = w.cell_items;
+    v.cell_box = w.cell_box;
     v.gx = w.gx;
     v.gy = w.gy;
     v.gminx = w.gminx;

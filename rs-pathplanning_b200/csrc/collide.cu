@@ -332,10 +332,11 @@ __device__ __forceinline__ bool pp_verify_segment_grid(const pp_world_view &w, b
             uint32_t ring = 0xFFFFFFFFu;
             while (more) {
                 if (kcur < kend) {
-                    const uint32_t r = linear ? kcur : __ldg(w.cell_items + kcur);
-                    ++kcur;
-                    const float4 bb = __ldg(w.aabb32 + r);
+                    // box k of the cell-ordered copy: no dependent load through the ring id
+                    const float4 bb = __ldg((linear ? w.aabb32 : w.cell_box) + kcur);
+                    const uint32_t kk = kcur++;
                     if (!(q32x1 < bb.x || q32x0 > bb.z || q32y1 < bb.y || q32y0 > bb.w)) {
+                        const uint32_t r = linear ? kk : __ldg(w.cell_items + kk);
                         // circle filter: most box candidates are decided here, per lane, without the warp-wide
                         // exact predicates (edge outside the ring's outer circle, or both ends inside its inner one)
                         const int cls = pp_ring_circle_class(w, r, x0, y0, x1, y1);
@@ -552,7 +553,9 @@ __global__ void __launch_bounds__(PP_SEG_THREADS, PP_EXTEND_MIN_BLOCKS)
         j = perm ? __ldg(perm + t) : t;
         x0 = qx[j];
         y0 = qy[j];
-        pp_nn_grid_search(g, x0, y0, best, bi, x1, y1);  // RRT::get_nearest_node, src/rrt.rs:378-391
+    }
+    pp_nn_grid_search(g, live, x0, y0, best, bi, x1, y1);  // RRT::get_nearest_node, src/rrt.rs:378-391 (whole warp)
+    if (live) {
         idx_out[j] = bi;
         const bool none = bi == 0xFFFFFFFFu;  // no nearest node: get_random_node's None -> ok = 0, yaw = NaN
         if (none) x1 = y1 = CUDART_NAN;
@@ -872,10 +875,10 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 uint32_t ring = 0xFFFFFFFFu;
                 while (more) {
                     if (kcur < kend) {
-                        const uint32_t r = linear ? kcur : __ldg(w.cell_items + kcur);
-                        ++kcur;
-                        const float4 bb = __ldg(w.aabb32 + r);
+                        const float4 bb = __ldg((linear ? w.aabb32 : w.cell_box) + kcur);  // cell-ordered boxes
+                        const uint32_t kk = kcur++;
                         if (!(q32x1 < bb.x || q32x0 > bb.z || q32y1 < bb.y || q32y0 > bb.w)) {
+                            const uint32_t r = linear ? kk : __ldg(w.cell_items + kk);
                             // circle filter on this lane's segment (its vertex alone for the last point)
                             const int cls = pp_ring_circle_class(w, r, x, y, xe, ye);
                             if (cls == 1) {  // both ends inside the ring's inner circle: the polyline is blocked

@@ -229,7 +229,7 @@ int pp_obstacles_upload_bcast(pp_ctx *ctx, int root, const double *bounds_x, con
             (rc = alloc_dev(ctx, &w.oy, h.n_pts)) || (rc = alloc_dev(ctx, &w.meta, h.n_rings)) ||
             (rc = alloc_dev(ctx, &w.aabb32, n_aabb)) || (rc = alloc_dev(ctx, &w.circ, h.n_rings)) ||
             (rc = alloc_dev(ctx, &w.cell_start, n_cells)) ||
-            (rc = alloc_dev(ctx, &w.cell_items, h.n_cell_items)))
+            (rc = alloc_dev(ctx, &w.cell_items, h.n_cell_items)) || (rc = alloc_dev(ctx, &w.cell_box, h.n_cell_items)))
             return rc;
         w.nb = h.nb; w.n_pts = h.n_pts; w.n_rings = h.n_rings; w.n_aabb_tiles = h.n_aabb_tiles;
         w.n_cell_items = h.n_cell_items;
@@ -238,7 +238,8 @@ int pp_obstacles_upload_bcast(pp_ctx *ctx, int root, const double *bounds_x, con
         w.gminx = h.d[4]; w.gminy = h.d[5]; w.gcell = h.d[6]; w.ginv = h.d[7];
     }
     struct item { void *p; size_t bytes; };
-    const item items[10] = {{w.circ, (size_t)h.n_rings * sizeof(pp_ring_circle)},
+    const item items[11] = {{w.circ, (size_t)h.n_rings * sizeof(pp_ring_circle)},
+                           {w.cell_box, (size_t)h.n_cell_items * sizeof(float4)},
                            {w.bx, (size_t)h.nb * 8}, {w.by, (size_t)h.nb * 8}, {w.bcls, n_bcls},
                            {w.ox, (size_t)h.n_pts * 8}, {w.oy, (size_t)h.n_pts * 8},
                            {w.meta, (size_t)h.n_rings * sizeof(pp_ring_meta)}, {w.aabb32, n_aabb * sizeof(float4)},

@@ -246,12 +246,14 @@ __global__ void __launch_bounds__(128)
     pp_nn_grid_kernel(pp_nn_grid_view g, const double *__restrict__ qx, const double *__restrict__ qy, size_t m,
                       uint32_t *__restrict__ idx_out, double *__restrict__ d2_out) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
+    const bool live = j < m;  // no early return: the whole warp walks the tail together
     double best, bx, by;
     uint32_t bi;
-    pp_nn_grid_search(g, qx[j], qy[j], best, bi, bx, by);
-    idx_out[j] = bi;
-    if (d2_out) d2_out[j] = best;
+    pp_nn_grid_search(g, live, live ? qx[j] : 0.0, live ? qy[j] : 0.0, best, bi, bx, by);
+    if (live) {
+        idx_out[j] = bi;
+        if (d2_out) d2_out[j] = best;
+    }
 }
 
 
@@ -584,7 +586,7 @@ pp_nn_grid_view pp_nn_make_grid_view(const pp_tree_dev &t) {
 // nodes).  Rebuild when the tail exceeds PP_NN_TAIL_MAX nodes (bounds a scalar query's latency; amortised cost of
 // the rebuild: n / 4096 node visits per appended node) or when this call's m * tail pair evaluations outweigh a
 // rebuild.  Returns true when the grid must be rebuilt before it is searched.
-#define PP_NN_TAIL_MAX 4096
+#define PP_NN_TAIL_MAX 4096  // ~12 warp instructions per tail node and warp: <= 25 us per call
 bool pp_nn_grid_policy(const pp_tree_dev &t, size_t m) {
     if (t.grid_n == (size_t)-1 || t.grid_n > t.n || (t.grid_n == 0 && t.n != 0)) return true;
     const size_t tail = t.n - t.grid_n;

@@ -24,22 +24,36 @@ struct pp_nn_grid_view {
 // the 3 x 3 block are loaded before any of them is used, the coordinate loop runs one load ahead, and a candidate's
 // node id is NOT fetched inside the loop -- the winner is tracked by its position in the cell arrays and its id is
 // read once at the end; only an exact tie of two distances (rare) needs ids early.
-__device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, double x, double y, double &best_out,
+// ALL 32 lanes of the warp call together (the tail is fetched cooperatively); a lane without a query passes
+// live = false and gets bi_out = 0xFFFFFFFF.
+__device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, bool live, double x, double y, double &best_out,
                                                   uint32_t &bi_out, double &bx_out, double &by_out) {
     double best = CUDART_INF, bx = 0.0, by = 0.0;
     uint32_t bi = 0xFFFFFFFFu;  // id of the winner when known (src == 1)
     uint32_t bk = 0;            // position of the winner in the cell arrays (src == 2)
     int src = 0;                // 0: no node yet, 1: id known (tail node or resolved tie), 2: position known
-    for (uint32_t i = g.grid_n; i < g.n_nodes; ++i) {  // the tail, in index order, strict compare (as the scans)
-        const double nx = __ldg(g.node_x + i), ny = __ldg(g.node_y + i);
-        const double dx = nx - x, dy = ny - y;
-        const double v = dx * dx + dy * dy;
-        if (v < best) {
-            best = v;
-            bi = i;
-            bx = nx;
-            by = ny;
-            src = 1;
+    // the tail, in index order, strict compare (as the scans).  Every lane needs every tail node: the warp loads 32
+    // nodes at a time, one per lane, and hands them round by shuffle -- one load latency per 32 nodes instead of one
+    // per node (a per-thread loop over a 4 096-node tail spent ~1 ms waiting on L2, profiles/r02_append_latency.json)
+    {
+        const int lane = (int)(threadIdx.x & 31u);
+        for (uint32_t base = g.grid_n; base < g.n_nodes; base += 32u) {
+            const uint32_t mine = base + (uint32_t)lane;
+            const double tx = (mine < g.n_nodes) ? __ldg(g.node_x + mine) : CUDART_INF;
+            const double ty = (mine < g.n_nodes) ? __ldg(g.node_y + mine) : CUDART_INF;
+            const int cnt = (int)min(32u, g.n_nodes - base);
+            for (int k = 0; k < cnt; ++k) {
+                const double nx = __shfl_sync(0xffffffffu, tx, k), ny = __shfl_sync(0xffffffffu, ty, k);
+                const double dx = nx - x, dy = ny - y;
+                const double v = dx * dx + dy * dy;
+                if (v < best) {
+                    best = v;
+                    bi = base + (uint32_t)k;
+                    bx = nx;
+                    by = ny;
+                    src = 1;
+                }
+            }
         }
     }
     // candidates k0 <= k < k1 of the cell-sorted arrays: same d2 arithmetic as the scans, (d2, id) lexicographic minimum
@@ -71,7 +85,7 @@ __device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, doub
             }
         }
     };
-    if (g.grid_n > 0) {
+    if (live && g.grid_n > 0) {
         const int gx = g.gx, gy = g.gy;
         double fx = floor((x - g.gminx) * g.ginv), fy = floor((y - g.gminy) * g.ginv);
         int cx = (fx >= (double)gx) ? gx - 1 : ((fx > 0.0) ? (int)fx : 0);  // NaN -> 0
@@ -113,7 +127,7 @@ __device__ __forceinline__ void pp_nn_grid_search(const pp_nn_grid_view &g, doub
     }
     if (src == 2) bi = __ldg(g.cell_items + bk);
     best_out = best;
-    bi_out = (src == 0) ? 0xFFFFFFFFu : bi;
+    bi_out = (src == 0 || !live) ? 0xFFFFFFFFu : bi;
     bx_out = bx;
     by_out = by;
 }

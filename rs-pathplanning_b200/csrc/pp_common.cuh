@@ -62,6 +62,7 @@ struct pp_world_dev {
     int gx = 0, gy = 0;
     double gminx = 0, gminy = 0, gcell = 1, ginv = 1;
     uint32_t *cell_start = nullptr, *cell_items = nullptr;
+    float4 *cell_box = nullptr;  // aabb32[cell_items[k]] at position k: the walk tests a box without knowing the ring id
     uint32_t n_cell_items = 0;
 };
 
@@ -146,6 +147,7 @@ struct pp_world_view {
     const struct pp_ring_circle *circ;
     uint32_t n_aabb_tiles;
     const uint32_t *cell_start, *cell_items;
+    const float4 *cell_box;
     int gx, gy;
     double gminx, gminy, ginv;
 };

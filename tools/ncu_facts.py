@@ -79,16 +79,17 @@ def facts_from_csv(path, units=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("csvs", nargs="+", help="raw csv[:units_per_launch]")
+    ap.add_argument("csvs", nargs="+", help="raw csv[:units_per_launch[:key suffix]]")
     ap.add_argument("-o", "--out", default="profiles/kernel_facts.json")
     a = ap.parse_args()
     facts = {}
     if os.path.exists(a.out):
         facts = json.load(open(a.out))
     for spec in a.csvs:
-        path, _, units = spec.partition(":")
+        path, _, rest = spec.partition(":")
+        units, _, suffix = rest.partition(":")
         for f in facts_from_csv(path, float(eval(units)) if units else None):  # noqa: S307 (own command line)
-            key = f["kernel"]
+            key = f["kernel"] + (f" [{suffix}]" if suffix else "")
             if key in facts and facts[key].get("source") != f["source"]:
                 pass  # newer capture replaces the older one
             facts[key] = f
