@@ -727,7 +727,8 @@ struct pp_points_dubins {
 
 #define PP_POLY_THREADS 128
 #ifndef PP_POLY_MIN_BLOCKS
-#define PP_POLY_MIN_BLOCKS 7  // 72 registers; C5 slice / Dubins extend / no-hit: 2.17 / 2.09 / 3.35 ms (64 registers: 2.16 / 2.12 / 3.56; 80: 2.32 / 2.23 / 3.39)
+#define PP_POLY_MIN_BLOCKS 7  // 72 registers; round 2 (circle filter, cell-ordered boxes): C5 slice / Dubins extend / no-hit 1.56 / 1.98 / 3.35 ms
+                              // (5 blocks, 96 registers: 1.79 / 2.19 / 3.42; 8 blocks, 64 registers: 2.41 / 3.21 / 3.37)
 #endif
 
 template <bool CULL, bool DUBINS>
