@@ -82,8 +82,13 @@ __global__ void __launch_bounds__(PP_EVAL_THREADS, PP_EVAL_MIN_BLOCKS)
                  b5 = __ldg(eyaw + j1);
     const double c0 = HAS_RADIUS_ARR ? 1.0 / __ldg(radius_arr + i0) : inv_radius;
     const double c1 = HAS_RADIUS_ARR ? 1.0 / __ldg(radius_arr + j1) : inv_radius;
+#if PP_EVAL_PAIRS == 3  // the same, with the evaluation inlined twice instead of called (code size x2, no call ABI)
+    pp_eval_one<WANT_TPQ>(a0, a1, a2, a3, a4, a5, c0, i0, cost, word, tpq);
+    if (two) pp_eval_one<WANT_TPQ>(b0, b1, b2, b3, b4, b5, c1, i1, cost, word, tpq);
+#else
     pp_eval_one_call<WANT_TPQ>(a0, a1, a2, a3, a4, a5, c0, i0, cost, word, tpq);
     if (two) pp_eval_one_call<WANT_TPQ>(b0, b1, b2, b3, b4, b5, c1, i1, cost, word, tpq);
+#endif
 }
 
 int pp_launch_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
@@ -92,7 +97,7 @@ int pp_launch_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double 
     if (n == 0) return PP_OK;
     pp_launch_scope scope(ctx, "dubins_eval");
     const double inv_radius = 1.0 / radius;
-#if PP_EVAL_PAIRS == 2
+#if PP_EVAL_PAIRS >= 2
     const unsigned grid = (unsigned)((n + 2 * PP_EVAL_THREADS - 1) / (2 * PP_EVAL_THREADS));
 #define PP_GO(RA, TPQ)                                                                                           \
     pp_dubins_eval2_kernel<RA, TPQ><<<grid, PP_EVAL_THREADS, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius_arr, \
