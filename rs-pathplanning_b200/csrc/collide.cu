@@ -51,16 +51,19 @@ __device__ __forceinline__ bool pp_outside_padded(const pp_ring_meta &m, double 
 }
 
 // circle filter of ring r for the segment a-b (geo_predicates.cuh: pp_circle_class): 0 skip the ring, 1 blocked, 2 exact
-__device__ __forceinline__ int pp_ring_circle_class(const pp_world_view &w, uint32_t r, double ax, double ay, double bx,
-                                                    double by) {
-    const double2 lo = __ldg(reinterpret_cast<const double2 *>(w.circ + r));
-    const double2 hi = __ldg(reinterpret_cast<const double2 *>(w.circ + r) + 1);
+__device__ __forceinline__ int pp_circle_class_at(const pp_ring_circle *cp, double ax, double ay, double bx, double by) {
+    const double2 lo = __ldg(reinterpret_cast<const double2 *>(cp));
+    const double2 hi = __ldg(reinterpret_cast<const double2 *>(cp) + 1);
     pp_ring_circle c;
     c.cx = lo.x;
     c.cy = lo.y;
     c.rout2 = hi.x;
     c.rin2 = hi.y;
     return pp_circle_class(c, ax, ay, bx, by);
+}
+__device__ __forceinline__ int pp_ring_circle_class(const pp_world_view &w, uint32_t r, double ax, double ay, double bx,
+                                                    double by) {
+    return pp_circle_class_at(w.circ + r, ax, ay, bx, by);
 }
 
 // ---- warp-cooperative narrow phase.  The warp is split into four groups of eight lanes; a group works on one
@@ -292,6 +295,9 @@ __global__ void __launch_bounds__(PP_SEG_THREADS)
 #ifndef PP_SEGGRID_MIN_BLOCKS
 #define PP_SEGGRID_MIN_BLOCKS 6  // 80 registers: 0.186 ms per 2^20 C4 edges (0.211 at 90 registers, 0.189 at 64)
 #endif
+#ifndef PP_SEG_FOLD_COUNT
+#define PP_SEG_FOLD_COUNT 1
+#endif
 // Space::verify of one straight edge per lane through the obstacle grid; ALL 32 lanes of the warp call together
 // (ballots and shuffles inside), lanes without an edge pass live = false
 __device__ __forceinline__ bool pp_verify_segment_grid(const pp_world_view &w, bool live, double x0, double y0, double x1,
@@ -316,12 +322,21 @@ __device__ __forceinline__ bool pp_verify_segment_grid(const pp_world_view &w, b
             kend = w.n_rings;
             cy = cy1 + 1;
         } else {
+#if PP_SEG_FOLD_COUNT
+            // first row's run fetched here and handed to the walk: an empty single-row range ends the lane's work
+            const uint32_t *row = w.cell_start + (size_t)cy * w.gx;
+            kcur = __ldg(row + cx0);
+            kend = __ldg(row + cx1 + 1);
+            ++cy;
+            if (kcur == kend && cy > cy1) more = false;
+#else
             uint32_t cnt = 0;
             for (int r = cy; r <= cy1; ++r) {
                 const uint32_t *row = w.cell_start + (size_t)r * w.gx;
                 cnt += __ldg(row + cx1 + 1) - __ldg(row + cx0);
             }
             more = cnt != 0u;
+#endif
         }
     }
     if (__ballot_sync(0xffffffffu, more) != 0u) {
@@ -338,7 +353,9 @@ __device__ __forceinline__ bool pp_verify_segment_grid(const pp_world_view &w, b
                     if (!(q32x1 < bb.x || q32x0 > bb.z || q32y1 < bb.y || q32y0 > bb.w)) {
                         const uint32_t r = linear ? kk : __ldg(w.cell_items + kk);
                         // circle filter: most box candidates are decided here, per lane, without the warp-wide
-                        // exact predicates (edge outside the ring's outer circle, or both ends inside its inner one)
+                        // exact predicates (edge outside the ring's outer circle, or both ends inside its inner one).
+                        // (A cell-ordered copy of the circles, like the boxes', was measured and dropped: the polyline
+                        // kernel ran 40 % slower -- neighbouring cells share rings, and the per-ring array hits in L1.)
                         const int cls = pp_ring_circle_class(w, r, x0, y0, x1, y1);
                         if (cls == 1) {
                             hit = true;
@@ -844,6 +861,36 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             cx1 = min(cx1, w.gx - 1);
             cy = max(cy, 0);
             cy1 = min(cy1, w.gy - 1);
+            uint32_t kcur = 0, kend = 0;
+            bool linear = false;
+#ifndef PP_POLY_FOLD_COUNT
+#define PP_POLY_FOLD_COUNT 1
+#endif
+#if PP_POLY_FOLD_COUNT
+            // user-supplied polylines may hold segments whose box covers more cells than there are rings: walk
+            // the ring list instead (bounds the cost per segment by O(rings)); Dubins samples are a step apart
+            if (!DUBINS && more &&
+                (unsigned long long)(cx1 - cx0 + 1) * (unsigned long long)(cy1 - cy + 1) > (unsigned long long)w.n_rings + 64ull) {
+                linear = true;
+                kend = w.n_rings;
+                cy = cy1 + 1;
+            } else if (more) {
+                // The first row's run is fetched here and handed to the walk (a sample segment nearly always lies in ONE
+                // row of cells): an empty single-row run ends the lane's work after two loads, exactly as the separate
+                // "rings registered under the box" count did, without loading the same offsets twice.
+                const uint32_t *row = w.cell_start + (size_t)cy * w.gx;
+                kcur = __ldg(row + cx0);
+                kend = __ldg(row + cx1 + 1);
+                ++cy;
+                if (kcur == kend && cy > cy1) more = false;
+            }
+            if (__ballot_sync(0xffffffffu, more) == 0u) continue;
+            // some lane has rings to look at: its box, rounded outward to fp32, for the per-ring overlap test
+            const double xe = own_segment ? xn : x, ye = own_segment ? yn : y;
+            const bool swx = xe < x, swy = ye < y;
+            const float q32x0 = __double2float_rd(swx ? xe : x), q32x1 = __double2float_ru(swx ? x : xe);
+            const float q32y0 = __double2float_rd(swy ? ye : y), q32y1 = __double2float_ru(swy ? y : ye);
+#else
             if (more) {
                 // rings registered under the box's cells, row by row (a row's cells are contiguous in the CSR
                 // array): in free space the sum is zero for every lane and the chunk is done after one vote
@@ -860,16 +907,15 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             const bool swx = xe < x, swy = ye < y;
             const float q32x0 = __double2float_rd(swx ? xe : x), q32x1 = __double2float_ru(swx ? x : xe);
             const float q32y0 = __double2float_rd(swy ? ye : y), q32y1 = __double2float_ru(swy ? y : ye);
-            uint32_t kcur = 0, kend = 0;
             // user-supplied polylines may hold segments whose box covers more cells than there are rings: walk
             // the ring list instead (bounds the cost per segment by O(rings)); Dubins samples are a step apart
-            bool linear = false;
             if (!DUBINS && more &&
                 (unsigned long long)(cx1 - cx0 + 1) * (unsigned long long)(cy1 - cy + 1) > (unsigned long long)w.n_rings + 64ull) {
                 linear = true;
                 kend = w.n_rings;
                 cy = cy1 + 1;
             }
+#endif
             // the ids of a ROW of cells are one contiguous run of cell_items: the walk goes row by row
             bool inner = false;
             for (;;) {

@@ -50,7 +50,7 @@ def test_extern_block_matches_the_header():
 
 def test_every_ffi_call_in_the_shim_is_declared():
     externs = rust_externs()
-    for f in ("dubins.rs", "rrt.rs"):
+    for f in ("dubins.rs", "rrt.rs", "group.rs"):
         src = open(os.path.join(RUST, f)).read()
         for name in set(re.findall(r"ffi::(pp_[a-z0-9_]+)\s*\(", src)):
             assert name in externs, f"{f} calls ffi::{name}, which ffi.rs does not declare"
