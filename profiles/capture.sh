@@ -30,7 +30,8 @@ if [ "${2:-}" = "all" ]; then
   cap verify_c5 "pp_verify_polylines_kernel" 5 1
   cap verify_nohit "pp_verify_polylines_kernel" 7 1
   cap verify_extend "pp_verify_polylines_kernel" 3 1
-  cap fill "pp_dubins_fill_kernel|pp_dubins_plan_kernel" 0 2
+  cap fill "pp_dubins_fill_kernel" 0 1
+  cap plan "pp_dubins_plan_kernel" 5 1
 fi
 ncu -i gpurun_out/${R}_dubins_eval.ncu-rep --page raw --csv > gpurun_out/${R}_dubins_eval_raw.csv 2>/dev/null
 ncu -i gpurun_out/${R}_dubins_eval.ncu-rep --page source --csv --print-source cuda,sass \
