@@ -100,6 +100,8 @@ def lib():
     L.ppo_verify.argtypes = [wp, _dp, _dp, sz]
     L.ppo_verify_culled.restype = C.c_int
     L.ppo_verify_culled.argtypes = [wp, _dp, _dp, sz]
+    L.ppo_circle_class.restype = C.c_int
+    L.ppo_circle_class.argtypes = [_dp, _dp, sz, d, d, d, d]
     L.ppo_verify_segments.restype = None
     L.ppo_verify_segments.argtypes = [wp, sz, _dp, _dp, _dp, _dp, _u8p, C.c_int, C.c_int]
     L.ppo_dubins_edge_polyline.restype = C.c_long
@@ -387,6 +389,12 @@ def check_finish(world, nx, ny, nyaw, parent, node, goal, goal_yaw, radius, step
         n, c = ln.value, cn.value
         return Finish((lx[:n].copy(), ly[:n].copy()), r >= 0, np.stack([cx[:c], cy[:c], cyaw[:c]], 1),
                       int(fl.value), int(lfl.value), int(nv.value))
+
+
+def circle_class(rx, ry, ax, ay, bx, by):
+    """class of segment a-b against one (closed) ring under the circle filter of the culled loop: 0 skip, 1 blocked, 2 exact"""
+    rx, ry = _f64(rx), _f64(ry)
+    return int(lib().ppo_circle_class(_p(rx), _p(ry), rx.size, ax, ay, bx, by))
 
 
 def ring_has_point(rx, ry, px, py):

@@ -776,6 +776,13 @@ static int circle_class(const circle_t *c, double ax, double ay, double bx, doub
     return (a2 * f - e * e > c->rout2 * f) ? 0 : 2;
 }
 
+/* harness entry: the class the culled loop assigns to segment a-b against one ring (0 skip, 1 blocked, 2 exact) */
+int ppo_circle_class(const double *rx, const double *ry, size_t n, double ax, double ay, double bx, double by) {
+    aabb_t b = ring_aabb(rx, ry, n);
+    circle_t c = ring_circle(rx, ry, n, &b, n ? aabb_pad(&b) : 0.0);
+    return circle_class(&c, ax, ay, bx, by);
+}
+
 int ppo_verify_culled(const ppo_world *w, const double *lx, const double *ly, size_t n) {
     for (size_t k = 0; k < n; ++k)
         if (!poly_contains_point(w->bx, w->by, w->nb, lx[k], ly[k])) return 0;

@@ -126,6 +126,10 @@ int ppo_verify(const ppo_world *w, const double *lx, const double *ly, size_t n)
 /* same, with the exactness-preserving AABB culls of SURVEY B.1 (must agree with ppo_verify) */
 int ppo_verify_culled(const ppo_world *w, const double *lx, const double *ly, size_t n);
 
+/* HARNESS: the circle-filter class of segment a-b against one ring in the culled loop: 0 = the ring is skipped,
+ * 1 = blocked (both end points inside the ring's inner circle), 2 = the exact predicates decide */
+int ppo_circle_class(const double *rx, const double *ry, size_t n, double ax, double ay, double bx, double by);
+
 /* straight 2-point edges a->b, batch */
 void ppo_verify_segments(const ppo_world *w, size_t m, const double *ax, const double *ay, const double *bx,
                          const double *by, uint8_t *ok, int culled, int nthreads);

@@ -124,3 +124,64 @@ def test_verify_matches_exact_geometry(O):
             free += ok
             blocked += not ok
     assert free > 100 and blocked > 100
+
+
+def test_circle_filter_classes_are_exact_statements(O):
+    """the second cull of the culled loop (circle filter): class 0 must mean that the closed segment
+    and the closed polygon have NO point in common, class 1 that both end points lie strictly inside the polygon --
+    checked in exact rational arithmetic on random star-shaped (concave) rings and create_circle polygons, for segments
+    of all lengths including ones that graze the outer / inner circle"""
+    rng = np.random.default_rng(77)
+    seen = {0: 0, 1: 0, 2: 0}
+    for trial in range(60):
+        if trial % 2:
+            rx, ry = _star_ring(rng, rng.uniform(-50, 50), rng.uniform(-50, 50), int(rng.integers(3, 24)))
+        else:
+            rx, ry = O.create_circle(rng.uniform(-50, 50), rng.uniform(-50, 50), rng.uniform(0.6, 4.0))
+        cx, cy = 0.5 * (rx.min() + rx.max()), 0.5 * (ry.min() + ry.max())
+        rout = np.hypot(rx - cx, ry - cy).max()
+        for _ in range(120):
+            kind = rng.integers(0, 4)
+            if kind == 0:    # anywhere around
+                a = np.array([cx, cy]) + rng.uniform(-3 * rout, 3 * rout, 2)
+                b = a + rng.normal(0, rout, 2)
+            elif kind == 1:  # short, near the centre
+                a = np.array([cx, cy]) + rng.normal(0, 0.3 * rout, 2)
+                b = a + rng.normal(0, 0.1 * rout, 2)
+            elif kind == 2:  # tangent-ish to the outer circle
+                th = rng.uniform(0, 2 * np.pi)
+                rad = rout * (1.0 + rng.choice([1e-9, 1e-6, 1e-3, 0.05]) * rng.choice([-1, 1]))
+                mid = np.array([cx + rad * np.cos(th), cy + rad * np.sin(th)])
+                tang = np.array([-np.sin(th), np.cos(th)]) * rng.uniform(0.1, 3.0) * rout
+                a, b = mid - tang, mid + tang
+            else:            # a single vertex (a == b), as the last point of a polyline
+                a = np.array([cx, cy]) + rng.uniform(-1.5 * rout, 1.5 * rout, 2)
+                b = a.copy()
+            cls = O.circle_class(rx, ry, a[0], a[1], b[0], b[1])
+            seen[cls] += 1
+            if cls == 0:
+                # no contact: neither an intersection with a ring segment nor an end point inside
+                for i in range(len(rx) - 1):
+                    meet = _exact_segments_touch((a[0], a[1], b[0], b[1]), (rx[i], ry[i], rx[i + 1], ry[i + 1]))
+                    assert not meet, (trial, i)
+                assert _exact_inside(rx, ry, a[0], a[1]) is False and _exact_inside(rx, ry, b[0], b[1]) is False
+            elif cls == 1:
+                assert _exact_inside(rx, ry, a[0], a[1]) is True and _exact_inside(rx, ry, b[0], b[1]) is True
+    assert seen[0] > 500 and seen[1] > 200 and seen[2] > 500, seen
+
+
+def _exact_segments_touch(a, b):
+    """closed segments share at least one point (exact, degenerate cases included)"""
+    ax0, ay0, ax1, ay1 = map(F, a)
+    bx0, by0, bx1, by1 = map(F, b)
+
+    def on(px, py, qx, qy, rx_, ry_):
+        return min(px, qx) <= rx_ <= max(px, qx) and min(py, qy) <= ry_ <= max(py, qy)
+    o1, o2 = _orient(ax0, ay0, ax1, ay1, bx0, by0), _orient(ax0, ay0, ax1, ay1, bx1, by1)
+    o3, o4 = _orient(bx0, by0, bx1, by1, ax0, ay0), _orient(bx0, by0, bx1, by1, ax1, ay1)
+    if (ax0, ay0) == (ax1, ay1):  # a is a single point
+        return _orient(bx0, by0, bx1, by1, ax0, ay0) == 0 and on(bx0, by0, bx1, by1, ax0, ay0)
+    if o1 != o2 and o3 != o4:
+        return True
+    return ((o1 == 0 and on(ax0, ay0, ax1, ay1, bx0, by0)) or (o2 == 0 and on(ax0, ay0, ax1, ay1, bx1, by1)) or
+            (o3 == 0 and on(bx0, by0, bx1, by1, ax0, ay0)) or (o4 == 0 and on(bx0, by0, bx1, by1, ax1, ay1)))
