@@ -138,8 +138,8 @@ int pp_ctx_create(int device, pp_ctx **out) {
     ctx->own_stream_handle = ctx->stream;
     for (int i = 0; i < 3 && ok; ++i)
         ok = cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->tickets, 64 * sizeof(unsigned int)) == cudaSuccess;
-    ok = ok && cudaMemset(ctx->tickets, 0, 64 * sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->tickets, PP_TICKETS * sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->tickets, 0, PP_TICKETS * sizeof(unsigned int)) == cudaSuccess;
     if (ok) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

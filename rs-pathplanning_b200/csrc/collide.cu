@@ -742,6 +742,84 @@ struct pp_points_dubins {
     const double *ex, *ey;  // parent point appended after the samples
 };
 
+// ---- Dubins samples for the verify kernel: table-driven, in the world frame (dubins_device.cuh: pp_seg_world,
+// pp_arc_coef).  Sample j of a segment is split as j = 32 c + l; the chunk (segment, c) contributes four coefficients
+// (one sincos per chunk, computed by ONE lane when the warp takes up the path), l contributes (cos, sin)(l * step)
+// from a 32-entry table that only changes with the step, and the sample is two fused multiply-adds per coordinate:
+//     x = X0 + u Px + v Qx        (arc: (u, v) = (cos, sin)(l step);   straight: (u, v) = (1, l), X0 = 0)
+// The default form (pp_plan_sample_local + pp_local_to_world: one sincos and two rotations per sample) spends ~60 of
+// the ~200 warp instructions of a 32-sample chunk here.  Paths longer than 32 chunks slide a 32-entry window.
+#ifndef PP_POLY_TABLES
+#define PP_POLY_TABLES 0  // A/B switch, 1 = the table-driven form.  MEASURED AND NOT ADOPTED (profiles/r02_summary.md section 10):
+                          // extend_dubins 2.01 ms against 1.83, C5 slice 1.61 against 1.45, no-hit 3.50 against 3.40 -- the
+                          // per-sample sincos overlaps with the cell walk's load latency, the per-path table set-up does not
+#endif
+struct pp_poly_tables {
+    pp_arc_coef coef[32];  // window of chunk coefficients, entry index = first[seg] + c - w0
+    double2 uv[64];        // [l] = (cos, sin)(l * step); [32 + l] = (1, l)
+    double2 x0y0[3];       // per segment: (X0, Y0) of an arc, (0, 0) of a straight segment
+    pp_seg_world segw[3];
+    uint32_t first[4];     // first entry of each segment; first[3] = number of entries of the path
+    double step;           // step the uv table was made for (NaN before the first path)
+};
+
+// entry `idx` of the path's chunk table
+__device__ __forceinline__ pp_arc_coef pp_poly_entry(const pp_dubins_plan &pl, const pp_poly_tables &t, uint32_t idx) {
+    const int seg = (idx >= t.first[2]) ? 2 : ((idx >= t.first[1]) ? 1 : 0);
+    const uint32_t c = idx - t.first[seg];
+    const double d = (pl.len[seg] > 0.0) ? pl.step : -pl.step;
+    const double A = pl.pd0[seg] + (double)(32u * c) * d;
+    const pp_seg_world &sw = t.segw[seg];
+    pp_arc_coef k;
+    if (pp_word_mode(pl.word, seg) == PP_MODE_S) {
+        pp_line_sample(sw, A, &k.Px, &k.Py);
+        k.Qx = d * sw.Cr;
+        k.Qy = d * sw.Sr;
+    } else {
+        k = pp_arc_coef_make(sw, A);
+        if (!(d > 0.0)) {  // l counts steps of -step: sin(l d) = -sin(l step)
+            k.Qx = -k.Qx;
+            k.Qy = -k.Qy;
+        }
+    }
+    return k;
+}
+
+// the warp takes up a path: segment constants by lanes 0-2, the (cos, sin)(l step) table when the step changed, the
+// first 32 chunk entries one per lane.
+// (out of line on purpose: run once per path, and inlining its sincos twice into the kernel costs the chunk loop registers)
+static __device__ __noinline__ void pp_poly_window_fill(const pp_dubins_plan &pl, pp_poly_tables &t, uint32_t w0, int lane) {
+    __syncwarp();
+    if (w0 + (uint32_t)lane < t.first[3]) t.coef[lane] = pp_poly_entry(pl, t, w0 + (uint32_t)lane);
+    __syncwarp();
+}
+static __device__ __noinline__ void pp_poly_tables_init(const pp_dubins_plan &pl, const pp_plan_aux &aux, pp_poly_tables &t,
+                                                        int lane) {
+    if (lane < 3) {
+        const int mode = pp_word_mode(pl.word, lane);
+        const pp_seg_origin &o = aux.o[lane];
+        const pp_seg_world sw = pp_seg_world_make(aux.ss, aux.cs, pl.sx, pl.sy, o.ox, o.oy, o.so, o.co, pl.rinv, mode);
+        t.segw[lane] = sw;
+        t.x0y0[lane] = (mode == PP_MODE_S) ? make_double2(0.0, 0.0) : make_double2(sw.X0, sw.Y0);
+    }
+    if (lane == 3) {
+        const uint32_t c0 = (pl.n[0] + 31u) >> 5, c1 = (pl.n[1] + 31u) >> 5, c2 = (pl.n[2] + 31u) >> 5;
+        t.first[0] = 0u;
+        t.first[1] = c0;
+        t.first[2] = c0 + c1;
+        t.first[3] = c0 + c1 + c2;
+    }
+    if (pl.step != t.step) {  // warp-uniform (true for a NaN: the first path of the warp)
+        double sB, cB;
+        pp_sincos1((double)lane * pl.step, &sB, &cB);
+        t.uv[lane] = make_double2(cB, sB);
+        t.uv[32 + lane] = make_double2(1.0, (double)lane);
+        __syncwarp();
+        if (lane == 0) t.step = pl.step;
+    }
+    pp_poly_window_fill(pl, t, 0u, lane);
+}
+
 #define PP_POLY_THREADS 128
 #ifndef PP_POLY_MIN_BLOCKS
 #define PP_POLY_MIN_BLOCKS 7  // 72 registers; round 2 (circle filter, cell-ordered boxes): C5 slice / Dubins extend / no-hit 1.56 / 1.98 / 3.35 ms
@@ -756,6 +834,14 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = (int)(tid & 31u), wib = (int)(tid >> 5);
     const size_t warps_total = (size_t)gridDim.x * (PP_POLY_THREADS / 32);
+#if PP_POLY_TABLES
+    __shared__ __align__(16) pp_poly_tables s_tab[DUBINS ? PP_POLY_THREADS / 32 : 1];
+    pp_poly_tables &tab = s_tab[DUBINS ? wib : 0];
+    if (DUBINS) {  // no (cos, sin)(l step) table yet
+        if (lane == 0) tab.step = CUDART_NAN;
+        __syncwarp();
+    }
+#endif
     for (size_t line = (size_t)blockIdx.x * (PP_POLY_THREADS / 32) + wib; line < n_lines; line += warps_total) {
         uint32_t np;      // points of this polyline
         uint32_t base = 0;
@@ -765,8 +851,12 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
         __shared__ pp_dubins_plan s_plan[PP_POLY_THREADS / 32];
         __shared__ pp_plan_aux s_aux[PP_POLY_THREADS / 32];
         const pp_dubins_plan &pl = s_plan[wib];
-        const pp_seg_origin *o = s_aux[wib].o;
         const pp_plan_aux &aux = s_aux[wib];
+#if PP_POLY_TABLES
+        uint32_t w0 = 0;  // first entry of the coefficient window
+#else
+        const pp_seg_origin *o = s_aux[wib].o;
+#endif
         uint32_t nsamp = 0;
         if (DUBINS) {
             __syncwarp();  // every lane is done with the previous polyline's record
@@ -787,6 +877,12 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 nsamp = pl.count;
             }
             np = nsamp + 1;
+#if PP_POLY_TABLES
+            if (nsamp > 1u) {
+                pp_poly_tables_init(pl, aux, tab, lane);
+                w0 = 0u;
+            }
+#endif
         } else {
             base = csr.off[line];
             np = csr.off[line + 1] - base;
@@ -805,9 +901,33 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 // divergence between the lanes of a chunk except where a chunk straddles a segment junction
                 if (nsamp > 1u) {  // uniform; implies a feasible word
                     const uint32_t kk = min(max(k, 1u), nsamp - 1u);
+#if PP_POLY_TABLES
+                    uint32_t j = kk - 1u;
+                    int seg = 0;
+                    if (j >= pl.n[0]) {
+                        j -= pl.n[0];
+                        seg = 1;
+                        if (j >= pl.n[1]) {
+                            j -= pl.n[1];
+                            seg = 2;
+                        }
+                    }
+                    const uint32_t e = tab.first[seg] + (j >> 5);
+                    if (__any_sync(0xffffffffu, e >= w0 + 32u)) {  // slide the window (lane 0 holds the lowest entry)
+                        w0 = __shfl_sync(0xffffffffu, e, 0);
+                        pp_poly_window_fill(pl, tab, w0, lane);
+                    }
+                    const pp_arc_coef kc = tab.coef[e - w0];
+                    // straight segments: the middle one of the four CSC words (src/dubins.rs:26-113)
+                    const double2 uv = tab.uv[(j & 31u) + ((seg == 1 && pl.word < PP_RLR) ? 32u : 0u)];
+                    const double2 c0 = tab.x0y0[seg];
+                    x = fma(uv.x, kc.Px, fma(uv.y, kc.Qx, c0.x));
+                    y = fma(uv.x, kc.Py, fma(uv.y, kc.Qy, c0.y));
+#else
                     double lx, ly, lyaw;
                     pp_plan_sample_local(pl, o, kk, &lx, &ly, &lyaw);
                     pp_local_to_world(aux.ss, aux.cs, pl.sx, pl.sy, lx, ly, &x, &y);
+#endif
                 }
                 if (k == 0u) {  // slot 0 is exactly the start pose (0*cos + 0*sin + sx)
                     x = pl.sx;

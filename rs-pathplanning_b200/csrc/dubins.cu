@@ -3,8 +3,11 @@
 //
 // Reference arithmetic: src/dubins.rs:14-428.  Layout: SoA f64 arrays sx[], sy[], syaw[], ex[], ey[],
 // eyaw[] (one coalesced 8-byte load per lane and array); outputs cost[] f64, word[] u8, optional tpq[3n].
+#include <algorithm>
+
 #include "dubins_device.cuh"
 #include "pp_common.cuh"
+#include "pp_replay.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // kernel 1: evaluate.  One thread per pose pair; FP64-pipe bound (about 490 DP instructions per
@@ -158,10 +161,14 @@ int pp_launch_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi
 // plan / count: evaluate, then replay generate_local_course's index arithmetic (src/dubins.rs:200-289)
 // without producing samples: per segment the first `pd`, the number of loop iterations obtained by
 // the reference's own repeated addition (Q10), the carried remainder `ll`, and finally the trim rule
-// (Q6/Q7) which needs the local x of the trailing slots.  One thread per path; the replay is a
-// dependent DADD/DSETP chain (2 DP instructions per sample), cheap next to the fill pass.
+// (Q6/Q7) which needs the local x of the trailing slots.  One thread per path.  The literal replay is a
+// dependent DADD/DSETP/BRA chain per sample (80 % of this kernel's instructions on C5 paths); pp_replay.cuh
+// produces the same count and the same final `pd` by jumping binade by binade.
 // ------------------------------------------------------------------------------------------------
 #define PP_PLAN_MAX_ITERS (1u << 26)
+#ifndef PP_PLAN_LITERAL_REPLAY
+#define PP_PLAN_LITERAL_REPLAY 0  // A/B switch.  1: the serial `pd += d` loop (round 1 / early round 2)
+#endif
 
 // one path: evaluate + replay; (sx, sy, syaw) are ignored when from_origin
 __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, double syaw, double ex, double ey,
@@ -200,6 +207,7 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
             pl.pd0[sgm] = pd;
             uint32_t cnt = 0;
             double al = fabs(l);
+#if PP_PLAN_LITERAL_REPLAY
             while (fabs(pd) <= al) {  // :239
                 pd += d;
                 if (++cnt >= PP_PLAN_MAX_ITERS) {
@@ -207,6 +215,10 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
                     break;
                 }
             }
+#else
+            // the same loop, bit for bit, in O(binades) steps (pp_replay.cuh)
+            if (!pp_replay_segment(pd, d, al, PP_PLAN_MAX_ITERS, &cnt, &pd)) overflow = true;
+#endif
             pl.n[sgm] = cnt;
             ll = (l - pd) - d;  // :256
         }
@@ -298,25 +310,34 @@ __global__ void __launch_bounds__(128)
         out[1] = pl.from_origin ? 0.0 : (ss * 0.0 + cs * 0.0) + pl.sy;
         out[2] = pl.from_origin ? 0.0 : pp_pi_2_pi_fast(0.0 + pl.syaw);
     }
+    // samples exactly as pp_dubins_fill_kernel makes them (same chunk / lane split of the arc parameter, same device
+    // functions): the scalar call and the batch return the same bits
     double ox = 0.0, oy = 0.0, oyaw = 0.0, so = 0.0, co = 1.0;
     uint32_t base = 1;
+    double sB, cB;
+    pp_sincos1((double)(threadIdx.x & 31u) * pl.step, &sB, &cB);
 #pragma unroll
     for (int seg = 0; seg < 3; ++seg) {
         const int mode = pp_word_mode(pl.word, seg);
         const double len = pl.len[seg], pd0 = pl.pd0[seg];
         const double d = (len > 0.0) ? pl.step : -pl.step;
         const uint32_t ns = pl.n[seg];
+        const pp_seg_world sw = pp_seg_world_make(ss, cs, pl.sx, pl.sy, ox, oy, so, co, pl.rinv, mode);
+        const double sBd = (d > 0.0) ? sB : -sB;
+        const bool right = mode == PP_MODE_R;
         for (uint32_t j = threadIdx.x; j < ns; j += blockDim.x) {
             const uint32_t k = base + j;
             if (k >= pl.count) break;
+            const double jf = (double)j;
             double x, y, yaw;
-            pp_interpolate(mode, pd0 + (double)j * d, ox, oy, oyaw, so, co, pl.rinv, &x, &y, &yaw);
-            if (!pl.from_origin) {
-                const double xw = (cs * x + (-ss) * y) + pl.sx;
-                const double yw = (ss * x + cs * y) + pl.sy;
-                x = xw;
-                y = yw;
-                yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
+            if (mode == PP_MODE_S) {
+                pp_line_sample(sw, fma(jf, d, pd0), &x, &y);
+                yaw = pl.from_origin ? oyaw : pp_pi_2_pi_fast(oyaw + pl.syaw);
+            } else {
+                const pp_arc_coef kc = pp_arc_coef_make(sw, pd0 + (double)(j & ~31u) * d);
+                pp_arc_sample(sw, kc, sBd, cB, &x, &y);
+                yaw = oyaw + fma(jf, right ? -d : d, right ? -pd0 : pd0);
+                if (!pl.from_origin) yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
             }
             out[3 * (size_t)k + 0] = x;
             out[3 * (size_t)k + 1] = y;
@@ -368,6 +389,9 @@ int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double 
                        // two rows per warp).  MEASURED AND NOT ADOPTED: 0.378 ms against 0.306 ms for the same kernel with
                        // vector stores and 0.280 ms for the single-row kernel below (5.1e7 samples): 1.6 M bulk copies of
                        // 768 B are too small for the TMA engine to beat 48 coalesced 16-byte stores per row.
+#endif
+#ifndef PP_FILL_LEGACY
+#define PP_FILL_LEGACY 0  // A/B switch.  1: the round-1 kernel (one sincos per SAMPLE, local frame + per-sample rotation)
 #endif
 #if PP_FILL_TMA
 #define PP_FILL_ROW 100  // doubles per staging row: 96 (32 samples) + 1 (alignment shift) + padding to a 16-byte multiple
@@ -473,7 +497,7 @@ __global__ void __launch_bounds__(PP_FILL_THREADS)
     if (lane == 0) pp_bulk_wait<0>();  // every bulk store of this warp has landed before the CTA retires
 #endif
 }
-#else
+#elif PP_FILL_LEGACY
 // Variants measured on 5.1e7 samples (2^16 C5 paths) and NOT adopted (round 2, profiles/r02_summary.md): rows leaving
 // through the TMA engine (cp.async.bulk shared -> global, two rows per warp; PP_FILL_TMA=1 above) 0.378 ms; rows of
 // 64 samples with two interpolations in flight per lane 0.366 ms; this kernel under __launch_bounds__(128, 6) 0.418 ms;
@@ -556,11 +580,193 @@ __global__ void __launch_bounds__(PP_FILL_THREADS)
         }
     }
 }
+#else
+// Default since round 2 (late): the same warp-per-path, 32-samples-per-row staging, but the samples are produced in
+// the WORLD frame from per-segment constants (pp_seg_world) and, for arcs, per-chunk coefficients (pp_arc_coef):
+// one sincos per 32-sample chunk -- computed 32 chunks at a time, one chunk per lane, parked in shared memory -- and
+// one sincos per lane and path (lane * step) instead of one sincos plus two rotations per sample.  The round-1 kernel
+// (PP_FILL_LEGACY=1) executed ~129 warp instructions per row and ran at 0.61 of a pure store stream because of them.
+// The staging row is shifted by the parity of the row's first global element (constant per segment: rows are 96
+// doubles), so both the shared-memory reads and the global stores of a row are 16-byte vectors; full rows -- all but
+// the last of a segment -- take a path with no per-row index arithmetic.
+#define PP_FILL_STAGE 100  // 96 doubles + the parity shift, padded to a 16-byte multiple
+#ifndef PP_FILL_MIN_BLOCKS
+#define PP_FILL_MIN_BLOCKS 4  // 120 registers
+#endif
+
+// one row of `cnt` samples (3 cnt doubles, contiguous in `out` from d0) leaves the staging row: the generic form for
+// the last, partial row of a segment
+__device__ __forceinline__ void pp_fill_store_partial(double *d0, const double *stage, const double2 *svec, uint32_t head,
+                                                      uint32_t cnt, int lane) {
+    const uint32_t D = 3 * cnt;
+    const uint32_t nvec = (D - head) >> 1;
+    double2 *gvec = reinterpret_cast<double2 *>(d0 + head);
+    if (lane == 0 && head) d0[0] = stage[0];
+#pragma unroll
+    for (uint32_t v = lane; v < 64; v += 32)
+        if (v < nvec) gvec[v] = svec[v];
+    if (lane == 0 && ((D - head) & 1u)) d0[D - 1] = stage[D - 1];
+}
+
+//
+// Work distribution: path lengths differ by orders of magnitude, so a static path -> warp map leaves the SMs idle at
+// the end (and the short warps of a CTA idle all along).  The grid is exactly the resident CTAs and every warp draws
+// `batch` consecutive paths at a time from a counter in the context (work[0]; work[1] counts finished CTAs, the last
+// one re-arms both for the next launch on the stream).
+__global__ void __launch_bounds__(PP_FILL_THREADS, PP_FILL_MIN_BLOCKS)
+    pp_dubins_fill_kernel(uint32_t n, uint32_t batch, unsigned int *__restrict__ work,
+                          const pp_dubins_plan *__restrict__ plans, const uint64_t *__restrict__ offsets,
+                          double *__restrict__ out) {
+    __shared__ __align__(16) double fill_stage[PP_FILL_THREADS / 32][PP_FILL_STAGE];
+    __shared__ pp_arc_coef fill_coef[PP_FILL_THREADS / 32][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    pp_arc_coef *coef = fill_coef[wib];
+    uint32_t path = 0, path_end = 0;
+    for (;; ++path) {
+        if (path >= path_end) {  // warp-uniform
+            unsigned int first = 0;
+            if (lane == 0) first = atomicAdd(&work[0], batch);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first >= n) break;
+            path = first;
+            path_end = min(n, first + batch);
+        }
+        const pp_dubins_plan pl = plans[path];
+        if (pl.count == 0 || pl.count == 0xFFFFFFFFu) continue;
+        double ss = 0.0, cs = 1.0;
+        if (!pl.from_origin) pp_sincos1(pl.syaw, &ss, &cs);
+        double *dst = out + 3 * offsets[path];
+        if (lane == 0) {  // slot 0: the untouched zero of the reference's buffer = the start pose
+            dst[0] = pl.from_origin ? 0.0 : (cs * 0.0 + (-ss) * 0.0) + pl.sx;
+            dst[1] = pl.from_origin ? 0.0 : (ss * 0.0 + cs * 0.0) + pl.sy;
+            dst[2] = pl.from_origin ? 0.0 : pp_pi_2_pi_fast(0.0 + pl.syaw);
+        }
+        double sB, cB;  // this lane's offset inside a chunk: lane * step
+        pp_sincos1((double)lane * pl.step, &sB, &cB);
+        double ox = 0.0, oy = 0.0, oyaw = 0.0, so = 0.0, co = 1.0;
+        uint32_t base = 1;
+#pragma unroll 1
+        for (int seg = 0; seg < 3; ++seg) {
+            const int mode = pp_word_mode(pl.word, seg);
+            const double len = pl.len[seg], pd0 = pl.pd0[seg];
+            const double d = (len > 0.0) ? pl.step : -pl.step;
+            const uint32_t ns = pl.n[seg];
+            // samples of this segment that survive the trim rule (Q6/Q7), as full rows of 32 + one partial row
+            const uint32_t nseg = min(ns, pl.count > base ? pl.count - base : 0u);
+            const uint32_t nfull = nseg >> 5, rem = nseg & 31u;
+            if (nseg != 0u) {
+                const pp_seg_world sw = pp_seg_world_make(ss, cs, pl.sx, pl.sy, ox, oy, so, co, pl.rinv, mode);
+                double *d0 = dst + 3 * (size_t)base;
+                // parity of the first global element of every row of this segment (a full row is 96 doubles)
+                const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(d0) >> 3) & 1u);
+                double *stage = fill_stage[wib] + head;  // element e of a row sits at stage[e]: e = head (mod 2) is 16-byte aligned
+                const double2 *svec = reinterpret_cast<const double2 *>(fill_stage[wib]) + head;  // vector v = elements head + 2v, + 1
+                double *mine = stage + 3 * lane;  // stride of 3 doubles: conflict-free
+                double2 *gvec = reinterpret_cast<double2 *>(d0 + head) + lane;
+                // a full row is 48 vectors (head = 0) or 1 + 47 vectors + 1: lane 0's vector pointer sits one element
+                // after the row's first, lane 15's second-round pointer exactly on its last
+                const bool second = lane < 16 - (int)head, first_el = head && lane == 0, last_el = head && lane == 15;
+                double jf = (double)lane;  // sample index inside the segment, as a double (exact)
+                if (mode == PP_MODE_S) {
+                    // a straight segment keeps its origin's yaw (src/dubins.rs:166): one normalisation per segment
+                    const double yaw_s = pl.from_origin ? oyaw : pp_pi_2_pi_fast(oyaw + pl.syaw);
+                    for (uint32_t c = 0; c < nfull; ++c) {
+                        double x, y;
+                        pp_line_sample(sw, fma(jf, d, pd0), &x, &y);
+                        mine[0] = x;
+                        mine[1] = y;
+                        mine[2] = yaw_s;
+                        __syncwarp();
+                        gvec[0] = svec[lane];
+                        if (second) gvec[32] = svec[lane + 32];
+                        if (first_el) reinterpret_cast<double *>(gvec)[-1] = reinterpret_cast<const double *>(svec + lane)[-1];
+                        if (last_el) *reinterpret_cast<double *>(gvec + 32) = *reinterpret_cast<const double *>(svec + lane + 32);
+                        __syncwarp();
+                        gvec += 48;
+                        jf += 32.0;
+                    }
+                    if (rem != 0u) {
+                        if ((uint32_t)lane < rem) {
+                            double x, y;
+                            pp_line_sample(sw, fma(jf, d, pd0), &x, &y);
+                            mine[0] = x;
+                            mine[1] = y;
+                            mine[2] = yaw_s;
+                        }
+                        __syncwarp();
+                        pp_fill_store_partial(d0 + 96 * (size_t)nfull, stage, svec, head, rem, lane);
+                        __syncwarp();
+                    }
+                } else {
+                    const double sBd = (d > 0.0) ? sB : -sB;
+                    // yaw of an arc sample: oyaw + pd (left) / oyaw - pd (right); the negation is exact, so the right
+                    // turn walks (-pd0) + j (-d)
+                    const bool right = mode == PP_MODE_R;
+                    const double pdy0 = right ? -pd0 : pd0, dy = right ? -d : d;
+                    for (uint32_t g0 = 0; g0 < nfull; g0 += 32) {
+                        // coefficients of the next 32 chunks, one chunk per lane
+                        __syncwarp();
+                        coef[lane] = pp_arc_coef_make(sw, pd0 + (double)(32u * min(g0 + (uint32_t)lane, nfull)) * d);
+                        __syncwarp();
+                        const pp_arc_coef *cp = coef, *cend = coef + min(32u, nfull - g0);
+                        do {
+                            double x, y;
+                            pp_arc_sample(sw, *cp, sBd, cB, &x, &y);
+                            double yaw = oyaw + fma(jf, dy, pdy0);
+                            if (!pl.from_origin) yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
+                            mine[0] = x;
+                            mine[1] = y;
+                            mine[2] = yaw;
+                            __syncwarp();
+                            gvec[0] = svec[lane];
+                            if (second) gvec[32] = svec[lane + 32];
+                            if (first_el) reinterpret_cast<double *>(gvec)[-1] = reinterpret_cast<const double *>(svec + lane)[-1];
+                            if (last_el) *reinterpret_cast<double *>(gvec + 32) = *reinterpret_cast<const double *>(svec + lane + 32);
+                            __syncwarp();
+                            gvec += 48;
+                            jf += 32.0;
+                        } while (++cp != cend);
+                    }
+                    if (rem != 0u) {
+                        if ((uint32_t)lane < rem) {
+                            const pp_arc_coef kc = pp_arc_coef_make(sw, pd0 + (double)(32u * nfull) * d);
+                            double x, y;
+                            pp_arc_sample(sw, kc, sBd, cB, &x, &y);
+                            double yaw = oyaw + fma(jf, dy, pdy0);
+                            if (!pl.from_origin) yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
+                            mine[0] = x;
+                            mine[1] = y;
+                            mine[2] = yaw;
+                        }
+                        __syncwarp();
+                        pp_fill_store_partial(d0 + 96 * (size_t)nfull, stage, svec, head, rem, lane);
+                        __syncwarp();
+                    }
+                }
+            }
+            base += ns;
+            if (seg < 2) {  // next origin = this segment's end point (src/dubins.rs:258-271, read back at :230)
+                double ex_, ey_, eyaw_;
+                pp_interpolate(mode, len, ox, oy, oyaw, so, co, pl.rinv, &ex_, &ey_, &eyaw_);
+                ox = ex_;
+                oy = ey_;
+                oyaw = eyaw_;
+                pp_sincos1(oyaw, &so, &co);
+            }
+        }
+    }
+    __syncthreads();  // every warp of this CTA has drawn its last batch
+    if (threadIdx.x == 0 && atomicAdd(&work[1], 1u) == gridDim.x - 1u) {
+        work[0] = 0u;
+        work[1] = 0u;
+    }
+}
 #endif
 
 int pp_launch_dubins_fill(pp_ctx *ctx, size_t n, const void *plans, const uint64_t *offsets, double *out,
                           cudaStream_t stream) {
     if (n == 0) return PP_OK;
+#if PP_FILL_TMA || PP_FILL_LEGACY
     pp_launch_scope scope(ctx, "dubins_fill");
     size_t warps = n;
     size_t blocks = (warps + (PP_FILL_THREADS / 32) - 1) / (PP_FILL_THREADS / 32);
@@ -569,6 +775,28 @@ int pp_launch_dubins_fill(pp_ctx *ctx, size_t n, const void *plans, const uint64
     pp_dubins_fill_kernel<<<(unsigned)blocks, PP_FILL_THREADS, 0, stream>>>(n, (const pp_dubins_plan *)plans, offsets,
                                                                             out);
     PP_CUDA(ctx, cudaGetLastError());
+#else
+    static int resident = 0;  // CTAs of this kernel per SM (same on every device this library targets)
+    if (resident == 0) {
+        int r = 0;
+        PP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, pp_dubins_fill_kernel, PP_FILL_THREADS, 0));
+        resident = r > 0 ? r : 1;
+    }
+    const size_t slots = (size_t)ctx->sm_count * resident;  // CTAs that run side by side
+    const size_t piece = (size_t)1 << 30;                    // the work counter is 32 bits wide
+    for (size_t first = 0; first < n; first += piece) {
+        const size_t m = std::min(piece, n - first);
+        const size_t warps = slots * (PP_FILL_THREADS / 32);
+        // ~8 draws per warp: fine enough to level the tail, coarse enough that 10^6 short paths do not queue on one
+        // address
+        const uint32_t batch = (uint32_t)std::min<size_t>(64, std::max<size_t>(1, m / (warps * 8)));
+        const size_t blocks = std::min(slots, (m + (PP_FILL_THREADS / 32) - 1) / (PP_FILL_THREADS / 32));
+        pp_launch_scope scope(ctx, "dubins_fill");
+        pp_dubins_fill_kernel<<<(unsigned)blocks, PP_FILL_THREADS, 0, stream>>>(
+            (uint32_t)m, batch, ctx->tickets + PP_TICKETS_FILL, (const pp_dubins_plan *)plans + first, offsets + first, out);
+        PP_CUDA(ctx, cudaGetLastError());
+    }
+#endif
     return PP_OK;
 }
 

@@ -46,23 +46,26 @@ __device__ __forceinline__ double pp_pi_2_pi(double a) { return fmod(a + PP_PI, 
 // Same value, bit for bit, without the library fmod: fmod's result is exactly representable, so ONE fma
 // reproduces it when the integer quotient is right, and a quotient that is off by one (product rounding next
 // to a multiple of 2pi) is repaired by redoing the fma with the neighbouring integer.
-__device__ __forceinline__ double pp_pi_2_pi_fast(double a) {
-    const double b = a + PP_PI;
+// b = a + pi with |b| >= 2 pi (or NaN): the quotient route.  Out of line: the callers' common case is the one-line
+// test in pp_pi_2_pi_fast.
+static __device__ __noinline__ double pp_pi_2_pi_wrap(double b) {
     const double ab = fabs(b);
-    double r = ab;
-    if (ab >= PP_TWO_PI) {
-        if (!(ab < 1e15)) return fmod(b, PP_TWO_PI) - PP_PI;  // huge or infinite
-        double k = floor(ab * PP_INV_TWO_PI);
+    if (!(ab < 1e15)) return fmod(b, PP_TWO_PI) - PP_PI;  // huge, infinite or NaN
+    double k = floor(ab * PP_INV_TWO_PI);
+    double r = fma(-k, PP_TWO_PI, ab);
+    if (r < 0.0) {
+        k -= 1.0;
         r = fma(-k, PP_TWO_PI, ab);
-        if (r < 0.0) {
-            k -= 1.0;
-            r = fma(-k, PP_TWO_PI, ab);
-        } else if (r >= PP_TWO_PI) {
-            k += 1.0;
-            r = fma(-k, PP_TWO_PI, ab);
-        }
+    } else if (r >= PP_TWO_PI) {
+        k += 1.0;
+        r = fma(-k, PP_TWO_PI, ab);
     }
     return copysign(r, b) - PP_PI;
+}
+__device__ __forceinline__ double pp_pi_2_pi_fast(double a) {
+    const double b = a + PP_PI;
+    if (fabs(b) < PP_TWO_PI) return b - PP_PI;  // fmod(b, 2 pi) == b
+    return pp_pi_2_pi_wrap(b);
 }
 
 struct pp_dubins_sol {
@@ -474,6 +477,60 @@ __device__ __forceinline__ void pp_plan_sample_local(const pp_dubins_plan &pl, c
                    y, yaw);
 }
 
+
+// ---- samples of one segment straight in the world frame (sample fill / scalar path kernels) ----------------------
+// The reference interpolates in the local frame (src/dubins.rs:155-198) and rotates / translates every sample
+// afterwards (:412-422).  Both maps are rigid, so they compose per SEGMENT: world origin (wox, woy) and the sine /
+// cosine of (syaw + origin yaw) by the angle-addition formulas.  An arc sample at arc parameter pd = A + B, with A the
+// parameter of the first sample of a 32-sample chunk and B = lane * step, is then LINEAR in (sin B, cos B):
+//     x = X0 + cos B * Px + sin B * Qx,   y = Y0 + cos B * Py + sin B * Qy
+// with four per-chunk coefficients (pp_arc_coef, one sincos per CHUNK instead of one per sample) and one sincos per
+// lane and path for B.  Rounding differs from the reference's order by a few ulp of the path's extent -- the same
+// class as `pd0 + j d` against the accumulated `pd` (Q10), far inside the 1e-9 contract.
+struct pp_seg_world {
+    double wox, woy;  // segment origin, world frame
+    double Cr, Sr;    // radius * cos / sin (syaw + origin yaw)
+    double X0, Y0;    // arc centre-relative constants (arc modes only)
+    double Sg, Cg;    // Sr, Cr signed by the turn direction (+ left, - right)
+};
+__device__ __forceinline__ pp_seg_world pp_seg_world_make(double ss, double cs, double sx, double sy, double ox, double oy,
+                                                          double so, double co, double rinv, int mode) {
+    pp_seg_world s;
+    s.wox = (cs * ox + (-ss) * oy) + sx;  // pp_local_to_world of the origin (exact identity for from_origin: ss = 0, cs = 1)
+    s.woy = (ss * ox + cs * oy) + sy;
+    const double C = fma(cs, co, -(ss * so)), S = fma(ss, co, cs * so);
+    s.Cr = C * rinv;
+    s.Sr = S * rinv;
+    const bool right = mode == PP_MODE_R;
+    s.Sg = right ? -s.Sr : s.Sr;
+    s.Cg = right ? -s.Cr : s.Cr;
+    s.X0 = s.wox - s.Sg;
+    s.Y0 = s.woy + s.Cg;
+    return s;
+}
+struct __align__(16) pp_arc_coef {
+    double Px, Qx, Py, Qy;
+};
+// coefficients of the chunk whose first sample has arc parameter A
+__device__ __forceinline__ pp_arc_coef pp_arc_coef_make(const pp_seg_world &s, double A) {
+    double sA, cA;
+    pp_sincos1(A, &sA, &cA);
+    pp_arc_coef k;
+    k.Px = fma(s.Cr, sA, s.Sg * cA);
+    k.Qx = fma(s.Cr, cA, -(s.Sg * sA));
+    k.Py = fma(s.Sr, sA, -(s.Cg * cA));
+    k.Qy = fma(s.Sr, cA, s.Cg * sA);
+    return k;
+}
+__device__ __forceinline__ void pp_arc_sample(const pp_seg_world &s, const pp_arc_coef &k, double sB, double cB, double *x,
+                                              double *y) {
+    *x = fma(cB, k.Px, fma(sB, k.Qx, s.X0));
+    *y = fma(cB, k.Py, fma(sB, k.Qy, s.Y0));
+}
+__device__ __forceinline__ void pp_line_sample(const pp_seg_world &s, double pd, double *x, double *y) {
+    *x = fma(pd, s.Cr, s.wox);
+    *y = fma(pd, s.Sr, s.woy);
+}
 
 // local -> world (src/dubins.rs:412-422); (ss, cs) = sincos(syaw)
 __device__ __forceinline__ void pp_local_to_world(double ss, double cs, double sx, double sy, double x, double y,

@@ -72,6 +72,9 @@ struct pp_timing_slot {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
+#define PP_TICKETS 128
+#define PP_TICKETS_FILL 64
+
 struct pp_ctx {
     int device = 0;
     int sm_count = PP_SM_COUNT_B200;
@@ -89,7 +92,8 @@ struct pp_ctx {
     pp_tree_dev tree;
     pp_world_dev world;
     // scratch (grown on demand)
-    unsigned int *tickets = nullptr;  // 64 zeroed counters for last-block-done reductions
+    unsigned int *tickets = nullptr;  // PP_TICKETS zeroed counters: [0, 64) last-block-done reductions (nn.cu),
+                                      // [PP_TICKETS_FILL, +2) work / done counters of the sample fill kernel
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     void *pinned = nullptr;

@@ -223,6 +223,51 @@ def test_sampling_from_origin_and_none(ctx, O):
     assert ctx.dubins_path(float("nan"), 0.0, 0.0, 3.0, 2.0, 1.0, 0.8, 0.1) is None  # reference: None
 
 
+@pytest.mark.parametrize("radius,step,span", [(1.0, 0.1, 4.0), (0.5, 0.05, 2.0), (2.5, 0.2, 40.0)])
+def test_from_origin_batch(ctx, O, pp, radius, step, span):
+    """dubins_path_planning_from_origin (src/dubins.rs:326-399) as a batch: goals given in the start frame, NO
+    rotation and NO translation of the samples, yaw left un-normalised -- counts, words and every sample against the
+    oracle's own from_origin route, plus the scalar entry point on the same goals."""
+    rng = np.random.default_rng(4242)
+    n = 400
+    ex, ey = rng.uniform(-span, span, n), rng.uniform(-span, span, n)
+    eyaw = rng.uniform(-math.pi, math.pi, n)
+    z = np.zeros(n)
+    junk = rng.uniform(-9, 9, n)  # start poses are ignored when from_origin is set
+    out, offsets, counts = pp.dubins.batch_paths(junk, junk, junk, ex, ey, eyaw, radius, step, from_origin=True, ctx=ctx)
+    assert int(counts.sum()) == out.shape[0]
+    worst, compared = 0.0, 0
+    for i in range(n):
+        q = O.dubins_path(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, from_origin=True)
+        cnt, fl = O.dubins_path_flags(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, from_origin=True)
+        if q is None:
+            assert counts[i] == 0
+            continue
+        if counts[i] != len(q.x):
+            assert fl != 0, ("from_origin count differs on a path the oracle calls robust", i, int(counts[i]), len(q.x))
+            continue
+        seg = out[int(offsets[i]):int(offsets[i]) + int(counts[i])]
+        if fl == 0:
+            scale = max(1.0, np.abs(q.x).max(initial=0), np.abs(q.y).max(initial=0))
+            worst = max(worst, np.abs(seg[:, 0] - q.x).max(initial=0) / scale, np.abs(seg[:, 1] - q.y).max(initial=0) / scale,
+                        np.abs(seg[:, 2] - q.yaw).max(initial=0))  # yaw is NOT wrapped on this route: plain difference
+            compared += 1
+        if i % 40 == 0:  # the scalar entry point walks the same plan
+            p = ctx.dubins_path(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, from_origin=True)
+            assert p is not None and len(p[0]) == counts[i] and p[3] == q.word
+            assert np.array_equal(p[0], seg[:, 0]) and np.array_equal(p[1], seg[:, 1]) and np.array_equal(p[2], seg[:, 2])
+    assert compared > 0.9 * n and worst < TOL
+    # the same goals through the world-frame entry with a zero start pose: identical positions (rotation by 0,
+    # translation by 0 are exact), yaw wrapped by pi_2_pi there and raw here
+    out0, off0, cnt0 = pp.dubins.batch_paths(z, z, z, ex, ey, eyaw, radius, step, from_origin=False, ctx=ctx)
+    same = cnt0 == counts
+    assert same.mean() > 0.95
+    for i in np.nonzero(same)[0][::20]:
+        a = out[int(offsets[i]):int(offsets[i]) + int(counts[i])]
+        b = out0[int(off0[i]):int(off0[i]) + int(cnt0[i])]
+        assert np.abs(a[:, :2] - b[:, :2]).max(initial=0) < TOL
+
+
 def test_drop_in_module_api(pp, ctx, O):
     """the mirror of `pathplanning::dubins` reads like the reference's own call sites (benches/all.rs:100-115)"""
     d = pp.dubins

@@ -30,6 +30,20 @@ def test_division_free_predicates_are_exact(tmp_path):
     assert v == {"bad_random": 0, "bad_close": 0, "bad_special": 0, "bad_ring": 0}, v
 
 
+def test_sample_loop_fast_forward_is_exact(tmp_path):
+    """pp_replay.cuh jumps through generate_local_course's `while pd.abs() <= l.abs() { pd += d }` loop
+    (src/dubins.rs:239-255) binade by binade: iteration count and final pd must equal the literal loop's, bit for bit,
+    on the reference's call pattern, arbitrary steps of either sign, limits placed on iterates / binade tops / their
+    neighbours, tie binades, steps that vanish against pd, zeros, subnormals, infinities and NaN
+    (tools/replay_check.cpp)"""
+    exe = str(tmp_path / "replay_check")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off",
+                    os.path.join(ROOT, "tools", "replay_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe, "400000"], capture_output=True, text=True, check=True).stdout
+    v = {k: int(x) for k, x in (ln.split() for ln in out.strip().splitlines())}
+    assert v == {"bad_call_pattern": 0, "bad_steps": 0, "bad_random": 0, "bad_special": 0, "bad_tiny": 0}, v
+
+
 def test_tables_are_reproducible(tmp_path):
     """the committed coefficient tables are what tools/gen_math_tables.py generates"""
     import shutil
