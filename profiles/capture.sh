@@ -22,6 +22,11 @@ cap() {  # name, kernel regex, launch-skip, launch-count
   ncu -i gpurun_out/${R}_$1.ncu-rep --page raw --csv > gpurun_out/${R}_$1_raw.csv 2>/dev/null
   ncu -i gpurun_out/${R}_$1.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${R}_$1_source.csv 2>/dev/null
 }
+if [ "${2:-}" = "fillplan" ]; then  # late round 2: only the two kernels that changed after the r02b captures
+  $CMD > /dev/null 2>&1
+  cap fill "pp_dubins_fill_kernel" 0 1
+  cap plan "pp_dubins_plan_kernel" 5 1
+fi
 if [ "${2:-}" = "all" ]; then
   $CMD > /dev/null 2>&1
   # the extend step: default pair of launches (first instances), then the binned fused kernel and its binning

@@ -820,6 +820,55 @@ static __device__ __noinline__ void pp_poly_tables_init(const pp_dubins_plan &pl
     pp_poly_window_fill(pl, t, 0u, lane);
 }
 
+// ---- path-level test of the Dubins verify kernel.  `box` = the plan kernel's bounding box of every point of the path
+// and of the parent point (pp_path_box).  True when (i) every cell of the bounds classification grid under the box is
+// "inside" and (ii) no ring registered under the box's cells of the obstacle grid has an fp32 box that meets the
+// box -- then no sample can fail its own bounds test and no sample segment can find a candidate ring in its own walk
+// (its cells and its fp32 box are subsets of the path's), so the per-sample loop would return "free": the same
+// verdict without generating a single sample.  Applies to boxes of at most 32 bounds cells and 8 x 8 obstacle cells
+// (short edges: the extend step); long paths go straight to the per-sample loop.  All 32 lanes call together.
+#ifndef PP_POLY_PATH_BOX
+#define PP_POLY_PATH_BOX 1  // A/B switch
+#endif
+__device__ __forceinline__ bool pp_path_box_free(const pp_world_view &w, double x0, double y0, double x1, double y1, int lane) {
+    if (!((x1 - x0) < 1e300 && (y1 - y0) < 1e300 && x0 <= x1 && y0 <= y1)) return false;  // NaN / inf: no shortcut
+    {   // (i) bounds
+        const int ix0 = __double2int_rd((x0 - w.bminx) * w.binvx), iy0 = __double2int_rd((y0 - w.bminy) * w.binvy);
+        const int ix1 = __double2int_rd((x1 - w.bminx) * w.binvx), iy1 = __double2int_rd((y1 - w.bminy) * w.binvy);
+        if (ix0 < 0 || iy0 < 0 || ix1 >= w.bgx || iy1 >= w.bgy) return false;
+        const int nx = ix1 - ix0 + 1, ny = iy1 - iy0 + 1;
+        if (nx > 32 || ny > 32 || nx * ny > 32) return false;
+        bool inside = true;
+        if (lane < nx * ny) inside = __ldg(w.bcls + (size_t)(iy0 + lane / nx) * w.bgx + (ix0 + lane % nx)) == 1;
+        if (!__all_sync(0xffffffffu, inside)) return false;
+    }
+    if (w.n_rings == 0u) return true;
+    // (ii) obstacles: the cell range exactly as the per-sample walk computes it
+    int cx0 = __double2int_rd((x0 - w.gminx) * w.ginv), cy0 = __double2int_rd((y0 - w.gminy) * w.ginv);
+    int cx1 = __double2int_rd((x1 - w.gminx) * w.ginv), cy1 = __double2int_rd((y1 - w.gminy) * w.ginv);
+    if (cx1 < 0 || cy1 < 0 || cx0 >= w.gx || cy0 >= w.gy) return true;  // beside the ring grid: nothing is registered there
+    cx0 = max(cx0, 0);
+    cy0 = max(cy0, 0);
+    cx1 = min(cx1, w.gx - 1);
+    cy1 = min(cy1, w.gy - 1);
+    if (cx1 - cx0 >= 8 || cy1 - cy0 >= 8) return false;
+    const float q0x = __double2float_rd(x0), q0y = __double2float_rd(y0), q1x = __double2float_ru(x1), q1y = __double2float_ru(y1);
+    for (int r = cy0; r <= cy1; ++r) {
+        const uint32_t *row = w.cell_start + (size_t)r * w.gx;
+        const uint32_t k0 = __ldg(row + cx0), k1 = __ldg(row + cx1 + 1);  // a row of cells is one run of the cell-ordered boxes
+        for (uint32_t base = k0; base < k1; base += 32u) {
+            const uint32_t k = base + (uint32_t)lane;
+            bool meets = false;
+            if (k < k1) {
+                const float4 bb = __ldg(w.cell_box + k);
+                meets = !(q1x < bb.x || q0x > bb.z || q1y < bb.y || q0y > bb.w);
+            }
+            if (__any_sync(0xffffffffu, meets)) return false;
+        }
+    }
+    return true;
+}
+
 #define PP_POLY_THREADS 128
 #ifndef PP_POLY_MIN_BLOCKS
 #define PP_POLY_MIN_BLOCKS 7  // 72 registers; round 2 (circle filter, cell-ordered boxes): C5 slice / Dubins extend / no-hit 1.56 / 1.98 / 3.35 ms
@@ -877,6 +926,23 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 nsamp = pl.count;
             }
             np = nsamp + 1;
+            {
+                // the o[0] slot of the record carries the path's bounding box (pp_path_box); o[0] itself is the
+                // identity origin and is put back before the samples need it
+                const double bx0 = aux.o[0].ox, by0 = aux.o[0].oy, bx1 = aux.o[0].oyaw, by1 = aux.o[0].so;
+                __syncwarp();
+                if (lane < 5) reinterpret_cast<double *>(&s_aux[wib].o[0])[lane] = (lane == 4) ? 1.0 : 0.0;
+                __syncwarp();
+#if PP_POLY_PATH_BOX
+                // (the box already holds the parent point that closes the polyline, SURVEY Q6/Q12: it is the plan's goal)
+                if (CULL && pl.word != PP_WORD_NONE && pp_path_box_free(w, bx0, by0, bx1, by1, lane)) {
+                    if (lane == 0) ok[line] = 1;
+                    continue;
+                }
+#else
+                (void)bx0; (void)by0; (void)bx1; (void)by1;
+#endif
+            }
 #if PP_POLY_TABLES
             if (nsamp > 1u) {
                 pp_poly_tables_init(pl, aux, tab, lane);

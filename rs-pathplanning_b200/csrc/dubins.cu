@@ -173,7 +173,7 @@ int pp_launch_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi
 // one path: evaluate + replay; (sx, sy, syaw) are ignored when from_origin
 __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, double syaw, double ex, double ey,
                                                        double eyaw, double radius, double step, int from_origin,
-                                                       pp_plan_aux *aux = nullptr) {
+                                                       pp_plan_aux *aux = nullptr, double box_limit = 0.0) {
     pp_dubins_plan pl;
     if (from_origin) {  // the goal is given in the start frame: start pose = origin
         pl.sx = pl.sy = pl.syaw = 0.0;
@@ -228,10 +228,24 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
             // trim (:281-288): count = index of the last slot whose local x is non-zero
             uint32_t N = pl.n[0] + pl.n[1] + pl.n[2];
             pp_seg_origin o[3];
-            double gx;
-            pp_segment_origins(pl, o, &gx);
+            double gx, gy;
+            pp_segment_origins(pl, o, &gx, &gy);
             if (aux) {
-                aux->o[0] = o[0];
+                // o[0] is the identity origin by definition: its slot carries the path's bounding box to the verify kernel
+                pp_sincos1(pl.syaw, &aux->ss, &aux->cs);
+                double box[4];
+                // the verify kernel can only use boxes below `box_limit` in either extent (its cell-count caps, set by
+                // the launcher from the world's grids); the start-to-goal offset is a lower bound of the extent, so
+                // long edges (C5) skip the computation and carry a NaN box
+                if (fabs(ex - sx) < box_limit && fabs(ey - sy) < box_limit)
+                    pp_path_box(pl, o, aux->ss, aux->cs, gx, gy, from_origin ? pl.sx : ex, from_origin ? pl.sy : ey, box);
+                else
+                    box[0] = box[1] = box[2] = box[3] = CUDART_NAN;
+                aux->o[0].ox = box[0];
+                aux->o[0].oy = box[1];
+                aux->o[0].oyaw = box[2];
+                aux->o[0].so = box[3];
+                aux->o[0].co = 0.0;
                 aux->o[1] = o[1];
                 aux->o[2] = o[2];
             }
@@ -252,28 +266,64 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
             pl.count = cntout;
         }
     }
-    if (aux) pp_sincos1(pl.syaw, &aux->ss, &aux->cs);
+    if (aux && (s.word == PP_WORD_NONE || pl.count == 0xFFFFFFFFu)) {  // no path: no box (NaN never passes the box test)
+        pp_sincos1(pl.syaw, &aux->ss, &aux->cs);
+        aux->o[0].ox = aux->o[0].oy = aux->o[0].oyaw = aux->o[0].so = CUDART_NAN;
+    }
     return pl;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef PP_PLAN_MIN_BLOCKS
+#define PP_PLAN_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, PP_PLAN_MIN_BLOCKS)
     pp_dubins_plan_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
                           const double *__restrict__ syaw, const double *__restrict__ ex,
                           const double *__restrict__ ey, const double *__restrict__ eyaw, double radius, double step,
                           int from_origin, uint32_t *__restrict__ counts, pp_dubins_plan *__restrict__ plans,
-                          pp_plan_aux *__restrict__ aux_out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    pp_plan_aux aux;
+                          pp_plan_aux *__restrict__ aux_out, double box_limit) {
+    // Records leave through shared memory: a thread's own 112 / 136-byte record written straight to global memory is
+    // seven / seventeen warp stores that each touch 32 half-used sectors (ncu r03: lg_throttle on these stores was 31 %
+    // of the kernel's stall samples for 5 % of its instructions).  A warp's 32 records are contiguous in global
+    // memory, so they are parked per warp and copied out as coalesced 16-byte vectors.
+    __shared__ __align__(16) unsigned char s_plan[128 / 32][32 * sizeof(pp_dubins_plan)];
+    __shared__ __align__(16) unsigned char s_aux[128 / 32][32 * sizeof(pp_plan_aux)];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t first = i - (size_t)lane;  // first path of this warp
+    if (first >= n) return;                 // warp-uniform
+    const uint32_t live = (uint32_t)((n - first < 32) ? (n - first) : 32);
+    if (i < n) {
+        pp_plan_aux aux;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) aux.o[k].ox = aux.o[k].oy = aux.o[k].oyaw = aux.o[k].so = aux.o[k].co = 0.0;
-    pp_plan_aux *ap = aux_out ? &aux : nullptr;
-    const pp_dubins_plan pl = from_origin
-                                  ? pp_make_plan(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, 1, ap)
-                                  : pp_make_plan(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0, ap);
-    counts[i] = pl.count;
-    if (plans) plans[i] = pl;
-    if (aux_out) aux_out[i] = aux;
+        for (int k = 0; k < 3; ++k) aux.o[k].ox = aux.o[k].oy = aux.o[k].oyaw = aux.o[k].so = aux.o[k].co = 0.0;
+        pp_plan_aux *ap = aux_out ? &aux : nullptr;
+        const pp_dubins_plan pl = from_origin
+                                      ? pp_make_plan(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, 1, ap, box_limit)
+                                      : pp_make_plan(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0, ap, box_limit);
+        counts[i] = pl.count;
+        if (plans) *reinterpret_cast<pp_dubins_plan *>(&s_plan[wib][lane * sizeof(pp_dubins_plan)]) = pl;
+        if (aux_out) {
+            double *sa = reinterpret_cast<double *>(&s_aux[wib][lane * sizeof(pp_plan_aux)]);
+            const double *a = reinterpret_cast<const double *>(&aux);
+#pragma unroll
+            for (int k = 0; k < PP_PLAN_AUX_DOUBLES; ++k) sa[k] = a[k];
+        }
+    }
+    __syncwarp();
+    if (plans) {  // sizeof(pp_dubins_plan) = 7 x 16 bytes
+        const uint4 *src = reinterpret_cast<const uint4 *>(s_plan[wib]);
+        uint4 *dst = reinterpret_cast<uint4 *>(plans + first);
+        for (uint32_t v = lane; v < live * (uint32_t)(sizeof(pp_dubins_plan) / 16); v += 32) dst[v] = src[v];
+    }
+    if (aux_out) {  // 17 doubles per record; 32 records start 16-byte aligned, an odd number of them ends on a half vector
+        const double2 *src = reinterpret_cast<const double2 *>(s_aux[wib]);
+        double2 *dst = reinterpret_cast<double2 *>(aux_out + first);
+        const uint32_t nd = live * PP_PLAN_AUX_DOUBLES;
+        for (uint32_t v = lane; v < nd / 2; v += 32) dst[v] = src[v];
+        if ((nd & 1u) && lane == 0)
+            reinterpret_cast<double *>(aux_out + first)[nd - 1] = reinterpret_cast<const double *>(s_aux[wib])[nd - 1];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -370,9 +420,18 @@ int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double 
                           int from_origin, uint32_t *counts, void *plans, void *aux, cudaStream_t stream) {
     if (n == 0) return PP_OK;
     pp_launch_scope scope(ctx, "dubins_plan");
+    // largest box extent the verify kernel's path-level test accepts (collide.cu: pp_path_box_free -- at most 32 cells of
+    // the bounds grid, 8 x 8 cells of the obstacle grid); 0 without a world or without an aux record
+    double box_limit = 0.0;
+    if (aux && ctx->world.valid) {
+        const pp_world_dev &w = ctx->world;
+        box_limit = std::min(32.0 / w.binvx, 32.0 / w.binvy);
+        if (w.n_rings) box_limit = std::min(box_limit, 9.0 * w.gcell);
+        if (!(box_limit > 0.0)) box_limit = 0.0;
+    }
     pp_dubins_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius, step,
                                                                            from_origin, counts, (pp_dubins_plan *)plans,
-                                                                           (pp_plan_aux *)aux);
+                                                                           (pp_plan_aux *)aux, box_limit);
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;
 }

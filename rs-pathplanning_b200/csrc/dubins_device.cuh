@@ -435,7 +435,8 @@ static_assert(sizeof(pp_plan_aux) == PP_PLAN_AUX_DOUBLES * 8, "aux record is cop
 
 // origins of the three segments: segment i starts at segment i-1's end point, written by
 // interpolate(ind, l) at src/dubins.rs:258-271 and read back at :230.
-__device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_seg_origin o[3], double *gx) {
+__device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_seg_origin o[3], double *gx,
+                                                   double *gy = nullptr) {
     o[0].ox = 0.0;
     o[0].oy = 0.0;
     o[0].oyaw = 0.0;
@@ -452,8 +453,71 @@ __device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_
             pp_sincos1(yaw, &o[i + 1].so, &o[i + 1].co);
         } else {
             *gx = x;
+            if (gy) *gy = y;
         }
     }
+}
+
+// Axis-aligned box (world frame) around EVERY point the sampled path can produce: the start pose, the three segment
+// origins, the end point, and for each arc the axis extremes of its circle that fall inside the swept angle.  The box
+// travels to the verify kernel in the o[0] slot of the aux record (o[0] is the identity origin by definition) and
+// lets it dismiss a whole path with one look at the rings registered under the box.  Conservative by construction:
+// extremes are included with a 1e-6 rad margin and the box is padded by 1e-9 of the coordinates' scale, orders of
+// magnitude above the ulp-level differences between this arithmetic and the samples'.
+// (ss, cs) = sincos(pl.syaw); (gx, gy) = local end point of the third segment; (ex, ey) = the goal as given (the
+// verify kernel appends it to the samples as the parent point).
+__device__ __forceinline__ void pp_path_box(const pp_dubins_plan &pl, const pp_seg_origin o[3], double ss, double cs,
+                                            double gx, double gy, double ex, double ey, double box[4]) {
+    double minx = (ex < pl.sx) ? ex : pl.sx, maxx = (ex > pl.sx) ? ex : pl.sx;
+    double miny = (ey < pl.sy) ? ey : pl.sy, maxy = (ey > pl.sy) ? ey : pl.sy;
+    double nan_guard = ex + ey;
+    const double r = pl.rinv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        // world position of origin i (i = 3: the end point)
+        const double lx = (i < 3) ? o[i].ox : gx, ly = (i < 3) ? o[i].oy : gy;
+        const double wx = (cs * lx + (-ss) * ly) + pl.sx, wy = (ss * lx + cs * ly) + pl.sy;
+        // plain compare-and-select (fmin / fmax cost ~13 instructions apiece here); a NaN coordinate poisons the pad
+        // below and with it the whole box, which the verify kernel then refuses
+        minx = (wx < minx) ? wx : minx;
+        maxx = (wx > maxx) ? wx : maxx;
+        miny = (wy < miny) ? wy : miny;
+        maxy = (wy > maxy) ? wy : maxy;
+        nan_guard += wx + wy;
+        if (i == 3) break;
+        const int mode = pp_word_mode(pl.word, i);
+        const double len = pl.len[i];
+        if (mode == PP_MODE_S || !(len > 0.0)) continue;
+        const double C = fma(cs, o[i].co, -(ss * o[i].so)), S = fma(ss, o[i].co, cs * o[i].so);  // heading at the origin
+        const double theta0 = pl.syaw + o[i].oyaw;
+        const bool left = mode == PP_MODE_L;
+        // centre of the turn circle; phi0 = direction centre -> origin; the sweep is counter-clockwise for a left turn
+        const double ccx = left ? wx - r * S : wx + r * S, ccy = left ? wy + r * C : wy - r * C;
+        const double phi0 = left ? theta0 - 0.5 * PP_PI : theta0 + 0.5 * PP_PI;
+        // angle from phi0, in sweep direction, to the +x axis (k = 0); the other axes follow a quarter turn apart
+        const double v = left ? -phi0 : phi0;
+        const double a0 = v - PP_TWO_PI * floor(v * PP_INV_TWO_PI);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // left: axis k sits at k pi/2 counter-clockwise of +x; right (clockwise sweep): at k pi/2 clockwise, i.e. axis (4 - k) & 3
+            double a = a0 + (double)k * (0.5 * PP_PI);
+            if (a >= PP_TWO_PI) a -= PP_TWO_PI;
+            const bool in = !(a > len + 1e-6) || (a > PP_TWO_PI - 1e-6);  // NaN: included
+            const int axis = left ? k : ((4 - k) & 3);
+            if (in) {
+                if (axis == 0) maxx = (ccx + r > maxx) ? ccx + r : maxx;
+                if (axis == 1) maxy = (ccy + r > maxy) ? ccy + r : maxy;
+                if (axis == 2) minx = (ccx - r < minx) ? ccx - r : minx;
+                if (axis == 3) miny = (ccy - r < miny) ? ccy - r : miny;
+            }
+            nan_guard += ccx + ccy;
+        }
+    }
+    const double pad = 1e-9 * (((fabs(minx) + fabs(maxx)) + (fabs(miny) + fabs(maxy))) + (fabs(r) + 1.0)) + 0.0 * nan_guard;
+    box[0] = minx - pad;
+    box[1] = miny - pad;
+    box[2] = maxx + pad;
+    box[3] = maxy + pad;
 }
 
 // local-frame sample of output slot k (1 <= k <= n0+n1+n2)

@@ -58,6 +58,48 @@ def test_c5_edges_default_equals_exhaustive_loop(ctx, pp, O):
     check_dubins_verdicts(O, W, ok[sub], sx[sub], sy[sub], syaw[sub], ex[sub], ey[sub], eyaw[sub], 1.0, 0.05)
 
 
+@pytest.mark.parametrize("radius,step,n_rings", [(1.0, 0.1, 10_000), (0.4, 0.05, 40_000), (3.0, 0.2, 2_000)])
+def test_short_dubins_edges_path_box_equals_exhaustive_loop(ctx, pp, O, radius, step, n_rings):
+    """the verify kernel dismisses a whole Dubins edge when nothing is registered under the path's bounding box
+    (pp_path_box / pp_path_box_free): exercised where it fires -- extend-step edges (query -> nearest tree node, a few
+    turn radii long) -- against PP_COLLIDE_NO_CULL on the same device-generated samples (byte-equal), against the
+    oracle on a sub-sample, and on edges hugging the bounds and pointing out of them."""
+    m = 1 << 16
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(m, 1 << 18)
+    bounds, rings = pp.synth.circle_world(n_rings)
+    ctx.tree_upload(nx, ny, nyaw)
+    ctx.obstacles_upload(bounds, rings)
+    idx = ctx.nn(qx, qy)[0]
+    sx, sy = qx, qy                                   # new node -> its parent, yaw aimed at the parent (src/rrt.rs:267-271)
+    ex, ey, eyaw = nx[idx], ny[idx], nyaw[idx]
+    syaw = np.arctan2(ey - sy, ex - sx)
+    ok = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, radius, step)
+    ok_all = ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, radius, step, flags=NO_CULL)
+    assert np.array_equal(ok, ok_all)
+    assert 0.2 < ok.mean() < 0.999
+    W = O.OracleWorld(bounds, rings)
+    sub = np.arange(0, m, 97)
+    check_dubins_verdicts(O, W, ok[sub], sx[sub], sy[sub], syaw[sub], ex[sub], ey[sub], eyaw[sub], radius, step)
+    # edges whose loops leave the bounds: start poses within a turn radius of the border, heading outward
+    lo_x, hi_x, lo_y, hi_y = bounds[0].min(), bounds[0].max(), bounds[1].min(), bounds[1].max()
+    rng = np.random.default_rng(77)
+    k = 4096
+    t = rng.uniform(0.0, 1.0, k)
+    side = rng.integers(0, 4, k)
+    off = rng.uniform(0.0, 2.5 * radius, k)
+    sx2 = np.where(side == 0, lo_x + off, np.where(side == 1, hi_x - off, lo_x + t * (hi_x - lo_x)))
+    sy2 = np.where(side == 2, lo_y + off, np.where(side == 3, hi_y - off, lo_y + t * (hi_y - lo_y)))
+    syaw2 = rng.uniform(-math.pi, math.pi, k)
+    ex2 = np.clip(sx2 + rng.uniform(-2, 2, k) * radius, lo_x + 1e-3, hi_x - 1e-3)
+    ey2 = np.clip(sy2 + rng.uniform(-2, 2, k) * radius, lo_y + 1e-3, hi_y - 1e-3)
+    eyaw2 = rng.uniform(-math.pi, math.pi, k)
+    a = ctx.collide_dubins(sx2, sy2, syaw2, ex2, ey2, eyaw2, radius, step)
+    b = ctx.collide_dubins(sx2, sy2, syaw2, ex2, ey2, eyaw2, radius, step, flags=NO_CULL)
+    assert np.array_equal(a, b) and 0.02 < a.mean() < 0.98
+    sub = np.arange(0, k, 13)
+    check_dubins_verdicts(O, W, a[sub], sx2[sub], sy2[sub], syaw2[sub], ex2[sub], ey2[sub], eyaw2[sub], radius, step)
+
+
 def test_near_parallel_extensions(ctx, pp, O):
     """the adversarial class of DESIGN section 3 (ii): PP_COLLIDE_NO_CULL must reproduce geo's exhaustive answer bit
     for bit (rounding noise included), every culled path must reproduce the oracle's culled answer, and the two differ
