@@ -747,7 +747,8 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
         "config": {"workload": f"c5 slice: {e} Dubins edges/GPU (2^22 over 8 GPUs), step 0.05, radius 1.0, vs {C5_RINGS} rings",
                    "free_fraction_rank0": float(ok5.float().mean().item())},
     }
-    # same edges against the no-hit ring set: no early exit, every sample segment is generated and tested
+    # same edges against the no-hit ring set: no early exit; every sample segment of a path whose bounding box is too
+    # large for the path-level test (pp_path_box_free: most C5 edges) is generated and tested
     _, rings6 = pp.synth.circle_world(C5_RINGS, rmin=0.5, rmax=1.5, shift=5000.0)
     bx = np.array([-100.0, -100.0, 1100.0, 1100.0, -100.0])
     ctx.obstacles_upload((bx, np.array([-100.0, 1100.0, 1100.0, -100.0, -100.0])), rings6)
@@ -761,7 +762,8 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
     out["dubins_rrt_nohit"] = {
         "metric": "dubins_edges_verified_per_s", "value": world * e * steps / (ms * 1e-3), "unit": "edges/s",
         "ms_per_step": ms / steps, "verify_kernel_ms": v_ms / max(v_n, 1),
-        "config": {"workload": "c5 slice against rings translated outside the (enlarged) bounds: every sample is tested",
+        "config": {"workload": "c5 slice against rings translated outside the (enlarged) bounds: no early exit; every sample of the paths "
+                                "too long for the path-level box test is generated and tested",
                    "free_fraction_rank0": float(ok5.float().mean().item())},
     }
     # ---- sample materialisation (config-1 style paths in bulk): count -> prefix sum -> fill

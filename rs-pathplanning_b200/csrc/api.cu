@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "geo_predicates.cuh"
@@ -46,6 +47,11 @@ int pp_launch_extend_gather(pp_ctx *, size_t, const double *, const double *, co
 
 #define PP_AABB_TILE 1024
 #define PP_BOUNDS_GRID 256
+#ifndef PP_GRID_CELL_SCALE_DEFAULT
+#define PP_GRID_CELL_SCALE_DEFAULT 0.5  // obstacle-grid cell edge in units of sqrt(area / rings); swept on the GPU
+                                        // (profiles/r03_grid_sweep.txt): 1.0 -> 0.5 takes the C5 slice from 1.36 to 1.29 ms
+                                        // and the C4 straight-edge verify from 0.114 to 0.105 ms; 0.25 loses again
+#endif
 #define PP_SCAN_TILE_ITEMS 2048
 
 // ---------------------------------------------------------------------------------------------------
@@ -864,8 +870,13 @@ int pp_obstacles_upload(pp_ctx *ctx, const double *bounds_x, const double *bound
     double cell = 1.0, ginv = 1.0, g0x = 0.0, g0y = 0.0;
     if (n_fin) {
         const double gw = std::max(wmaxx - wminx, 1e-300), gh = std::max(wmaxy - wminy, 1e-300);
-        cell = std::sqrt(gw * gh / (double)n_fin);
-        cell = std::max(cell, 0.75 * ext_sum / (double)n_fin);
+        // tuning knobs (developer A/B, read at upload): PP_GRID_CELL_SCALE scales the "one ring per cell" edge,
+        // PP_GRID_EXT_SCALE the floor of 0.75 mean ring extents
+        double cs = PP_GRID_CELL_SCALE_DEFAULT, es = 0.75;
+        if (const char *e = getenv("PP_GRID_CELL_SCALE")) cs = atof(e) > 0.0 ? atof(e) : cs;
+        if (const char *e = getenv("PP_GRID_EXT_SCALE")) es = atof(e) > 0.0 ? atof(e) : es;
+        cell = cs * std::sqrt(gw * gh / (double)n_fin);
+        cell = std::max(cell, es * ext_sum / (double)n_fin);
         cell = std::max(cell, std::max(gw, gh) / 2048.0);
         if (!(cell > 0.0) || !std::isfinite(cell)) cell = std::max(gw, gh);
         ginv = 1.0 / cell;

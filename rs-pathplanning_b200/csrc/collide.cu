@@ -825,8 +825,9 @@ static __device__ __noinline__ void pp_poly_tables_init(const pp_dubins_plan &pl
 // "inside" and (ii) no ring registered under the box's cells of the obstacle grid has an fp32 box that meets the
 // box -- then no sample can fail its own bounds test and no sample segment can find a candidate ring in its own walk
 // (its cells and its fp32 box are subsets of the path's), so the per-sample loop would return "free": the same
-// verdict without generating a single sample.  Applies to boxes of at most 32 bounds cells and 8 x 8 obstacle cells
-// (short edges: the extend step); long paths go straight to the per-sample loop.  All 32 lanes call together.
+// verdict without generating a single sample.  Applies to boxes of at most 32 bounds cells and PP_PATH_BOX_CELLS^2
+// obstacle cells (short edges: the extend step); long paths go straight to the per-sample loop.  All 32 lanes call
+// together.
 #ifndef PP_POLY_PATH_BOX
 #define PP_POLY_PATH_BOX 1  // A/B switch
 #endif
@@ -851,7 +852,7 @@ __device__ __forceinline__ bool pp_path_box_free(const pp_world_view &w, double 
     cy0 = max(cy0, 0);
     cx1 = min(cx1, w.gx - 1);
     cy1 = min(cy1, w.gy - 1);
-    if (cx1 - cx0 >= 8 || cy1 - cy0 >= 8) return false;
+    if (cx1 - cx0 >= PP_PATH_BOX_CELLS || cy1 - cy0 >= PP_PATH_BOX_CELLS) return false;
     const float q0x = __double2float_rd(x0), q0y = __double2float_rd(y0), q1x = __double2float_ru(x1), q1y = __double2float_ru(y1);
     for (int r = cy0; r <= cy1; ++r) {
         const uint32_t *row = w.cell_start + (size_t)r * w.gx;

@@ -421,12 +421,12 @@ int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double 
     if (n == 0) return PP_OK;
     pp_launch_scope scope(ctx, "dubins_plan");
     // largest box extent the verify kernel's path-level test accepts (collide.cu: pp_path_box_free -- at most 32 cells of
-    // the bounds grid, 8 x 8 cells of the obstacle grid); 0 without a world or without an aux record
+    // the bounds grid, PP_PATH_BOX_CELLS^2 cells of the obstacle grid); 0 without a world or without an aux record
     double box_limit = 0.0;
     if (aux && ctx->world.valid) {
         const pp_world_dev &w = ctx->world;
         box_limit = std::min(32.0 / w.binvx, 32.0 / w.binvy);
-        if (w.n_rings) box_limit = std::min(box_limit, 9.0 * w.gcell);
+        if (w.n_rings) box_limit = std::min(box_limit, (PP_PATH_BOX_CELLS + 1.0) * w.gcell);
         if (!(box_limit > 0.0)) box_limit = 0.0;
     }
     pp_dubins_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius, step,

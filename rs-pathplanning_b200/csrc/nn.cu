@@ -16,6 +16,8 @@
 //                       split the nodes of one query, per-thread running minimum, warp-shuffle
 //                       argmin with lowest-index tie-break, last CTA reduces the partials.
 //   pp_nn_grid_kernel   exact ring-expanding search over a uniform grid of the nodes.
+#include <cstdlib>
+
 #include "nn_grid.cuh"
 #include "pp_common.cuh"
 
@@ -802,13 +804,19 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+#ifndef PP_NN_GRID_OCC_DEFAULT
+#define PP_NN_GRID_OCC_DEFAULT 2.0
+#endif
 int pp_tree_build_grid(pp_ctx *ctx, cudaStream_t stream) {
     pp_tree_dev &t = ctx->tree;
     if (t.grid_n == t.n) return PP_OK;
     ctx->grid_builds += 1;
     const size_t n = t.n;
     // geometry: ~2 nodes per cell, square cells over the bounding box of the finite nodes
-    long g = (long)floor(sqrt((double)(n > 1 ? n : 1) / 2.0));
+    // (PP_NN_GRID_OCC: developer knob for the nodes-per-cell target, read at build time)
+    double occ = PP_NN_GRID_OCC_DEFAULT;
+    if (const char *e = getenv("PP_NN_GRID_OCC")) occ = atof(e) > 0.0 ? atof(e) : occ;
+    long g = (long)floor(sqrt((double)(n > 1 ? n : 1) / occ));
     g = g < 1 ? 1 : (g > 4095 ? 4095 : g);  // (g + 1)^2 cells <= 1 024 scan blocks
     const size_t max_cells = (size_t)(g + 1) * (size_t)(g + 1);
     int rc = pp_scratch_reserve(ctx, 64 + 4096 + max_cells * 4);
