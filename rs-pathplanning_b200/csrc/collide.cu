@@ -742,84 +742,6 @@ struct pp_points_dubins {
     const double *ex, *ey;  // parent point appended after the samples
 };
 
-// ---- Dubins samples for the verify kernel: table-driven, in the world frame (dubins_device.cuh: pp_seg_world,
-// pp_arc_coef).  Sample j of a segment is split as j = 32 c + l; the chunk (segment, c) contributes four coefficients
-// (one sincos per chunk, computed by ONE lane when the warp takes up the path), l contributes (cos, sin)(l * step)
-// from a 32-entry table that only changes with the step, and the sample is two fused multiply-adds per coordinate:
-//     x = X0 + u Px + v Qx        (arc: (u, v) = (cos, sin)(l step);   straight: (u, v) = (1, l), X0 = 0)
-// The default form (pp_plan_sample_local + pp_local_to_world: one sincos and two rotations per sample) spends ~60 of
-// the ~200 warp instructions of a 32-sample chunk here.  Paths longer than 32 chunks slide a 32-entry window.
-#ifndef PP_POLY_TABLES
-#define PP_POLY_TABLES 0  // A/B switch, 1 = the table-driven form.  MEASURED AND NOT ADOPTED (profiles/r02_summary.md section 10):
-                          // extend_dubins 2.01 ms against 1.83, C5 slice 1.61 against 1.45, no-hit 3.50 against 3.40 -- the
-                          // per-sample sincos overlaps with the cell walk's load latency, the per-path table set-up does not
-#endif
-struct pp_poly_tables {
-    pp_arc_coef coef[32];  // window of chunk coefficients, entry index = first[seg] + c - w0
-    double2 uv[64];        // [l] = (cos, sin)(l * step); [32 + l] = (1, l)
-    double2 x0y0[3];       // per segment: (X0, Y0) of an arc, (0, 0) of a straight segment
-    pp_seg_world segw[3];
-    uint32_t first[4];     // first entry of each segment; first[3] = number of entries of the path
-    double step;           // step the uv table was made for (NaN before the first path)
-};
-
-// entry `idx` of the path's chunk table
-__device__ __forceinline__ pp_arc_coef pp_poly_entry(const pp_dubins_plan &pl, const pp_poly_tables &t, uint32_t idx) {
-    const int seg = (idx >= t.first[2]) ? 2 : ((idx >= t.first[1]) ? 1 : 0);
-    const uint32_t c = idx - t.first[seg];
-    const double d = (pl.len[seg] > 0.0) ? pl.step : -pl.step;
-    const double A = pl.pd0[seg] + (double)(32u * c) * d;
-    const pp_seg_world &sw = t.segw[seg];
-    pp_arc_coef k;
-    if (pp_word_mode(pl.word, seg) == PP_MODE_S) {
-        pp_line_sample(sw, A, &k.Px, &k.Py);
-        k.Qx = d * sw.Cr;
-        k.Qy = d * sw.Sr;
-    } else {
-        k = pp_arc_coef_make(sw, A);
-        if (!(d > 0.0)) {  // l counts steps of -step: sin(l d) = -sin(l step)
-            k.Qx = -k.Qx;
-            k.Qy = -k.Qy;
-        }
-    }
-    return k;
-}
-
-// the warp takes up a path: segment constants by lanes 0-2, the (cos, sin)(l step) table when the step changed, the
-// first 32 chunk entries one per lane.
-// (out of line on purpose: run once per path, and inlining its sincos twice into the kernel costs the chunk loop registers)
-static __device__ __noinline__ void pp_poly_window_fill(const pp_dubins_plan &pl, pp_poly_tables &t, uint32_t w0, int lane) {
-    __syncwarp();
-    if (w0 + (uint32_t)lane < t.first[3]) t.coef[lane] = pp_poly_entry(pl, t, w0 + (uint32_t)lane);
-    __syncwarp();
-}
-static __device__ __noinline__ void pp_poly_tables_init(const pp_dubins_plan &pl, const pp_plan_aux &aux, pp_poly_tables &t,
-                                                        int lane) {
-    if (lane < 3) {
-        const int mode = pp_word_mode(pl.word, lane);
-        const pp_seg_origin &o = aux.o[lane];
-        const pp_seg_world sw = pp_seg_world_make(aux.ss, aux.cs, pl.sx, pl.sy, o.ox, o.oy, o.so, o.co, pl.rinv, mode);
-        t.segw[lane] = sw;
-        t.x0y0[lane] = (mode == PP_MODE_S) ? make_double2(0.0, 0.0) : make_double2(sw.X0, sw.Y0);
-    }
-    if (lane == 3) {
-        const uint32_t c0 = (pl.n[0] + 31u) >> 5, c1 = (pl.n[1] + 31u) >> 5, c2 = (pl.n[2] + 31u) >> 5;
-        t.first[0] = 0u;
-        t.first[1] = c0;
-        t.first[2] = c0 + c1;
-        t.first[3] = c0 + c1 + c2;
-    }
-    if (pl.step != t.step) {  // warp-uniform (true for a NaN: the first path of the warp)
-        double sB, cB;
-        pp_sincos1((double)lane * pl.step, &sB, &cB);
-        t.uv[lane] = make_double2(cB, sB);
-        t.uv[32 + lane] = make_double2(1.0, (double)lane);
-        __syncwarp();
-        if (lane == 0) t.step = pl.step;
-    }
-    pp_poly_window_fill(pl, t, 0u, lane);
-}
-
 // ---- path-level test of the Dubins verify kernel.  `box` = the plan kernel's bounding box of every point of the path
 // and of the parent point (pp_path_box).  True when (i) every cell of the bounds classification grid under the box is
 // "inside" and (ii) no ring registered under the box's cells of the obstacle grid has an fp32 box that meets the
@@ -870,6 +792,81 @@ __device__ __forceinline__ bool pp_path_box_free(const pp_world_view &w, double 
     return true;
 }
 
+// ---- coarse pass of the Dubins verify kernel (paths of several chunks).  Lane L takes the FIRST point of chunk L of a
+// batch of 31 chunks (a chunk = 32 consecutive points = 31 line segments) and its neighbour's first point = the
+// chunk's last point.  Consecutive samples are one step of path length apart, three across a segment junction
+// (src/dubins.rs:233-237: pd0 = d - ll or -d - ll with ll in [-2d, -d)), so every point of the chunk lies on a curve
+// of length <= S = 40 steps between the two end points (31 gaps; a junction next to a zero-length segment can add up to 4): inside the ellipse with these foci and major axis S, hence
+// inside the end points' box grown by h = sqrt(S^2 - c^2) / 2 (c = distance of the end points).  A chunk whose grown box
+// (i) lies in "inside" cells of the bounds grid and (ii) meets no registered ring box cannot fail any of its own
+// tests: it is skipped.  Before that (phase 1), the chunks' first points are actual polyline vertices: one outside the
+// bounds or inside a ring's inner circle (pp_circle_class == 1, exact by margin) blocks the path at once -- in a dense
+// world (C5: a quarter of the plane is covered) some coarse vertex nearly always is, and the path is decided without a
+// fine pass.  Vertices in a ring's annulus and everything a box meets are left to the fine pass of that chunk.
+#ifndef PP_POLY_COARSE
+#define PP_POLY_COARSE 1  // A/B switch
+#endif
+#define PP_COARSE_MIN_POINTS (4u * 31u + 2u)  // below this a path goes straight to the fine pass
+// phase 1: does the vertex (x, y) block the path on its own?  (outside the bounds, or inside the inner circle of a ring
+// registered in its cell -- a ring is registered in every cell its padded box meets, so the vertex's cell knows every
+// ring that can contain it)
+__device__ __forceinline__ bool pp_coarse_vertex_blocked(const pp_world_view &w, double x, double y) {
+    if (!pp_bounds_contains(w, x, y)) return true;
+    if (w.n_rings == 0u) return false;
+    const int cx = __double2int_rd((x - w.gminx) * w.ginv), cy = __double2int_rd((y - w.gminy) * w.ginv);
+    if ((unsigned)cx >= (unsigned)w.gx || (unsigned)cy >= (unsigned)w.gy) return false;
+    const uint32_t *cell = w.cell_start + (size_t)cy * w.gx + cx;
+    const uint32_t k1 = __ldg(cell + 1);
+    const float px0 = __double2float_rd(x), px1 = __double2float_ru(x), py0 = __double2float_rd(y), py1 = __double2float_ru(y);
+    for (uint32_t k = __ldg(cell); k < k1; ++k) {
+        const float4 bb = __ldg(w.cell_box + k);
+        if (!(px1 < bb.x || px0 > bb.z || py1 < bb.y || py0 > bb.w) &&
+            pp_ring_circle_class(w, __ldg(w.cell_items + k), x, y, x, y) == 1)
+            return true;
+    }
+    return false;
+}
+// phase 2: does the chunk between (x, y) and (xn, yn) need the fine pass?  (its grown box leaves the "inside" cells of the
+// bounds grid or meets a registered ring box)
+__device__ __forceinline__ bool pp_coarse_chunk_flag(const pp_world_view &w, double x, double y, double xn, double yn, double S2) {
+    const double dx = xn - x, dy = yn - y;
+    const double c2 = dx * dx + dy * dy;
+    const double t = S2 - c2;
+    const double pad = 1e-9 * ((fabs(x) + fabs(y)) + 1.0);
+    const double h = 0.5 * sqrt(t > 0.0 ? t : 0.0) + pad;
+    const bool swx = xn < x, swy = yn < y;
+    const double x0 = (swx ? xn : x) - h, x1 = (swx ? x : xn) + h, y0 = (swy ? yn : y) - h, y1 = (swy ? y : yn) + h;
+    if (!((x1 - x0) < 1e300 && (y1 - y0) < 1e300)) return true;  // NaN / inf: the fine pass decides
+    {   // (i) bounds cells under the box
+        const int ix0 = __double2int_rd((x0 - w.bminx) * w.binvx), iy0 = __double2int_rd((y0 - w.bminy) * w.binvy);
+        const int ix1 = __double2int_rd((x1 - w.bminx) * w.binvx), iy1 = __double2int_rd((y1 - w.bminy) * w.binvy);
+        if (ix0 < 0 || iy0 < 0 || ix1 >= w.bgx || iy1 >= w.bgy || ix1 - ix0 > 3 || iy1 - iy0 > 3) return true;
+        for (int iy = iy0; iy <= iy1; ++iy)
+            for (int ix = ix0; ix <= ix1; ++ix)
+                if (__ldg(w.bcls + (size_t)iy * w.bgx + ix) != 1) return true;
+    }
+    if (w.n_rings == 0u) return false;
+    // (ii) rings registered under the box
+    int cx0 = __double2int_rd((x0 - w.gminx) * w.ginv), cy0 = __double2int_rd((y0 - w.gminy) * w.ginv);
+    int cx1 = __double2int_rd((x1 - w.gminx) * w.ginv), cy1 = __double2int_rd((y1 - w.gminy) * w.ginv);
+    if (cx1 < 0 || cy1 < 0 || cx0 >= w.gx || cy0 >= w.gy) return false;
+    cx0 = max(cx0, 0);
+    cy0 = max(cy0, 0);
+    cx1 = min(cx1, w.gx - 1);
+    cy1 = min(cy1, w.gy - 1);
+    if (cx1 - cx0 > 7 || cy1 - cy0 > 7) return true;  // a huge step: no coarse decision
+    const float q0x = __double2float_rd(x0), q0y = __double2float_rd(y0), q1x = __double2float_ru(x1), q1y = __double2float_ru(y1);
+    for (int r = cy0; r <= cy1; ++r) {
+        const uint32_t *row = w.cell_start + (size_t)r * w.gx;
+        const uint32_t k1 = __ldg(row + cx1 + 1);
+        for (uint32_t k = __ldg(row + cx0); k < k1; ++k) {
+            const float4 bb = __ldg(w.cell_box + k);
+            if (!(q1x < bb.x || q0x > bb.z || q1y < bb.y || q0y > bb.w)) return true;
+        }
+    }
+    return false;
+}
+
 #define PP_POLY_THREADS 128
 #ifndef PP_POLY_MIN_BLOCKS
 #define PP_POLY_MIN_BLOCKS 7  // 72 registers; round 2 (circle filter, cell-ordered boxes): C5 slice / Dubins extend / no-hit 1.56 / 1.98 / 3.35 ms
@@ -884,14 +881,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = (int)(tid & 31u), wib = (int)(tid >> 5);
     const size_t warps_total = (size_t)gridDim.x * (PP_POLY_THREADS / 32);
-#if PP_POLY_TABLES
-    __shared__ __align__(16) pp_poly_tables s_tab[DUBINS ? PP_POLY_THREADS / 32 : 1];
-    pp_poly_tables &tab = s_tab[DUBINS ? wib : 0];
-    if (DUBINS) {  // no (cos, sin)(l step) table yet
-        if (lane == 0) tab.step = CUDART_NAN;
-        __syncwarp();
-    }
-#endif
     for (size_t line = (size_t)blockIdx.x * (PP_POLY_THREADS / 32) + wib; line < n_lines; line += warps_total) {
         uint32_t np;      // points of this polyline
         uint32_t base = 0;
@@ -902,11 +891,7 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
         __shared__ pp_plan_aux s_aux[PP_POLY_THREADS / 32];
         const pp_dubins_plan &pl = s_plan[wib];
         const pp_plan_aux &aux = s_aux[wib];
-#if PP_POLY_TABLES
-        uint32_t w0 = 0;  // first entry of the coefficient window
-#else
         const pp_seg_origin *o = s_aux[wib].o;
-#endif
         uint32_t nsamp = 0;
         if (DUBINS) {
             __syncwarp();  // every lane is done with the previous polyline's record
@@ -944,12 +929,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 (void)bx0; (void)by0; (void)bx1; (void)by1;
 #endif
             }
-#if PP_POLY_TABLES
-            if (nsamp > 1u) {
-                pp_poly_tables_init(pl, aux, tab, lane);
-                w0 = 0u;
-            }
-#endif
         } else {
             base = csr.off[line];
             np = csr.off[line + 1] - base;
@@ -959,51 +938,60 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             if (lane == 0) ok[line] = 1;
             continue;
         }
-        for (uint32_t k0 = 0; k0 == 0 || k0 + 1 < np; k0 += 31) {
+        // point k of a Dubins polyline: 0 = the start pose, 1 .. nsamp - 1 = samples, nsamp = the parent point.  Every
+        // lane evaluates a (clamped) sample slot, then the two special points are patched in: no divergence between
+        // the lanes of a chunk except where a chunk straddles a segment junction
+        auto dubins_point = [&](uint32_t k, double &x, double &y) {
+            if (nsamp > 1u) {  // uniform; implies a feasible word
+                const uint32_t kk = min(max(k, 1u), nsamp - 1u);
+                double lx, ly, lyaw;
+                pp_plan_sample_local(pl, o, kk, &lx, &ly, &lyaw);
+                pp_local_to_world(aux.ss, aux.cs, pl.sx, pl.sy, lx, ly, &x, &y);
+            }
+            if (k == 0u) {  // slot 0 is exactly the start pose (0*cos + 0*sin + sx)
+                x = pl.sx;
+                y = pl.sy;
+            }
+            if (k == nsamp) {  // the parent point closes the polyline (one lane of the last chunk)
+                x = __ldg(dub.ex + line);
+                y = __ldg(dub.ey + line);
+            }
+        };
+        // chunks are taken in batches of 31; bit c of `todo` = chunk c of the batch needs the fine pass
+        const uint32_t n_chunks = (np <= 2u) ? 1u : (np + 29u) / 31u;  // chunk c: points 31 c .. 31 c + 31, while 31 c + 1 < np
+#if PP_POLY_COARSE
+        const bool coarse = DUBINS && CULL && nsamp > 1u && np >= PP_COARSE_MIN_POINTS;
+#else
+        const bool coarse = false;
+#endif
+        for (uint32_t c0 = 0; c0 < n_chunks && !bad; c0 += 31u) {
+        const uint32_t n_batch = min(31u, n_chunks - c0);
+        uint32_t todo = (n_batch >= 32u) ? 0xFFFFFFFFu : ((1u << n_batch) - 1u);
+        if (coarse) {
+            double x = 0.0, y = 0.0;
+            dubins_point(min(31u * (c0 + (uint32_t)lane), np - 1u), x, y);
+            const double xn = __shfl_down_sync(0xffffffffu, x, 1), yn = __shfl_down_sync(0xffffffffu, y, 1);
+            // path length between the first and the last point of a chunk: 31 steps, up to 6 more across junctions with a zero-length segment, and slack
+            const double S = 40.0 * pl.step * pl.rinv * (1.0 + 1e-9);
+            // lanes 0 .. n_batch hold actual vertices (lane n_batch: the end point of the batch's last chunk)
+            const bool blocked = (uint32_t)lane <= n_batch && pp_coarse_vertex_blocked(w, x, y);
+            if (__ballot_sync(0xffffffffu, blocked) != 0u) {
+                bad = true;
+                break;
+            }
+            // a chunk's box is tested unless the chunk is the path's last one (its tail is the parent point, off the
+            // curve): that one always takes the fine pass
+            bool fine = (uint32_t)lane < n_batch;
+            if (fine && c0 + (uint32_t)lane + 1u < n_chunks) fine = pp_coarse_chunk_flag(w, x, y, xn, yn, S * S);
+            todo &= __ballot_sync(0xffffffffu, fine);
+        }
+        for (; todo != 0u; todo &= todo - 1u) {
+            const uint32_t k0 = 31u * (c0 + (uint32_t)__ffs((int)todo) - 1u);
             const uint32_t k = k0 + lane;
             double x = 0.0, y = 0.0;
             const bool have = k < np;
             if (DUBINS) {
-                // every lane evaluates a (clamped) sample slot, then the two special points are patched in: no
-                // divergence between the lanes of a chunk except where a chunk straddles a segment junction
-                if (nsamp > 1u) {  // uniform; implies a feasible word
-                    const uint32_t kk = min(max(k, 1u), nsamp - 1u);
-#if PP_POLY_TABLES
-                    uint32_t j = kk - 1u;
-                    int seg = 0;
-                    if (j >= pl.n[0]) {
-                        j -= pl.n[0];
-                        seg = 1;
-                        if (j >= pl.n[1]) {
-                            j -= pl.n[1];
-                            seg = 2;
-                        }
-                    }
-                    const uint32_t e = tab.first[seg] + (j >> 5);
-                    if (__any_sync(0xffffffffu, e >= w0 + 32u)) {  // slide the window (lane 0 holds the lowest entry)
-                        w0 = __shfl_sync(0xffffffffu, e, 0);
-                        pp_poly_window_fill(pl, tab, w0, lane);
-                    }
-                    const pp_arc_coef kc = tab.coef[e - w0];
-                    // straight segments: the middle one of the four CSC words (src/dubins.rs:26-113)
-                    const double2 uv = tab.uv[(j & 31u) + ((seg == 1 && pl.word < PP_RLR) ? 32u : 0u)];
-                    const double2 c0 = tab.x0y0[seg];
-                    x = fma(uv.x, kc.Px, fma(uv.y, kc.Qx, c0.x));
-                    y = fma(uv.x, kc.Py, fma(uv.y, kc.Qy, c0.y));
-#else
-                    double lx, ly, lyaw;
-                    pp_plan_sample_local(pl, o, kk, &lx, &ly, &lyaw);
-                    pp_local_to_world(aux.ss, aux.cs, pl.sx, pl.sy, lx, ly, &x, &y);
-#endif
-                }
-                if (k == 0u) {  // slot 0 is exactly the start pose (0*cos + 0*sin + sx)
-                    x = pl.sx;
-                    y = pl.sy;
-                }
-                if (k == nsamp) {  // the parent point closes the polyline (one lane of the last chunk)
-                    x = __ldg(dub.ex + line);
-                    y = __ldg(dub.ey + line);
-                }
+                dubins_point(k, x, y);
             } else if (have) {
                 x = csr.px[base + k];
                 y = csr.py[base + k];
@@ -1169,6 +1157,7 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 if (bad) break;
             }
             if (bad) break;
+        }
         }
         if (lane == 0) ok[line] = bad ? 0 : 1;
     }
