@@ -99,7 +99,9 @@ int pp_ctx_device(pp_ctx *ctx);
 int pp_ctx_sm_count(pp_ctx *ctx);
 /* the cudaStream_t all _dev calls are enqueued on (for event timing by the caller) */
 void *pp_ctx_stream(pp_ctx *ctx);
-/* run the _dev calls on a caller-owned cudaStream_t instead (NULL restores the ctx's own stream) */
+/* run the _dev calls on a caller-owned cudaStream_t instead (NULL restores the ctx's own stream).  A context keeps
+ * small device-side scratch (last-block tickets, the work counter of the sample fill): calls of ONE context must stay
+ * ordered -- when switching streams, order the new stream after the old one (event / pp_sync) before the next call. */
 int pp_ctx_set_stream(pp_ctx *ctx, void *cuda_stream);
 int pp_sync(pp_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */

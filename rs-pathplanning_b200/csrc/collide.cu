@@ -792,11 +792,14 @@ __device__ __forceinline__ bool pp_path_box_free(const pp_world_view &w, double 
     return true;
 }
 
-// ---- coarse pass of the Dubins verify kernel (paths of several chunks).  Lane L takes the FIRST point of chunk L of a
-// batch of 31 chunks (a chunk = 32 consecutive points = 31 line segments) and its neighbour's first point = the
-// chunk's last point.  Consecutive samples are one step of path length apart, three across a segment junction
-// (src/dubins.rs:233-237: pd0 = d - ll or -d - ll with ll in [-2d, -d)), so every point of the chunk lies on a curve
-// of length <= S = 40 steps between the two end points (31 gaps; a junction next to a zero-length segment can add up to 4): inside the ellipse with these foci and major axis S, hence
+// ---- coarse pass of the Dubins verify kernel (paths of several chunks, all three segment lengths positive).  Lane L
+// takes the FIRST point of chunk L of a batch of 31 chunks (a chunk = 32 consecutive points = 31 line segments) and its
+// neighbour's first point = the chunk's last point.  With three positive lengths consecutive samples are exactly one
+// step of path length apart, also across the junctions (src/dubins.rs:233-237: the next segment's first `pd` is the
+// previous overshoot, -d - ll), and all of them lie ON the path (0 < pd <= l) -- a word with a zero-length segment is
+// different (samples up to five steps off a segment's ends, even behind the start pose) and takes the fine pass only.
+// So every point of the chunk lies on a curve of length <= S = 31.5 steps between the two end points: inside the
+// ellipse with these foci and major axis S, hence
 // inside the end points' box grown by h = sqrt(S^2 - c^2) / 2 (c = distance of the end points).  A chunk whose grown box
 // (i) lies in "inside" cells of the bounds grid and (ii) meets no registered ring box cannot fail any of its own
 // tests: it is skipped.  Before that (phase 1), the chunks' first points are actual polyline vertices: one outside the
@@ -960,7 +963,9 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
         // chunks are taken in batches of 31; bit c of `todo` = chunk c of the batch needs the fine pass
         const uint32_t n_chunks = (np <= 2u) ? 1u : (np + 29u) / 31u;  // chunk c: points 31 c .. 31 c + 31, while 31 c + 1 < np
 #if PP_POLY_COARSE
-        const bool coarse = DUBINS && CULL && nsamp > 1u && np >= PP_COARSE_MIN_POINTS;
+        // (three positive lengths: a zero-length segment breaks the one-step spacing the chunk boxes rely on, see above)
+        const bool coarse = DUBINS && CULL && nsamp > 1u && np >= PP_COARSE_MIN_POINTS && pl.len[0] > 0.0 &&
+                            pl.len[1] > 0.0 && pl.len[2] > 0.0;
 #else
         const bool coarse = false;
 #endif
@@ -971,8 +976,9 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             double x = 0.0, y = 0.0;
             dubins_point(min(31u * (c0 + (uint32_t)lane), np - 1u), x, y);
             const double xn = __shfl_down_sync(0xffffffffu, x, 1), yn = __shfl_down_sync(0xffffffffu, y, 1);
-            // path length between the first and the last point of a chunk: 31 steps, up to 6 more across junctions with a zero-length segment, and slack
-            const double S = 40.0 * pl.step * pl.rinv * (1.0 + 1e-9);
+            // path length between the first and the last point of a chunk: 31 gaps of exactly one step (half a step
+            // of slack for the rounding of the `pd` values)
+            const double S = 31.5 * pl.step * pl.rinv;
             // lanes 0 .. n_batch hold actual vertices (lane n_batch: the end point of the batch's last chunk)
             const bool blocked = (uint32_t)lane <= n_batch && pp_coarse_vertex_blocked(w, x, y);
             if (__ballot_sync(0xffffffffu, blocked) != 0u) {

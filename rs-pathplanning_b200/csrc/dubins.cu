@@ -237,7 +237,12 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
                 // the verify kernel can only use boxes below `box_limit` in either extent (its cell-count caps, set by
                 // the launcher from the world's grids); the start-to-goal offset is a lower bound of the extent, so
                 // long edges (C5) skip the computation and carry a NaN box
-                if (fabs(ex - sx) < box_limit && fabs(ey - sy) < box_limit)
+                // A word with a zero-length segment gets no box either: there the reference's index arithmetic puts
+                // samples up to five steps off a segment's ends, even BEHIND the start pose (l = 0 makes d negative
+                // and the carried `ll` positive, src/dubins.rs:228-237), so "every point lies on the three segments"
+                // does not hold.  With three positive lengths every first `pd` is the previous overshoot in (0, d].
+                if (fabs(ex - sx) < box_limit && fabs(ey - sy) < box_limit && pl.len[0] > 0.0 && pl.len[1] > 0.0 &&
+                    pl.len[2] > 0.0)
                     pp_path_box(pl, o, aux->ss, aux->cs, gx, gy, from_origin ? pl.sx : ex, from_origin ? pl.sy : ey, box);
                 else
                     box[0] = box[1] = box[2] = box[3] = CUDART_NAN;
