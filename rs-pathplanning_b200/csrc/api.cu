@@ -19,7 +19,8 @@ int pp_launch_dubins_words(pp_ctx *, size_t, const double *, const double *, con
                            cudaStream_t);
 int pp_launch_mod2pi(pp_ctx *, size_t, const double *, double *, int, cudaStream_t);
 int pp_launch_dubins_plan(pp_ctx *, size_t, const double *, const double *, const double *, const double *,
-                          const double *, const double *, double, double, int, uint32_t *, void *, void *, cudaStream_t);
+                          const double *, const double *, double, double, int, uint32_t *, void *, void *, cudaStream_t,
+                          uint8_t *ok = nullptr, uint32_t *todo = nullptr, unsigned int *todo_count = nullptr);
 int pp_launch_dubins_fill(pp_ctx *, size_t, const void *, const uint64_t *, double *, cudaStream_t);
 int pp_launch_dubins_path(pp_ctx *, double, double, double, double, double, double, double, double, int, uint32_t, void *,
                           double *, cudaStream_t);
@@ -38,7 +39,7 @@ int pp_launch_collide_segments(pp_ctx *, size_t, const double *, const double *,
 int pp_launch_verify_polylines(pp_ctx *, size_t, const double *, const double *, const uint32_t *, uint8_t *, int,
                                cudaStream_t);
 int pp_launch_collide_dubins(pp_ctx *, size_t, const void *, const void *, const double *, const double *, uint8_t *,
-                             int, cudaStream_t);
+                             int, const uint32_t *, const unsigned int *, cudaStream_t);
 int pp_launch_fp64_peak(pp_ctx *, int, double *, cudaStream_t, unsigned *, unsigned *);
 int pp_launch_rrt_extend_fused(pp_ctx *, size_t, const double *, const double *, uint32_t *, double *, uint8_t *,
                                cudaStream_t);
@@ -1107,14 +1108,24 @@ int pp_verify_polylines(pp_ctx *ctx, size_t n_lines, const double *px, const dou
 static int pp_collide_dubins_impl(pp_ctx *ctx, size_t m, const double *sx, const double *sy, const double *syaw,
                                   const double *ex, const double *ey, const double *eyaw, double radius, double step,
                                   uint8_t *ok, int flags, cudaStream_t s) {
-    // pass 1: plan records (evaluate + replay of the sampling loop); pass 2: generate-and-test per warp
+    // pass 1: plan records (evaluate + the sampling loop's counts) and, per path, the path-level box test -- a path
+    // with nothing registered under its bounding box is answered there; pass 2: generate-and-test per warp for the
+    // paths on pass 1's list (all of them under PP_COLLIDE_NO_CULL)
     PP_TMP(ctx, dcnt, s, m * 4);
     PP_TMP(ctx, dplan, s, m * PP_DUBINS_PLAN_BYTES);
     PP_TMP(ctx, daux, s, m * 136);  // pp_plan_aux: segment origins + sincos(syaw), computed once per path by pass 1
+    uint32_t *todo = nullptr;
+    unsigned int *todo_count = nullptr;
+    PP_TMP(ctx, dtodo, s, (m + 1) * 4);
+    if (!(flags & PP_COLLIDE_NO_CULL) && m < 0xFFFFFFFFull) {
+        todo_count = dtodo.as<unsigned int>();
+        todo = dtodo.as<uint32_t>() + 1;
+        PP_CUDA(ctx, cudaMemsetAsync(todo_count, 0, 4, s));
+    }
     int rc = pp_launch_dubins_plan(ctx, m, sx, sy, syaw, ex, ey, eyaw, radius, step, 0, dcnt.as<uint32_t>(), dplan.p,
-                                   daux.p, s);
+                                   daux.p, s, ok, todo, todo_count);
     if (rc) return rc;
-    return pp_launch_collide_dubins(ctx, m, dplan.p, daux.p, ex, ey, ok, flags, s);
+    return pp_launch_collide_dubins(ctx, m, dplan.p, daux.p, ex, ey, ok, flags, todo, todo_count, s);
 }
 
 int pp_collide_dubins_dev(pp_ctx *ctx, size_t m, const double *sx, const double *sy, const double *syaw,

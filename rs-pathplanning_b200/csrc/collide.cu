@@ -740,57 +740,11 @@ struct pp_points_dubins {
     const pp_dubins_plan *plans;
     const pp_plan_aux *aux;  // segment origins + sincos(syaw) per path, written by the plan kernel
     const double *ex, *ey;  // parent point appended after the samples
+    // paths left to verify: the plan kernel's path-level test (path_box.cuh) has already answered the others.
+    // todo == nullptr: every path (PP_COLLIDE_NO_CULL, or no plan-side test)
+    const uint32_t *todo;
+    const unsigned int *todo_count;
 };
-
-// ---- path-level test of the Dubins verify kernel.  `box` = the plan kernel's bounding box of every point of the path
-// and of the parent point (pp_path_box).  True when (i) every cell of the bounds classification grid under the box is
-// "inside" and (ii) no ring registered under the box's cells of the obstacle grid has an fp32 box that meets the
-// box -- then no sample can fail its own bounds test and no sample segment can find a candidate ring in its own walk
-// (its cells and its fp32 box are subsets of the path's), so the per-sample loop would return "free": the same
-// verdict without generating a single sample.  Applies to boxes of at most 32 bounds cells and PP_PATH_BOX_CELLS^2
-// obstacle cells (short edges: the extend step); long paths go straight to the per-sample loop.  All 32 lanes call
-// together.
-#ifndef PP_POLY_PATH_BOX
-#define PP_POLY_PATH_BOX 1  // A/B switch
-#endif
-__device__ __forceinline__ bool pp_path_box_free(const pp_world_view &w, double x0, double y0, double x1, double y1, int lane) {
-    if (!((x1 - x0) < 1e300 && (y1 - y0) < 1e300 && x0 <= x1 && y0 <= y1)) return false;  // NaN / inf: no shortcut
-    {   // (i) bounds
-        const int ix0 = __double2int_rd((x0 - w.bminx) * w.binvx), iy0 = __double2int_rd((y0 - w.bminy) * w.binvy);
-        const int ix1 = __double2int_rd((x1 - w.bminx) * w.binvx), iy1 = __double2int_rd((y1 - w.bminy) * w.binvy);
-        if (ix0 < 0 || iy0 < 0 || ix1 >= w.bgx || iy1 >= w.bgy) return false;
-        const int nx = ix1 - ix0 + 1, ny = iy1 - iy0 + 1;
-        if (nx > 32 || ny > 32 || nx * ny > 32) return false;
-        bool inside = true;
-        if (lane < nx * ny) inside = __ldg(w.bcls + (size_t)(iy0 + lane / nx) * w.bgx + (ix0 + lane % nx)) == 1;
-        if (!__all_sync(0xffffffffu, inside)) return false;
-    }
-    if (w.n_rings == 0u) return true;
-    // (ii) obstacles: the cell range exactly as the per-sample walk computes it
-    int cx0 = __double2int_rd((x0 - w.gminx) * w.ginv), cy0 = __double2int_rd((y0 - w.gminy) * w.ginv);
-    int cx1 = __double2int_rd((x1 - w.gminx) * w.ginv), cy1 = __double2int_rd((y1 - w.gminy) * w.ginv);
-    if (cx1 < 0 || cy1 < 0 || cx0 >= w.gx || cy0 >= w.gy) return true;  // beside the ring grid: nothing is registered there
-    cx0 = max(cx0, 0);
-    cy0 = max(cy0, 0);
-    cx1 = min(cx1, w.gx - 1);
-    cy1 = min(cy1, w.gy - 1);
-    if (cx1 - cx0 >= PP_PATH_BOX_CELLS || cy1 - cy0 >= PP_PATH_BOX_CELLS) return false;
-    const float q0x = __double2float_rd(x0), q0y = __double2float_rd(y0), q1x = __double2float_ru(x1), q1y = __double2float_ru(y1);
-    for (int r = cy0; r <= cy1; ++r) {
-        const uint32_t *row = w.cell_start + (size_t)r * w.gx;
-        const uint32_t k0 = __ldg(row + cx0), k1 = __ldg(row + cx1 + 1);  // a row of cells is one run of the cell-ordered boxes
-        for (uint32_t base = k0; base < k1; base += 32u) {
-            const uint32_t k = base + (uint32_t)lane;
-            bool meets = false;
-            if (k < k1) {
-                const float4 bb = __ldg(w.cell_box + k);
-                meets = !(q1x < bb.x || q0x > bb.z || q1y < bb.y || q0y > bb.w);
-            }
-            if (__any_sync(0xffffffffu, meets)) return false;
-        }
-    }
-    return true;
-}
 
 // ---- coarse pass of the Dubins verify kernel (paths of several chunks, all three segment lengths positive).  Lane L
 // takes the FIRST point of chunk L of a batch of 31 chunks (a chunk = 32 consecutive points = 31 line segments) and its
@@ -884,7 +838,9 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = (int)(tid & 31u), wib = (int)(tid >> 5);
     const size_t warps_total = (size_t)gridDim.x * (PP_POLY_THREADS / 32);
-    for (size_t line = (size_t)blockIdx.x * (PP_POLY_THREADS / 32) + wib; line < n_lines; line += warps_total) {
+    const size_t n_work = (DUBINS && dub.todo) ? (size_t)__ldg(dub.todo_count) : n_lines;
+    for (size_t item = (size_t)blockIdx.x * (PP_POLY_THREADS / 32) + wib; item < n_work; item += warps_total) {
+        const size_t line = (DUBINS && dub.todo) ? (size_t)__ldg(dub.todo + item) : item;
         uint32_t np;      // points of this polyline
         uint32_t base = 0;
         // The plan record and the three segment origins are warp-uniform and indexed by a run-time segment
@@ -915,23 +871,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
                 nsamp = pl.count;
             }
             np = nsamp + 1;
-            {
-                // the o[0] slot of the record carries the path's bounding box (pp_path_box); o[0] itself is the
-                // identity origin and is put back before the samples need it
-                const double bx0 = aux.o[0].ox, by0 = aux.o[0].oy, bx1 = aux.o[0].oyaw, by1 = aux.o[0].so;
-                __syncwarp();
-                if (lane < 5) reinterpret_cast<double *>(&s_aux[wib].o[0])[lane] = (lane == 4) ? 1.0 : 0.0;
-                __syncwarp();
-#if PP_POLY_PATH_BOX
-                // (the box already holds the parent point that closes the polyline, SURVEY Q6/Q12: it is the plan's goal)
-                if (CULL && pl.word != PP_WORD_NONE && pp_path_box_free(w, bx0, by0, bx1, by1, lane)) {
-                    if (lane == 0) ok[line] = 1;
-                    continue;
-                }
-#else
-                (void)bx0; (void)by0; (void)bx1; (void)by1;
-#endif
-            }
         } else {
             base = csr.off[line];
             np = csr.off[line + 1] - base;
@@ -1258,7 +1197,7 @@ int pp_launch_verify_polylines(pp_ctx *ctx, size_t n_lines, const double *px, co
     if (n_lines == 0) return PP_OK;
     pp_world_view w = pp_make_world_view(ctx->world);
     pp_points_csr csr{px, py, off};
-    pp_points_dubins dub{nullptr, nullptr, nullptr};
+    pp_points_dubins dub{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     pp_launch_scope scope(ctx, "verify_polylines");
     if (flags & PP_COLLIDE_NO_CULL)
         pp_verify_polylines_kernel<false, false><<<pp_poly_grid(ctx, n_lines), PP_POLY_THREADS, 0, stream>>>(
@@ -1271,18 +1210,23 @@ int pp_launch_verify_polylines(pp_ctx *ctx, size_t n_lines, const double *px, co
 }
 
 int pp_launch_collide_dubins(pp_ctx *ctx, size_t m, const void *plans, const void *aux, const double *ex,
-                             const double *ey, uint8_t *ok, int flags, cudaStream_t stream) {
+                             const double *ey, uint8_t *ok, int flags, const uint32_t *todo, const unsigned int *todo_count,
+                             cudaStream_t stream) {
     if (m == 0) return PP_OK;
     pp_world_view w = pp_make_world_view(ctx->world);
     pp_points_csr csr{nullptr, nullptr, nullptr};
-    pp_points_dubins dub{(const pp_dubins_plan *)plans, (const pp_plan_aux *)aux, ex, ey};
     pp_launch_scope scope(ctx, "collide_dubins");
-    if (flags & PP_COLLIDE_NO_CULL)
+    if (flags & PP_COLLIDE_NO_CULL) {
+        pp_points_dubins dub{(const pp_dubins_plan *)plans, (const pp_plan_aux *)aux, ex, ey, nullptr, nullptr};
         pp_verify_polylines_kernel<false, true><<<pp_poly_grid(ctx, m), PP_POLY_THREADS, 0, stream>>>(w, m, csr, dub,
                                                                                                       ok);
-    else
+    } else {
+        // with a todo list the number of paths is only known on the device: the grid is sized for all m, warps beyond
+        // the list's length leave at once
+        pp_points_dubins dub{(const pp_dubins_plan *)plans, (const pp_plan_aux *)aux, ex, ey, todo, todo_count};
         pp_verify_polylines_kernel<true, true><<<pp_poly_grid(ctx, m), PP_POLY_THREADS, 0, stream>>>(w, m, csr, dub,
                                                                                                      ok);
+    }
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;
 }

@@ -7,7 +7,10 @@
 
 #include "dubins_device.cuh"
 #include "pp_common.cuh"
+#include "path_box.cuh"
 #include "pp_replay.cuh"
+
+pp_world_view pp_make_world_view(const pp_world_dev &w);  // api.cu
 
 // ------------------------------------------------------------------------------------------------
 // kernel 1: evaluate.  One thread per pose pair; FP64-pipe bound (about 490 DP instructions per
@@ -173,7 +176,8 @@ int pp_launch_mod2pi(pp_ctx *ctx, size_t n, const double *x, double *out, int pi
 // one path: evaluate + replay; (sx, sy, syaw) are ignored when from_origin
 __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, double syaw, double ex, double ey,
                                                        double eyaw, double radius, double step, int from_origin,
-                                                       pp_plan_aux *aux = nullptr, double box_limit = 0.0) {
+                                                       pp_plan_aux *aux = nullptr, double box_limit = 0.0,
+                                                       double *box = nullptr) {
     pp_dubins_plan pl;
     if (from_origin) {  // the goal is given in the start frame: start pose = origin
         pl.sx = pl.sy = pl.syaw = 0.0;
@@ -231,26 +235,18 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
             double gx, gy;
             pp_segment_origins(pl, o, &gx, &gy);
             if (aux) {
-                // o[0] is the identity origin by definition: its slot carries the path's bounding box to the verify kernel
                 pp_sincos1(pl.syaw, &aux->ss, &aux->cs);
-                double box[4];
-                // the verify kernel can only use boxes below `box_limit` in either extent (its cell-count caps, set by
-                // the launcher from the world's grids); the start-to-goal offset is a lower bound of the extent, so
-                // long edges (C5) skip the computation and carry a NaN box
+                // The path's bounding box for the path-level test (path_box.cuh).  That test can only use boxes below
+                // `box_limit` in either extent (its cell-count caps, set by the launcher from the world's grids); the
+                // start-to-goal offset is a lower bound of the extent, so long edges (C5) skip the computation.
                 // A word with a zero-length segment gets no box either: there the reference's index arithmetic puts
                 // samples up to five steps off a segment's ends, even BEHIND the start pose (l = 0 makes d negative
                 // and the carried `ll` positive, src/dubins.rs:228-237), so "every point lies on the three segments"
                 // does not hold.  With three positive lengths every first `pd` is the previous overshoot in (0, d].
-                if (fabs(ex - sx) < box_limit && fabs(ey - sy) < box_limit && pl.len[0] > 0.0 && pl.len[1] > 0.0 &&
+                if (box && fabs(ex - sx) < box_limit && fabs(ey - sy) < box_limit && pl.len[0] > 0.0 && pl.len[1] > 0.0 &&
                     pl.len[2] > 0.0)
                     pp_path_box(pl, o, aux->ss, aux->cs, gx, gy, from_origin ? pl.sx : ex, from_origin ? pl.sy : ey, box);
-                else
-                    box[0] = box[1] = box[2] = box[3] = CUDART_NAN;
-                aux->o[0].ox = box[0];
-                aux->o[0].oy = box[1];
-                aux->o[0].oyaw = box[2];
-                aux->o[0].so = box[3];
-                aux->o[0].co = 0.0;
+                aux->o[0] = o[0];
                 aux->o[1] = o[1];
                 aux->o[2] = o[2];
             }
@@ -271,10 +267,7 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
             pl.count = cntout;
         }
     }
-    if (aux && (s.word == PP_WORD_NONE || pl.count == 0xFFFFFFFFu)) {  // no path: no box (NaN never passes the box test)
-        pp_sincos1(pl.syaw, &aux->ss, &aux->cs);
-        aux->o[0].ox = aux->o[0].oy = aux->o[0].oyaw = aux->o[0].so = CUDART_NAN;
-    }
+    if (aux && (s.word == PP_WORD_NONE || pl.count == 0xFFFFFFFFu)) pp_sincos1(pl.syaw, &aux->ss, &aux->cs);
     return pl;
 }
 
@@ -286,7 +279,8 @@ __global__ void __launch_bounds__(128, PP_PLAN_MIN_BLOCKS)
                           const double *__restrict__ syaw, const double *__restrict__ ex,
                           const double *__restrict__ ey, const double *__restrict__ eyaw, double radius, double step,
                           int from_origin, uint32_t *__restrict__ counts, pp_dubins_plan *__restrict__ plans,
-                          pp_plan_aux *__restrict__ aux_out, double box_limit) {
+                          pp_plan_aux *__restrict__ aux_out, double box_limit, pp_world_view w,
+                          uint8_t *__restrict__ ok, uint32_t *__restrict__ todo, unsigned int *__restrict__ todo_count) {
     // Records leave through shared memory: a thread's own 112 / 136-byte record written straight to global memory is
     // seven / seventeen warp stores that each touch 32 half-used sectors (ncu r03: lg_throttle on these stores was 31 %
     // of the kernel's stall samples for 5 % of its instructions).  A warp's 32 records are contiguous in global
@@ -298,15 +292,23 @@ __global__ void __launch_bounds__(128, PP_PLAN_MIN_BLOCKS)
     const size_t first = i - (size_t)lane;  // first path of this warp
     if (first >= n) return;                 // warp-uniform
     const uint32_t live = (uint32_t)((n - first < 32) ? (n - first) : 32);
+    bool verify = false;  // this path still needs the verify kernel (only meaningful with a todo list)
     if (i < n) {
         pp_plan_aux aux;
 #pragma unroll
         for (int k = 0; k < 3; ++k) aux.o[k].ox = aux.o[k].oy = aux.o[k].oyaw = aux.o[k].so = aux.o[k].co = 0.0;
         pp_plan_aux *ap = aux_out ? &aux : nullptr;
-        const pp_dubins_plan pl = from_origin
-                                      ? pp_make_plan(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, 1, ap, box_limit)
-                                      : pp_make_plan(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0, ap, box_limit);
+        double box[4] = {CUDART_NAN, CUDART_NAN, CUDART_NAN, CUDART_NAN};
+        const pp_dubins_plan pl =
+            from_origin ? pp_make_plan(0.0, 0.0, 0.0, ex[i], ey[i], eyaw[i], radius, step, 1, ap, box_limit, todo ? box : nullptr)
+                        : pp_make_plan(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], radius, step, 0, ap, box_limit,
+                                       todo ? box : nullptr);
         counts[i] = pl.count;
+        if (todo) {
+            // path-level test (path_box.cuh): a free path is answered here, the others go on the verify kernel's list
+            verify = !pp_path_box_free_thread(w, box[0], box[1], box[2], box[3]);
+            if (!verify) ok[i] = 1;
+        }
         if (plans) *reinterpret_cast<pp_dubins_plan *>(&s_plan[wib][lane * sizeof(pp_dubins_plan)]) = pl;
         if (aux_out) {
             double *sa = reinterpret_cast<double *>(&s_aux[wib][lane * sizeof(pp_plan_aux)]);
@@ -316,6 +318,13 @@ __global__ void __launch_bounds__(128, PP_PLAN_MIN_BLOCKS)
         }
     }
     __syncwarp();
+    if (todo) {  // append this warp's failing paths: one atomic per warp
+        const unsigned need = __ballot_sync(0xffffffffu, verify);
+        unsigned int base = 0;
+        if (lane == 0 && need) base = atomicAdd(todo_count, (unsigned int)__popc(need));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (verify) todo[base + __popc(need & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
     if (plans) {  // sizeof(pp_dubins_plan) = 7 x 16 bytes
         const uint4 *src = reinterpret_cast<const uint4 *>(s_plan[wib]);
         uint4 *dst = reinterpret_cast<uint4 *>(plans + first);
@@ -420,23 +429,35 @@ int pp_launch_dubins_path(pp_ctx *ctx, double sx, double sy, double syaw, double
     return PP_OK;
 }
 
+#ifndef PP_PLAN_PATH_BOX
+#define PP_PLAN_PATH_BOX 1  // A/B switch.  0: no path-level test, every path goes to the verify kernel
+#endif
+// ok / todo / todo_count != nullptr ("verify mode", with aux): the kernel answers the paths that pass the path-level test
+// itself (ok[i] = 1) and appends the indices of the others to todo[0 .. *todo_count); *todo_count must be zero.
 int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
                           const double *ex, const double *ey, const double *eyaw, double radius, double step,
-                          int from_origin, uint32_t *counts, void *plans, void *aux, cudaStream_t stream) {
+                          int from_origin, uint32_t *counts, void *plans, void *aux, cudaStream_t stream,
+                          uint8_t *ok, uint32_t *todo, unsigned int *todo_count) {
     if (n == 0) return PP_OK;
     pp_launch_scope scope(ctx, "dubins_plan");
-    // largest box extent the verify kernel's path-level test accepts (collide.cu: pp_path_box_free -- at most 32 cells of
-    // the bounds grid, PP_PATH_BOX_CELLS^2 cells of the obstacle grid); 0 without a world or without an aux record
+    // largest box extent the path-level test accepts (path_box.cuh -- at most 32 cells of the bounds grid,
+    // PP_PATH_BOX_CELLS^2 cells of the obstacle grid); 0 = no box is computed
     double box_limit = 0.0;
-    if (aux && ctx->world.valid) {
-        const pp_world_dev &w = ctx->world;
-        box_limit = std::min(32.0 / w.binvx, 32.0 / w.binvy);
-        if (w.n_rings) box_limit = std::min(box_limit, (PP_PATH_BOX_CELLS + 1.0) * w.gcell);
+    pp_world_view w{};
+    if (todo && aux && ok && todo_count && ctx->world.valid && n < 0xFFFFFFFFull) {
+        const pp_world_dev &wd = ctx->world;
+        w = pp_make_world_view(wd);
+#if PP_PLAN_PATH_BOX
+        box_limit = std::min(32.0 / wd.binvx, 32.0 / wd.binvy);
+        if (wd.n_rings) box_limit = std::min(box_limit, (PP_PATH_BOX_CELLS + 1.0) * wd.gcell);
         if (!(box_limit > 0.0)) box_limit = 0.0;
+#endif
+    } else {
+        todo = nullptr;
     }
-    pp_dubins_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius, step,
-                                                                           from_origin, counts, (pp_dubins_plan *)plans,
-                                                                           (pp_plan_aux *)aux, box_limit);
+    pp_dubins_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
+        n, sx, sy, syaw, ex, ey, eyaw, radius, step, from_origin, counts, (pp_dubins_plan *)plans, (pp_plan_aux *)aux,
+        box_limit, w, ok, todo, todo_count);
     PP_CUDA(ctx, cudaGetLastError());
     return PP_OK;
 }

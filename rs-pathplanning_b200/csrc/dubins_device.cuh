@@ -459,11 +459,11 @@ __device__ __forceinline__ void pp_segment_origins(const pp_dubins_plan &pl, pp_
 }
 
 // Axis-aligned box (world frame) around EVERY point the sampled path can produce: the start pose, the three segment
-// origins, the end point, and for each arc the axis extremes of its circle that fall inside the swept angle.  The box
-// travels to the verify kernel in the o[0] slot of the aux record (o[0] is the identity origin by definition) and
-// lets it dismiss a whole path with one look at the rings registered under the box.  Conservative by construction:
-// extremes are included with a 1e-6 rad margin and the box is padded by 1e-9 of the coordinates' scale, orders of
-// magnitude above the ulp-level differences between this arithmetic and the samples'.
+// origins, the end point, the parent point, and for each arc the axis extremes of its circle that fall inside the swept
+// angle.  Valid for words with three positive lengths only (the caller checks).  The plan kernel hands it to the
+// path-level test (path_box.cuh), which dismisses a whole path with one look at the rings registered under the box.
+// Conservative by construction: extremes are included with a 1e-6 rad margin and the box is padded by 1e-9 of the
+// coordinates' scale, orders of magnitude above the ulp-level differences between this arithmetic and the samples'.
 // (ss, cs) = sincos(pl.syaw); (gx, gy) = local end point of the third segment; (ex, ey) = the goal as given (the
 // verify kernel appends it to the samples as the parent point).
 __device__ __forceinline__ void pp_path_box(const pp_dubins_plan &pl, const pp_seg_origin o[3], double ss, double cs,

@@ -72,7 +72,7 @@ struct pp_timing_slot {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
-#define PP_PATH_BOX_CELLS 16  // obstacle-grid cells per axis a path box may span for the path-level test (collide.cu)
+#define PP_PATH_BOX_CELLS 4  // obstacle-grid cells per axis a path box may span for the path-level test (path_box.cuh): 16 costs the C5 slice 9 % (a third of its edges then compute a box that never passes)
 #define PP_TICKETS 128
 #define PP_TICKETS_FILL 64
 
