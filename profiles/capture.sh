@@ -27,6 +27,14 @@ if [ "${2:-}" = "fillplan" ]; then  # late round 2: only the two kernels that ch
   cap fill "pp_dubins_fill_kernel" 0 1
   cap plan "pp_dubins_plan_kernel" 5 1
 fi
+if [ "${2:-}" = "verifyplan" ]; then  # the kernels touched by the plan-side path test (final build of round 2)
+  $CMD > /dev/null 2>&1
+  cap verify_c5 "pp_verify_polylines_kernel" 5 1
+  cap verify_nohit "pp_verify_polylines_kernel" 7 1
+  cap verify_extend "pp_verify_polylines_kernel" 3 1
+  cap plan "pp_dubins_plan_kernel" 5 1
+  cap plan_extend "pp_dubins_plan_kernel" 3 1
+fi
 if [ "${2:-}" = "all" ]; then
   $CMD > /dev/null 2>&1
   # the extend step: default pair of launches (first instances), then the binned fused kernel and its binning
