@@ -861,13 +861,13 @@ int pp_launch_dubins_fill(pp_ctx *ctx, size_t n, const void *plans, const uint64
                                                                             out);
     PP_CUDA(ctx, cudaGetLastError());
 #else
-    static int resident = 0;  // CTAs of this kernel per SM (same on every device this library targets)
-    if (resident == 0) {
+    if (ctx->fill_resident == 0) {  // CTAs of this kernel per SM, asked once per context (contexts are per device and
+                                    // serialised by their mutex: no shared state between the workers of a pp_group)
         int r = 0;
         PP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, pp_dubins_fill_kernel, PP_FILL_THREADS, 0));
-        resident = r > 0 ? r : 1;
+        ctx->fill_resident = r > 0 ? r : 1;
     }
-    const size_t slots = (size_t)ctx->sm_count * resident;  // CTAs that run side by side
+    const size_t slots = (size_t)ctx->sm_count * ctx->fill_resident;  // CTAs that run side by side
     const size_t piece = (size_t)1 << 30;                    // the work counter is 32 bits wide
     for (size_t first = 0; first < n; first += piece) {
         const size_t m = std::min(piece, n - first);

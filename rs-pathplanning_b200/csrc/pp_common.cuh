@@ -87,6 +87,7 @@ struct pp_ctx {
     std::string last_error;
     uint64_t launches = 0;
     uint64_t grid_builds = 0;  // O(n) rebuilds of the node grid so far (pp_nn_grid_builds)
+    int fill_resident = 0;     // resident CTAs per SM of the sample fill kernel (0 = not asked yet)
     bool timing = false;
     std::map<std::string, pp_timing_slot> timings;
     std::vector<cudaEvent_t> event_pool;
