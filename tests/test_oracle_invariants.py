@@ -94,3 +94,68 @@ def test_sampled_paths_are_unit_speed_curves_from_start_to_goal(O):
         assert abs(math.remainder(p.yaw[-1] - eyaw, 2 * math.pi)) <= step * (1 + 1e-9)
         assert abs((p.x.size - 1) * step - p.cost) <= step * (1 + 1e-9)  # cost is the normalised length
     assert seen > 1400
+
+
+def _word_modes(word):
+    return {0: "LSL", 1: "RSR", 2: "LSR", 3: "RSL", 4: "RLR", 5: "LRL"}[word]
+
+
+def _path_box(sx, sy, syaw, ex, ey, tpq, word, r):
+    """Python restatement of pp_path_box (csrc/dubins_device.cuh): start, segment origins, end, parent point, and per arc
+    the axis extremes of its turn circle that fall inside the swept angle"""
+    xs, ys = [sx, ex], [sy, ey]
+    x, y, th = sx, sy, syaw
+    for mode, ln in zip(_word_modes(word), tpq):
+        xs.append(x); ys.append(y)
+        if mode == "S":
+            x, y = x + ln * r * math.cos(th), y + ln * r * math.sin(th)
+        else:
+            left = mode == "L"
+            cx, cy = (x - r * math.sin(th), y + r * math.cos(th)) if left else (x + r * math.sin(th), y - r * math.cos(th))
+            phi0 = th - math.pi / 2 if left else th + math.pi / 2
+            for k in range(4):  # axis k at k pi/2
+                a = (k * math.pi / 2 - phi0) % (2 * math.pi) if left else (phi0 - k * math.pi / 2) % (2 * math.pi)
+                if a <= ln + 1e-6 or a >= 2 * math.pi - 1e-6:
+                    xs.append(cx + r * math.cos(k * math.pi / 2)); ys.append(cy + r * math.sin(k * math.pi / 2))
+            th = th + ln if left else th - ln
+            x, y = (cx + r * math.sin(th), cy - r * math.cos(th)) if left else (cx - r * math.sin(th), cy + r * math.cos(th))
+        xs.append(x); ys.append(y)
+    pad = 1e-9 * (abs(min(xs)) + abs(max(xs)) + abs(min(ys)) + abs(max(ys)) + r + 1.0)
+    return min(xs) - pad, min(ys) - pad, max(xs) + pad, max(ys) + pad
+
+
+def test_path_level_shortcut_geometry(O):
+    """The two geometric claims behind the verify kernel's hierarchy, checked on the ORACLE's samples:
+    for words with three positive lengths (i) every sample lies inside the path box, (ii) consecutive samples are at
+    most one step of path length apart, so every point of a 32-point chunk lies in the chunk's end-point box grown by
+    sqrt(S^2 - c^2) / 2 with S = 31.5 steps.  And a word with a zero-length segment violates both (why the GPU path
+    excludes it)."""
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for _ in range(5000):
+        span = rng.choice([1.5, 6.0, 40.0])
+        r = float(rng.choice([0.5, 1.0, 3.0]))
+        step = float(rng.choice([0.05, 0.1, 0.3]))
+        sx, sy, ex, ey = (float(v) for v in rng.uniform(-span, span, 4))
+        syaw, eyaw = (float(v) for v in rng.uniform(-math.pi, math.pi, 2))
+        p = O.dubins_path(sx, sy, syaw, ex, ey, eyaw, r, step)
+        w, cost, tpq, fl = O.dubins_eval(sx, sy, syaw, ex, ey, eyaw, r)
+        if p is None or not all(v > 0.0 for v in tpq) or len(p.x) < 2:
+            continue
+        checked += 1
+        x0, y0, x1, y1 = _path_box(sx, sy, syaw, ex, ey, tpq, w, r)
+        px, py = np.asarray(p.x), np.asarray(p.y)
+        assert px.min() >= x0 and px.max() <= x1 and py.min() >= y0 and py.max() <= y1, (sx, sy, syaw, ex, ey, eyaw, r, step)
+        gaps = np.hypot(np.diff(px), np.diff(py))
+        assert gaps.max() <= step * r * (1 + 1e-9), gaps.max() / (step * r)
+        S = 31.5 * step * r
+        for k0 in range(0, len(px) - 32, 31):  # chunks of 32 points, one point of overlap
+            ax, ay, bx, by = px[k0], py[k0], px[k0 + 31], py[k0 + 31]
+            h = 0.5 * math.sqrt(max(S * S - (bx - ax) ** 2 - (by - ay) ** 2, 0.0)) + 1e-9 * (abs(ax) + abs(ay) + 1.0)
+            cx, cy = px[k0:k0 + 32], py[k0:k0 + 32]
+            assert cx.min() >= min(ax, bx) - h and cx.max() <= max(ax, bx) + h
+            assert cy.min() >= min(ay, by) - h and cy.max() <= max(ay, by) + h
+    assert checked > 3500
+    # the counter-example: goal straight ahead (t = q = 0): a sample BEHIND the start, outside the geometric path's box
+    p = O.dubins_path(0.0, 0.0, 0.0, 9.9, 0.0, 0.0, 3.0, 0.2)
+    assert min(p.x) < -0.5 and 0.0 in O.dubins_eval(0.0, 0.0, 0.0, 9.9, 0.0, 0.0, 3.0)[2]
