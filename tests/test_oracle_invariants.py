@@ -159,3 +159,35 @@ def test_path_level_shortcut_geometry(O):
     # the counter-example: goal straight ahead (t = q = 0): a sample BEHIND the start, outside the geometric path's box
     p = O.dubins_path(0.0, 0.0, 0.0, 9.9, 0.0, 0.0, 3.0, 0.2)
     assert min(p.x) < -0.5 and 0.0 in O.dubins_eval(0.0, 0.0, 0.0, 9.9, 0.0, 0.0, 3.0)[2]
+
+
+def test_path_box_free_implies_oracle_free(O):
+    """the implication the plan kernel's path-level test rests on, on the oracle's side: a Dubins edge (three positive
+    lengths) whose path box lies inside the bounds and meets no ring's bounding box is free for the oracle's full
+    Space::verify of the sampled line (src/rrt.rs:124-137, 291-321)"""
+    rng = np.random.default_rng(99)
+    world = 120.0
+    cx, cy, rr = rng.uniform(0, world, 250), rng.uniform(0, world, 250), rng.uniform(0.5, 2.5, 250)
+    rings = [O.create_circle(float(a), float(b), float(c)) for a, b, c in zip(cx, cy, rr)]
+    bounds = (np.array([0.0, 0.0, world, world, 0.0]), np.array([0.0, world, world, 0.0, 0.0]))
+    W = O.OracleWorld(bounds, rings)
+    rb = np.array([(rx.min(), ry.min(), rx.max(), ry.max()) for rx, ry in rings])
+    n = 4000
+    sx, sy = rng.uniform(-2, world + 2, n), rng.uniform(-2, world + 2, n)
+    ex, ey = sx + rng.uniform(-2.5, 2.5, n), sy + rng.uniform(-2.5, 2.5, n)
+    syaw = np.arctan2(ey - sy, ex - sx)  # the new node aims at its parent (src/rrt.rs:267-271)
+    eyaw = rng.uniform(-math.pi, math.pi, n)
+    r, step = 0.8, 0.1
+    want = W.verify_dubins_edges(sx, sy, syaw, ex, ey, eyaw, r, step)
+    by_box = 0
+    for i in range(n):
+        w, cost, tpq, fl = O.dubins_eval(sx[i], sy[i], syaw[i], ex[i], ey[i], eyaw[i], r)
+        if w == O.NONE or not all(v > 0.0 for v in tpq):
+            continue
+        x0, y0, x1, y1 = _path_box(sx[i], sy[i], syaw[i], ex[i], ey[i], tpq, w, r)
+        inside = x0 > 1e-6 and y0 > 1e-6 and x1 < world - 1e-6 and y1 < world - 1e-6
+        meets = np.any(~((rb[:, 2] < x0 - 1e-6) | (rb[:, 0] > x1 + 1e-6) | (rb[:, 3] < y0 - 1e-6) | (rb[:, 1] > y1 + 1e-6)))
+        if inside and not meets:
+            by_box += 1
+            assert want[i] == 1, (i, sx[i], sy[i], ex[i], ey[i], eyaw[i])
+    assert by_box > 0.3 * n and 0.3 < want.mean() < 0.95  # the shortcut answers a large share, and not everything is free
