@@ -903,8 +903,9 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
         const uint32_t n_chunks = (np <= 2u) ? 1u : (np + 29u) / 31u;  // chunk c: points 31 c .. 31 c + 31, while 31 c + 1 < np
 #if PP_POLY_COARSE
         // (three positive lengths: a zero-length segment breaks the one-step spacing the chunk boxes rely on, see above)
-        const bool coarse = DUBINS && CULL && nsamp > 1u && np >= PP_COARSE_MIN_POINTS && pl.len[0] > 0.0 &&
-                            pl.len[1] > 0.0 && pl.len[2] > 0.0;
+        // (tested on the products of neighbouring lengths, as the reference's branch at src/dubins.rs:233 is)
+        const bool coarse = DUBINS && CULL && nsamp > 1u && np >= PP_COARSE_MIN_POINTS && pl.len[0] * pl.len[1] > 0.0 &&
+                            pl.len[1] * pl.len[2] > 0.0 && pl.len[1] > 0.0;
 #else
         const bool coarse = false;
 #endif

@@ -243,8 +243,10 @@ __device__ __forceinline__ pp_dubins_plan pp_make_plan(double sx, double sy, dou
                 // samples up to five steps off a segment's ends, even BEHIND the start pose (l = 0 makes d negative
                 // and the carried `ll` positive, src/dubins.rs:228-237), so "every point lies on the three segments"
                 // does not hold.  With three positive lengths every first `pd` is the previous overshoot in (0, d].
-                if (box && fabs(ex - sx) < box_limit && fabs(ey - sy) < box_limit && pl.len[0] > 0.0 && pl.len[1] > 0.0 &&
-                    pl.len[2] > 0.0)
+                // (the reference branches on the PRODUCTS of neighbouring lengths, :233: tested as such, so that an
+                // underflowing product of two tiny lengths counts as the zero-length case it would be treated as)
+                if (box && fabs(ex - sx) < box_limit && fabs(ey - sy) < box_limit && pl.len[0] * pl.len[1] > 0.0 &&
+                    pl.len[1] * pl.len[2] > 0.0 && pl.len[1] > 0.0)
                     pp_path_box(pl, o, aux->ss, aux->cs, gx, gy, from_origin ? pl.sx : ex, from_origin ? pl.sy : ey, box);
                 aux->o[0] = o[0];
                 aux->o[1] = o[1];
