@@ -471,122 +471,12 @@ int pp_launch_dubins_plan(pp_ctx *ctx, size_t n, const double *sx, const double 
 // ------------------------------------------------------------------------------------------------
 #define PP_FILL_THREADS 128
 
-#ifndef PP_FILL_TMA
-#define PP_FILL_TMA 0  // A/B switch.  1: staging rows leave through the TMA engine (cp.async.bulk shared -> global,
-                       // two rows per warp).  MEASURED AND NOT ADOPTED: 0.378 ms against 0.306 ms for the same kernel with
-                       // vector stores and 0.280 ms for the single-row kernel below (5.1e7 samples): 1.6 M bulk copies of
-                       // 768 B are too small for the TMA engine to beat 48 coalesced 16-byte stores per row.
-#endif
 #ifndef PP_FILL_LEGACY
 #define PP_FILL_LEGACY 0  // A/B switch.  1: the round-1 kernel (one sincos per SAMPLE, local frame + per-sample rotation)
 #endif
-#if PP_FILL_TMA
-#define PP_FILL_ROW 100  // doubles per staging row: 96 (32 samples) + 1 (alignment shift) + padding to a 16-byte multiple
-
-__global__ void __launch_bounds__(PP_FILL_THREADS)
-    pp_dubins_fill_kernel(size_t n, const pp_dubins_plan *__restrict__ plans, const uint64_t *__restrict__ offsets,
-                          double *__restrict__ out) {
-    // two staging rows per warp: while the TMA engine drains one, the warp interpolates into the other
-    __shared__ __align__(16) double fill_stage[PP_FILL_THREADS / 32][2][PP_FILL_ROW];
-    const int lane = threadIdx.x & 31;
-    uint32_t chunk = 0;  // running chunk counter of this warp: selects the staging row
-    const size_t warps_total = (size_t)gridDim.x * (PP_FILL_THREADS / 32);
-    for (size_t path = (size_t)blockIdx.x * (PP_FILL_THREADS / 32) + (threadIdx.x >> 5); path < n;
-         path += warps_total) {
-        const pp_dubins_plan pl = plans[path];
-        if (pl.count == 0 || pl.count == 0xFFFFFFFFu) continue;
-        double ss = 0.0, cs = 1.0;
-        if (!pl.from_origin) pp_sincos1(pl.syaw, &ss, &cs);
-        double *dst = out + 3 * offsets[path];
-        if (lane == 0) {  // slot 0: the untouched zero of the reference's buffer = the start pose
-            dst[0] = pl.from_origin ? 0.0 : (cs * 0.0 + (-ss) * 0.0) + pl.sx;
-            dst[1] = pl.from_origin ? 0.0 : (ss * 0.0 + cs * 0.0) + pl.sy;
-            dst[2] = pl.from_origin ? 0.0 : pp_pi_2_pi_fast(0.0 + pl.syaw);
-        }
-        // one loop per segment: origin, mode and first pd are loop invariants (no per-sample segment search)
-        double ox = 0.0, oy = 0.0, oyaw = 0.0, so = 0.0, co = 1.0;
-        uint32_t base = 1;
-#pragma unroll
-        for (int seg = 0; seg < 3; ++seg) {
-            const int mode = pp_word_mode(pl.word, seg);
-            const double len = pl.len[seg], pd0 = pl.pd0[seg];
-            const double d = (len > 0.0) ? pl.step : -pl.step;
-            const uint32_t ns = pl.n[seg];
-            for (uint32_t j0 = 0; j0 < ns; j0 += 32) {
-                const uint32_t k0 = base + j0;
-                if (k0 >= pl.count) break;  // the trim rule may cut the tail (Q6/Q7); warp-uniform
-                const uint32_t cnt = min(min(32u, ns - j0), pl.count - k0);
-                // The 3*cnt doubles of this step are contiguous in `out` (a full step = 768 B).  The row is staged
-                // in shared memory SHIFTED by the parity of its first global element, so that the 16-byte aligned
-                // part of the destination is 16-byte aligned in shared memory too.
-                double *d0 = dst + 3 * (size_t)k0;
-                const uint32_t D = 3 * cnt;
-                const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(d0) >> 3) & 1u);
-                double *stage = fill_stage[threadIdx.x >> 5][chunk & 1u] + head;
-                ++chunk;
-#if PP_FILL_TMA
-                if (lane == 0) pp_bulk_wait_read<1>();  // the copy issued two chunks ago has let go of this row
-                __syncwarp();
-#endif
-                if ((uint32_t)lane < cnt) {
-                    double x, y, yaw;
-                    pp_interpolate(mode, pd0 + (double)(j0 + lane) * d, ox, oy, oyaw, so, co, pl.rinv, &x, &y, &yaw);
-                    if (!pl.from_origin) {  // src/dubins.rs:412-422
-                        const double xw = (cs * x + (-ss) * y) + pl.sx;
-                        const double yw = (ss * x + cs * y) + pl.sy;
-                        x = xw;
-                        y = yw;
-                        yaw = pp_pi_2_pi_fast(yaw + pl.syaw);
-                    }
-                    stage[3 * lane + 0] = x;  // stride of 3 doubles: conflict-free
-                    stage[3 * lane + 1] = y;
-                    stage[3 * lane + 2] = yaw;
-                }
-                const uint32_t nvec = (D - head) >> 1;  // 16-byte units after the (optional) 8-byte head
-#if PP_FILL_TMA
-                // Per-lane (x,y,yaw) stores touched 24 sectors per warp instruction (L1 store-sector bound), 16-byte
-                // vector stores from the staging row still cost 2 LSU instructions per lane.  One bulk copy per row
-                // hands the whole 768 bytes to the TMA engine: no LSU / L1 store traffic at all.
-                pp_fence_proxy_async();  // this lane's staging writes -> visible to the async proxy
-                __syncwarp();
-                if (lane == 0) {
-                    if (head) d0[0] = stage[0];
-                    if (nvec) pp_bulk_s2g(d0 + head, stage + head, nvec * 16u);
-                    pp_bulk_commit();
-                    if ((D - head) & 1u) d0[D - 1] = stage[D - 1];
-                }
-#else
-                __syncwarp();
-                if (lane == 0 && head) d0[0] = stage[0];
-#pragma unroll
-                for (uint32_t v = lane; v < 64; v += 32) {
-                    if (v < nvec) {
-                        const uint32_t e = head + 2 * v;
-                        *reinterpret_cast<double2 *>(d0 + e) = make_double2(stage[e], stage[e + 1]);
-                    }
-                }
-                if (lane == 0 && ((D - head) & 1u)) d0[D - 1] = stage[D - 1];
-                __syncwarp();
-#endif
-            }
-            base += ns;
-            if (seg < 2) {  // next origin = this segment's end point (src/dubins.rs:258-271, read back at :230)
-                double ex_, ey_, eyaw_;
-                pp_interpolate(mode, len, ox, oy, oyaw, so, co, pl.rinv, &ex_, &ey_, &eyaw_);
-                ox = ex_;
-                oy = ey_;
-                oyaw = eyaw_;
-                pp_sincos1(oyaw, &so, &co);
-            }
-        }
-    }
-#if PP_FILL_TMA
-    if (lane == 0) pp_bulk_wait<0>();  // every bulk store of this warp has landed before the CTA retires
-#endif
-}
-#elif PP_FILL_LEGACY
+#if PP_FILL_LEGACY
 // Variants measured on 5.1e7 samples (2^16 C5 paths) and NOT adopted (round 2, profiles/r02_summary.md): rows leaving
-// through the TMA engine (cp.async.bulk shared -> global, two rows per warp; PP_FILL_TMA=1 above) 0.378 ms; rows of
+// through the TMA engine (cp.async.bulk shared -> global, two rows per warp; removed since) 0.378 ms; rows of
 // 64 samples with two interpolations in flight per lane 0.366 ms; this kernel under __launch_bounds__(128, 6) 0.418 ms;
 // this kernel as it stands 0.280 ms = 4.4 TB/s (a pure store stream, torch fill_, reaches 7.26 TB/s on the same box).
 __global__ void __launch_bounds__(PP_FILL_THREADS)
@@ -853,7 +743,7 @@ __global__ void __launch_bounds__(PP_FILL_THREADS, PP_FILL_MIN_BLOCKS)
 int pp_launch_dubins_fill(pp_ctx *ctx, size_t n, const void *plans, const uint64_t *offsets, double *out,
                           cudaStream_t stream) {
     if (n == 0) return PP_OK;
-#if PP_FILL_TMA || PP_FILL_LEGACY
+#if PP_FILL_LEGACY
     pp_launch_scope scope(ctx, "dubins_fill");
     size_t warps = n;
     size_t blocks = (warps + (PP_FILL_THREADS / 32) - 1) / (PP_FILL_THREADS / 32);
