@@ -57,63 +57,19 @@ __global__ void __launch_bounds__(PP_EVAL_THREADS, PP_EVAL_MIN_BLOCKS)
                           c, i, cost, word, tpq);
 }
 
-// Variant PP_EVAL_PAIRS == 2 (A/B switch): a thread takes TWO pairs, 128 apart, and issues both pairs' loads before it
-// evaluates the first -- the second pair's inputs arrive during the ~960 instructions of the first, so a warp waits
-// on the load scoreboard once per two pairs (ncu source page of the one-pair kernel: 30 % of the warp samples sit on
-// the load scoreboard at the top of the kernel).  The evaluation is behind a call so that the code is not duplicated.
-#ifndef PP_EVAL_PAIRS
-#define PP_EVAL_PAIRS 1
-#endif
-template <bool WANT_TPQ>
-__device__ __noinline__ void pp_eval_one_call(double sx, double sy, double syaw, double ex, double ey, double eyaw,
-                                              double c, size_t i, double *__restrict__ cost,
-                                              uint8_t *__restrict__ word, double *__restrict__ tpq) {
-    pp_eval_one<WANT_TPQ>(sx, sy, syaw, ex, ey, eyaw, c, i, cost, word, tpq);
-}
-template <bool HAS_RADIUS_ARR, bool WANT_TPQ>
-__global__ void __launch_bounds__(PP_EVAL_THREADS, PP_EVAL_MIN_BLOCKS)
-    pp_dubins_eval2_kernel(size_t n, const double *__restrict__ sx, const double *__restrict__ sy,
-                           const double *__restrict__ syaw, const double *__restrict__ ex,
-                           const double *__restrict__ ey, const double *__restrict__ eyaw,
-                           const double *__restrict__ radius_arr, double inv_radius, double *__restrict__ cost,
-                           uint8_t *__restrict__ word, double *__restrict__ tpq) {
-    const size_t i0 = (size_t)blockIdx.x * (2 * PP_EVAL_THREADS) + threadIdx.x;
-    if (i0 >= n) return;
-    const size_t i1 = i0 + PP_EVAL_THREADS;
-    const bool two = i1 < n;
-    const size_t j1 = two ? i1 : i0;
-    const double a0 = __ldg(sx + i0), a1 = __ldg(sy + i0), a2 = __ldg(syaw + i0), a3 = __ldg(ex + i0), a4 = __ldg(ey + i0),
-                 a5 = __ldg(eyaw + i0);
-    const double b0 = __ldg(sx + j1), b1 = __ldg(sy + j1), b2 = __ldg(syaw + j1), b3 = __ldg(ex + j1), b4 = __ldg(ey + j1),
-                 b5 = __ldg(eyaw + j1);
-    const double c0 = HAS_RADIUS_ARR ? 1.0 / __ldg(radius_arr + i0) : inv_radius;
-    const double c1 = HAS_RADIUS_ARR ? 1.0 / __ldg(radius_arr + j1) : inv_radius;
-#if PP_EVAL_PAIRS == 3  // the same, with the evaluation inlined twice instead of called (code size x2, no call ABI)
-    pp_eval_one<WANT_TPQ>(a0, a1, a2, a3, a4, a5, c0, i0, cost, word, tpq);
-    if (two) pp_eval_one<WANT_TPQ>(b0, b1, b2, b3, b4, b5, c1, i1, cost, word, tpq);
-#else
-    pp_eval_one_call<WANT_TPQ>(a0, a1, a2, a3, a4, a5, c0, i0, cost, word, tpq);
-    if (two) pp_eval_one_call<WANT_TPQ>(b0, b1, b2, b3, b4, b5, c1, i1, cost, word, tpq);
-#endif
-}
-
+// Two pairs per thread with both pairs' loads issued before the first evaluation (behind a call, or inlined twice) were
+// measured in round 2 and removed: 0.636 / 0.623 / 0.619 ms against 0.616 ms (profiles/r02_summary.md section 4) -- while
+// some warps wait on their loads, the others already saturate the issue port and the FP64 pipe together.
 int pp_launch_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
                           const double *ex, const double *ey, const double *eyaw, const double *radius_arr,
                           double radius, double *cost, uint8_t *word, double *tpq, cudaStream_t stream) {
     if (n == 0) return PP_OK;
     pp_launch_scope scope(ctx, "dubins_eval");
     const double inv_radius = 1.0 / radius;
-#if PP_EVAL_PAIRS >= 2
-    const unsigned grid = (unsigned)((n + 2 * PP_EVAL_THREADS - 1) / (2 * PP_EVAL_THREADS));
-#define PP_GO(RA, TPQ)                                                                                           \
-    pp_dubins_eval2_kernel<RA, TPQ><<<grid, PP_EVAL_THREADS, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius_arr, \
-                                                                          inv_radius, cost, word, tpq)
-#else
     const unsigned grid = (unsigned)((n + PP_EVAL_THREADS - 1) / PP_EVAL_THREADS);
 #define PP_GO(RA, TPQ)                                                                                          \
     pp_dubins_eval_kernel<RA, TPQ><<<grid, PP_EVAL_THREADS, 0, stream>>>(n, sx, sy, syaw, ex, ey, eyaw, radius_arr, \
                                                                          inv_radius, cost, word, tpq)
-#endif
     if (radius_arr) {
         if (tpq) PP_GO(true, true); else PP_GO(true, false);
     } else {
