@@ -984,10 +984,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             cy1 = min(cy1, w.gy - 1);
             uint32_t kcur = 0, kend = 0;
             bool linear = false;
-#ifndef PP_POLY_FOLD_COUNT
-#define PP_POLY_FOLD_COUNT 1
-#endif
-#if PP_POLY_FOLD_COUNT
             // user-supplied polylines may hold segments whose box covers more cells than there are rings: walk
             // the ring list instead (bounds the cost per segment by O(rings)); Dubins samples are a step apart
             if (!DUBINS && more &&
@@ -1011,32 +1007,6 @@ __global__ void __launch_bounds__(PP_POLY_THREADS, PP_POLY_MIN_BLOCKS)
             const bool swx = xe < x, swy = ye < y;
             const float q32x0 = __double2float_rd(swx ? xe : x), q32x1 = __double2float_ru(swx ? x : xe);
             const float q32y0 = __double2float_rd(swy ? ye : y), q32y1 = __double2float_ru(swy ? y : ye);
-#else
-            if (more) {
-                // rings registered under the box's cells, row by row (a row's cells are contiguous in the CSR
-                // array): in free space the sum is zero for every lane and the chunk is done after one vote
-                uint32_t cnt = 0;
-                for (int r = cy; r <= cy1; ++r) {
-                    const uint32_t *row = w.cell_start + (size_t)r * w.gx;
-                    cnt += __ldg(row + cx1 + 1) - __ldg(row + cx0);
-                }
-                more = cnt != 0u;
-            }
-            if (__ballot_sync(0xffffffffu, more) == 0u) continue;
-            // some lane has rings to look at: its box, rounded outward to fp32, for the per-ring overlap test
-            const double xe = own_segment ? xn : x, ye = own_segment ? yn : y;
-            const bool swx = xe < x, swy = ye < y;
-            const float q32x0 = __double2float_rd(swx ? xe : x), q32x1 = __double2float_ru(swx ? x : xe);
-            const float q32y0 = __double2float_rd(swy ? ye : y), q32y1 = __double2float_ru(swy ? y : ye);
-            // user-supplied polylines may hold segments whose box covers more cells than there are rings: walk
-            // the ring list instead (bounds the cost per segment by O(rings)); Dubins samples are a step apart
-            if (!DUBINS && more &&
-                (unsigned long long)(cx1 - cx0 + 1) * (unsigned long long)(cy1 - cy + 1) > (unsigned long long)w.n_rings + 64ull) {
-                linear = true;
-                kend = w.n_rings;
-                cy = cy1 + 1;
-            }
-#endif
             // the ids of a ROW of cells are one contiguous run of cell_items: the walk goes row by row
             bool inner = false;
             for (;;) {
