@@ -67,3 +67,25 @@ def test_cpu_baseline_leg_has_the_contract_keys(pp):
     assert ext["unit"] == "steps/s" and ext["value"] > 0 and ext["nn_brute_matches_grid"] is True
     assert ext["nn_grid_queries_per_s"] > ext["nn_brute_queries_per_s"] > 0
     assert 0 < ext["single_thread_value"] <= ext["value"] * 2
+
+
+def test_kernel_facts_point_at_committed_captures():
+    """bench.py quotes per-kernel figures (executed FP64 instructions per pair, DRAM bytes per launch) from
+    profiles/kernel_facts.json: every entry must name an ncu raw-page export that is committed under profiles/, and
+    re-extracting that file with tools/ncu_facts.py must reproduce the figures bench.py reads"""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    facts = json.load(open(os.path.join(root, "profiles", "kernel_facts.json")))
+    assert "pp_dubins_eval_kernel<0, 0>" in facts and "pp_dubins_fill_kernel" in facts
+    spec = importlib.util.spec_from_file_location("ncu_facts", os.path.join(root, "tools", "ncu_facts.py"))
+    nf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nf)
+    for key, f in facts.items():
+        path = os.path.join(root, f["source"])
+        assert os.path.exists(path), (key, f["source"])
+        again = [g for g in nf.facts_from_csv(path, f.get("units_per_launch")) if g["kernel"] == f["kernel"]]
+        assert any(abs(g["inst_executed"] - f["inst_executed"]) < 0.5 and
+                   abs(g["dram_bytes"] - f["dram_bytes"]) < 0.5 for g in again), key
+    ev = facts["pp_dubins_eval_kernel<0, 0>"]
+    assert 400 < ev["fp64_thread_instr_per_unit"] < 600 and 0.9e9 < ev["dram_bytes"] < 1.0e9
