@@ -414,6 +414,9 @@ int pp_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, co
     const size_t per_slot = chunk * (8 * (size_t)n_in + 8 + 8 /*word, padded*/ + (tpq ? 24 : 0));
     int rc = pp_scratch_reserve(ctx, per_slot * 3 + 4096);
     if (rc) return rc;
+    // the chunks run on the copy streams, which are not ordered after the context stream: work a `_dev` call left
+    // in flight there (scan, grid build) may still be using the scratch block
+    PP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double *in[7] = {sx, sy, syaw, ex, ey, eyaw, radius_arr};
     size_t c = 0;
     for (size_t off = 0; off < n; off += chunk, ++c) {
