@@ -379,8 +379,16 @@ inline Edges chain_edges(const NodePtr &node) {
 }  // namespace detail_rrt
 
 // src/rrt.rs:291-321 : per-edge Dubins samples in node->root order (one batched count + fill), then the
-// root's own point
+// root's own point.  An edge without a feasible word contributes its start point (:313); finalize's copy of the
+// loop panics instead (:529), which `strict` reproduces as a std::runtime_error.
+namespace detail_rrt {
+constexpr const char *SHOULD_PLAN = "Should plan dubins curve";  // src/rrt.rs:529
+inline LineString chain_line(const NodePtr &node, double turn_radius, double step_size, bool strict);
+}  // namespace detail_rrt
 inline LineString line_to_origin(const NodePtr &node, double turn_radius, double step_size) {
+    return detail_rrt::chain_line(node, turn_radius, step_size, false);
+}
+inline LineString detail_rrt::chain_line(const NodePtr &node, double turn_radius, double step_size, bool strict) {
     detail_rrt::Edges e = detail_rrt::chain_edges(node);
     const size_t m = e.sx.size();
     LineString out;
@@ -403,6 +411,7 @@ inline LineString line_to_origin(const NodePtr &node, double turn_radius, double
         for (size_t i = 0; i < m; ++i) {
             const uint8_t word = plan[i * PP_DUBINS_PLAN_BYTES + 104];
             if (word == PP_WORD_NONE) {  // src/rrt.rs:313
+                if (strict) throw std::runtime_error(SHOULD_PLAN);
                 out.push(e.sx[i], e.sy[i]);
                 continue;
             }
@@ -514,7 +523,7 @@ class RRT {  // src/rrt.rs:325-619
     }
     LineString finalize(const NodePtr &goal_node) const {  // src/rrt.rs:503-540
         NodePtr top = optimize_from_goal(goal_node);
-        LineString l = line_to_origin(top, space_->get_steer(), step_size_);
+        LineString l = detail_rrt::chain_line(top, space_->get_steer(), step_size_, true);  // :529 panics on None
         l.x.pop_back();  // the root contributes nothing here (None => vec![], :532)
         l.y.pop_back();
         LineString r;
@@ -637,10 +646,8 @@ class RRT {  // src/rrt.rs:325-619
         for (size_t j = 0; j < from.size(); ++j) {
             LineString fwd;  // node -> root order, the root's own point left out (finalize drops it, :532)
             for (size_t k = 0; k < edges[j].sx.size(); ++k, ++pos) {
-                if (plan[pos * PP_DUBINS_PLAN_BYTES + 104] == PP_WORD_NONE) {  // src/rrt.rs:313
-                    fwd.push(edges[j].sx[k], edges[j].sy[k]);
-                    continue;
-                }
+                if (plan[pos * PP_DUBINS_PLAN_BYTES + 104] == PP_WORD_NONE)  // finalize's loop, src/rrt.rs:529
+                    throw std::runtime_error(detail_rrt::SHOULD_PLAN);
                 for (uint64_t s = offsets[pos]; s < offsets[pos] + counts[pos]; ++s) fwd.push(xyyaw[3 * s], xyyaw[3 * s + 1]);
             }
             for (size_t k = fwd.size(); k-- > 0;) lines[j].push(fwd.x[k], fwd.y[k]);  // :538 reverse

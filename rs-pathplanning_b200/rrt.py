@@ -23,6 +23,7 @@ from . import _ffi, synth
 from .dubins import DubinsConfig
 
 RECURSION_LIMIT = 16  # src/rrt.rs:14
+SHOULD_PLAN = "Should plan dubins curve"  # src/rrt.rs:529: finalize panics when an edge has no feasible word
 Ring = Tuple[np.ndarray, np.ndarray]
 
 
@@ -172,8 +173,10 @@ def _chain_edges(node: Node):
     return sx, sy, syaw, ex, ey, eyaw
 
 
-def line_to_origin(node: Node, turn_radius: float, step_size: float, ctx=None) -> Ring:  # src/rrt.rs:291-321
-    """polyline node -> root: per-edge Dubins samples (one batched GPU call), then the root's point"""
+def line_to_origin(node: Node, turn_radius: float, step_size: float, ctx=None, _strict: bool = False) -> Ring:
+    """src/rrt.rs:291-321.  Polyline node -> root: per-edge Dubins samples (one batched GPU call), then the root's point.
+    An edge without a feasible word contributes its start point (:313); finalize's copy of the loop panics instead
+    (:529), which `_strict` reproduces"""
     from . import default_context
     ctx = ctx or default_context()
     sx, sy, syaw, ex, ey, eyaw = _chain_edges(node)
@@ -185,6 +188,8 @@ def line_to_origin(node: Node, turn_radius: float, step_size: float, ctx=None) -
         words = np.frombuffer(plan, np.uint8).reshape(-1, _ffi.PLAN_BYTES)[:, 104]
         for i in range(len(sx)):
             if words[i] == _ffi.WORD_NONE:  # src/rrt.rs:313
+                if _strict:
+                    raise RuntimeError(SHOULD_PLAN)
                 xs.append(np.array([sx[i]])); ys.append(np.array([sy[i]]))
             else:
                 o, c = int(offsets[i]), int(counts[i])
@@ -330,8 +335,8 @@ class RRT:  # src/rrt.rs:325-619
             xs, ys = [], []
             for k in range(len(e[0])):
                 i = pos + k
-                if words[i] == _ffi.WORD_NONE:  # src/rrt.rs:313
-                    xs.append(np.array([e[0][k]])); ys.append(np.array([e[1][k]]))
+                if words[i] == _ffi.WORD_NONE:  # src/rrt.rs:529 (finalize's loop, not line_to_origin's :313)
+                    raise RuntimeError(SHOULD_PLAN)
                 else:
                     o, c = int(offsets[i]), int(counts[i])
                     xs.append(out[o:o + c, 0]); ys.append(out[o:o + c, 1])
@@ -354,7 +359,7 @@ class RRT:  # src/rrt.rs:325-619
     # -- src/rrt.rs:503-540 : root contributes nothing, result reversed (start -> goal)
     def finalize(self, goal_node: Node) -> Ring:
         top = self.optimize_from_goal(goal_node)
-        lx, ly = line_to_origin(top, self.space.get_steer(), self.step_size, self.ctx)
+        lx, ly = line_to_origin(top, self.space.get_steer(), self.step_size, self.ctx, _strict=True)
         lx, ly = lx[:-1], ly[:-1]  # drop the root's own point (None => vec![] at :532)
         return lx[::-1].copy(), ly[::-1].copy()
 

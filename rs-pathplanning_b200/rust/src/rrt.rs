@@ -216,8 +216,10 @@ fn collide_dubins(ctx: &ffi::Ctx, e: &[Vec<f64>; 6], turn_radius: f64, step_size
     ok
 }
 
-/// per-edge Dubins samples of the chain in node -> root order: one count pass + one fill pass on the GPU
-fn chain_samples(e: &[Vec<f64>; 6], turn_radius: f64, step_size: f64) -> Vec<Vec<(f64, f64)>> {
+/// per-edge Dubins samples of the chain in node -> root order: one count pass + one fill pass on the GPU.
+/// An edge without a feasible word yields its start point (line_to_origin, src/rrt.rs:313) or, with `strict`,
+/// the panic of finalize's copy of the loop (src/rrt.rs:529)
+fn chain_samples(e: &[Vec<f64>; 6], turn_radius: f64, step_size: f64, strict: bool) -> Vec<Vec<(f64, f64)>> {
     let m = e[0].len();
     if m == 0 {
         return vec![];
@@ -246,6 +248,9 @@ fn chain_samples(e: &[Vec<f64>; 6], turn_radius: f64, step_size: f64) -> Vec<Vec
     (0..m)
         .map(|i| {
             if plan[i * ffi::PP_DUBINS_PLAN_BYTES + ffi::PP_PLAN_WORD_OFFSET] as i32 == ffi::PP_WORD_NONE {
+                if strict {
+                    panic!("Should plan dubins curve"); // src/rrt.rs:529
+                }
                 vec![(e[0][i], e[1][i])] // src/rrt.rs:313 fallback
             } else {
                 (offsets[i] as usize..(offsets[i] + counts[i] as u64) as usize).map(|k| (out[3 * k], out[3 * k + 1])).collect()
@@ -256,7 +261,7 @@ fn chain_samples(e: &[Vec<f64>; 6], turn_radius: f64, step_size: f64) -> Vec<Vec
 
 pub fn line_to_origin(node: Arc<Node>, turn_radius: f64, step_size: f64) -> LineString<f64> {
     let e = chain_edges(&node);
-    let mut l: Vec<(f64, f64)> = chain_samples(&e, turn_radius, step_size).into_iter().flatten().collect();
+    let mut l: Vec<(f64, f64)> = chain_samples(&e, turn_radius, step_size, false).into_iter().flatten().collect();
     let mut root = node;
     while let Some(p) = root.get_parent() {
         root = p;
@@ -410,7 +415,7 @@ impl RRT {
                 e[c].extend_from_slice(&te[c]);
             }
         }
-        let per_edge = chain_samples(&e, self.space.get_steer(), self.step_size);
+        let per_edge = chain_samples(&e, self.space.get_steer(), self.step_size, true);
         let lines: Vec<LineString<f64>> = spans
             .iter()
             .map(|&(a, n)| {
@@ -436,9 +441,9 @@ impl RRT {
     pub fn finalize(&self, goal_node: Arc<Node>) -> LineString<f64> {
         let top = self.optimize_from_goal(goal_node);
         let e = chain_edges(&top);
-        // the root contributes nothing here (None => vec![]); a chain edge without a feasible word yields its
-        // start point instead of the reference's panic!("Should plan dubins curve")
-        let mut l: Vec<(f64, f64)> = chain_samples(&e, self.space.get_steer(), self.step_size).into_iter().flatten().collect();
+        // the root contributes nothing here (None => vec![]); a chain edge without a feasible word panics as the
+        // reference does (src/rrt.rs:529)
+        let mut l: Vec<(f64, f64)> = chain_samples(&e, self.space.get_steer(), self.step_size, true).into_iter().flatten().collect();
         l.reverse();
         l.into()
     }

@@ -153,3 +153,23 @@ def test_plan_one_inserts_exactly_the_verified_samples(O, pp):
     assert 0 < inserted < 60  # some samples land in obstacles or cannot be connected
     for slot in range(1, len(planner.nodes)):
         assert _chain_ok(O, ctx, planner, slot)
+
+
+def test_finalize_panics_where_the_reference_does_and_line_to_origin_falls_back(O, pp):
+    """an edge without a feasible word (non-finite pose, Q5): line_to_origin yields the edge's start point
+    (src/rrt.rs:313), finalize's copy of the loop panics "Should plan dubins curve" (src/rrt.rs:529)"""
+    planner, ctx = _planner(O, pp, seed=3, max_iter=10, obstacles=False)
+    r = pp.rrt
+    root = planner.nodes[0]
+    # nodes outside the bounds: no shortcut verifies, so optimize() returns None and finalize walks this very chain
+    mid = r.Node((55.0, 54.0), root)
+    bad = r.Node.new_goal((58.0, 58.0), mid, float("nan"))  # a pose with a NaN heading has no Dubins word
+    leaf = r.Node((59.0, 59.5), bad)
+    lx, ly = r.line_to_origin(leaf, planner.space.get_steer(), planner.step_size, ctx)
+    assert (58.0, 58.0) in set(zip(lx.tolist(), ly.tolist()))  # the fallback point of the edge bad -> mid
+    assert (lx[-1], ly[-1]) == root.point
+    goal = r.Node.new_goal(planner.goal, leaf, planner.goal_yaw)
+    with pytest.raises(RuntimeError, match="Should plan dubins curve"):
+        planner.finalize(goal)
+    with pytest.raises(RuntimeError, match="Should plan dubins curve"):
+        planner.check_finish_many([leaf])
