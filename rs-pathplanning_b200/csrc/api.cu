@@ -10,6 +10,7 @@
 
 #include "geo_predicates.cuh"
 #include "pp_common.cuh"
+#include "pp_stage.hpp"
 
 // ---- launchers defined in the kernel translation units ---------------------------------------------
 int pp_launch_dubins_eval(pp_ctx *, size_t, const double *, const double *, const double *, const double *,
@@ -207,6 +208,8 @@ void pp_ctx_destroy(pp_ctx *ctx) {
     cudaFree(ctx->tickets);
     cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    delete ctx->stage_pool;
     if (ctx->own_stream_handle) cudaStreamDestroy(ctx->own_stream_handle);
     for (int i = 0; i < 3; ++i)
         if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
@@ -402,6 +405,113 @@ int pp_dubins_eval_dev(pp_ctx *ctx, size_t n, const double *sx, const double *sy
 #ifndef PP_EVAL_CHUNK_LOG2
 #define PP_EVAL_CHUNK_LOG2 20  // pairs per pipelined chunk of the host-pointer entry (8 MB per input array)
 #endif
+// true for ordinary host memory (malloc, Vec<f64>, numpy): neither pinned nor registered nor device / managed
+static bool pp_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// pinned ring of the staged path (grown on demand) and its copy threads (PP_STAGE_THREADS overrides; counts the caller)
+static int pp_stage_reserve(pp_ctx *ctx, size_t bytes) {
+    if (!ctx->stage_pool) {
+        // a quarter of the host's hardware threads, between 2 and 8: enough to outrun the link from one NUMA node
+        // without starving the other ranks of an 8-GPU host
+        int t = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 4));
+        if (const char *e = getenv("PP_STAGE_THREADS")) t = atoi(e);
+        ctx->stage_pool = new pp_stage_pool(std::max(1, std::min(t, 32)));
+    }
+    if (bytes <= ctx->stage_bytes) return PP_OK;
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    if (cudaHostAlloc(&ctx->stage, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return pp_fail(ctx, PP_ERR_NOMEM, "pinned staging ring allocation failed");
+    }
+    ctx->stage_bytes = bytes;
+    return PP_OK;
+}
+
+// The host-pointer evaluation for PAGEABLE caller memory: the same three-slot chunk pipeline as below, but every
+// chunk goes through the context's pinned ring.  The pool copies chunk c's inputs into its slot (and chunk c-3's
+// results out of it) with several threads while chunks c-1 and c-2 are on the wire, instead of leaving the staging
+// to the driver's single-threaded bounce-buffer path.  Device layout per slot as in pp_dubins_eval.
+static int pp_dubins_eval_staged(pp_ctx *ctx, size_t n, const double *const in[7], int n_in, double radius, double *cost,
+                                 uint8_t *word, double *tpq) {
+    const size_t chunk = (size_t)1 << PP_EVAL_CHUNK_LOG2;
+    const size_t per_slot = chunk * (8 * (size_t)n_in + 8 + 8 /*word, padded*/ + (tpq ? 24 : 0));
+    int rc = pp_scratch_reserve(ctx, per_slot * 3 + 4096);
+    if (rc) return rc;
+    rc = pp_stage_reserve(ctx, per_slot * 3);
+    if (rc) return rc;
+    PP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // see pp_dubins_eval
+    struct slot_events {
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~slot_events() {
+            for (cudaEvent_t x : e)
+                if (x) cudaEventDestroy(x);
+        }
+    } done;
+    for (int k = 0; k < 3; ++k) PP_CUDA(ctx, cudaEventCreateWithFlags(&done.e[k], cudaEventDisableTiming));
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    auto slot_host = [&](size_t c) { return (char *)ctx->stage + (c % 3) * per_slot; };
+    // results of chunk c: pinned slot -> caller's arrays
+    auto drain_pieces = [&](size_t c, std::vector<pp_copy_piece> &v) {
+        const size_t off = c * chunk, cnt = std::min(chunk, n - off);
+        char *h = slot_host(c) + (size_t)n_in * chunk * 8;
+        v.push_back({cost + off, h, cnt * 8});
+        v.push_back({word + off, h + chunk * 8, cnt});
+        if (tpq) v.push_back({tpq + 3 * off, h + chunk * 16, cnt * 24});
+    };
+    std::vector<pp_copy_piece> pieces;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t off = c * chunk, cnt = std::min(chunk, n - off);
+        cudaStream_t s = ctx->copy_streams[c % 3];
+        ctx->active_stream = s;
+        char *h = slot_host(c), *base = (char *)ctx->scratch + (c % 3) * per_slot;
+        pieces.clear();
+        if (c >= 3) {  // the slot's previous occupant must have landed before it is overwritten
+            PP_CUDA(ctx, cudaEventSynchronize(done.e[c % 3]));
+            drain_pieces(c - 3, pieces);
+        }
+        std::vector<pp_copy_piece> fill;
+        for (int k = 0; k < n_in; ++k) fill.push_back({h + (size_t)k * chunk * 8, in[k] + off, cnt * 8});
+        // drain first: its source is the slot region the fill does not touch (inputs and results do not overlap)
+        pieces.insert(pieces.end(), fill.begin(), fill.end());
+        ctx->stage_pool->run(pieces.data(), pieces.size());
+        double *din[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int k = 0; k < n_in; ++k) din[k] = (double *)(base + (size_t)k * chunk * 8);
+        if (cnt == chunk) {  // the slot's input block is contiguous: one copy
+            PP_CUDA(ctx, cudaMemcpyAsync(base, h, (size_t)n_in * chunk * 8, cudaMemcpyHostToDevice, s));
+        } else {
+            for (int k = 0; k < n_in; ++k)
+                PP_CUDA(ctx, cudaMemcpyAsync(din[k], h + (size_t)k * chunk * 8, cnt * 8, cudaMemcpyHostToDevice, s));
+        }
+        double *dcost = (double *)(base + (size_t)n_in * chunk * 8);
+        uint8_t *dword = (uint8_t *)(dcost + chunk);
+        double *dtpq = tpq ? (double *)(dword + chunk * 8) : nullptr;
+        rc = pp_launch_dubins_eval(ctx, cnt, din[0], din[1], din[2], din[3], din[4], din[5], din[6], radius, dcost, dword,
+                                   dtpq, s);
+        if (rc) return rc;
+        char *hout = h + (size_t)n_in * chunk * 8;
+        PP_CUDA(ctx, cudaMemcpyAsync(hout, dcost, cnt * 8, cudaMemcpyDeviceToHost, s));
+        PP_CUDA(ctx, cudaMemcpyAsync(hout + chunk * 8, dword, cnt, cudaMemcpyDeviceToHost, s));
+        if (tpq) PP_CUDA(ctx, cudaMemcpyAsync(hout + chunk * 16, dtpq, cnt * 24, cudaMemcpyDeviceToHost, s));
+        PP_CUDA(ctx, cudaEventRecord(done.e[c % 3], s));
+    }
+    for (size_t c = n_chunks > 3 ? n_chunks - 3 : 0; c < n_chunks; ++c) {
+        PP_CUDA(ctx, cudaEventSynchronize(done.e[c % 3]));
+        pieces.clear();
+        drain_pieces(c, pieces);
+        ctx->stage_pool->run(pieces.data(), pieces.size());
+    }
+    return PP_OK;
+}
+
 int pp_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw, const double *ex,
                    const double *ey, const double *eyaw, const double *radius_arr, double radius, double *cost,
                    uint8_t *word, double *tpq) {
@@ -409,8 +519,18 @@ int pp_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, co
     if (!radius_arr && !pp_pos_finite(radius)) return PP_ERR_INVALID;
     if (n == 0) return PP_OK;
     pp_guard g(ctx);
-    const size_t chunk = std::min(n, (size_t)1 << PP_EVAL_CHUNK_LOG2);
     const int n_in = radius_arr ? 7 : 6;
+    if (n >= ((size_t)2 << PP_EVAL_CHUNK_LOG2) && (pp_is_pageable(sx) || pp_is_pageable(cost))) {
+        // large batch in pageable memory: stage it through the pinned ring with the copy threads
+        const double *in_all[7] = {sx, sy, syaw, ex, ey, eyaw, radius_arr};
+        int rc = pp_dubins_eval_staged(ctx, n, in_all, n_in, radius, cost, word, tpq);
+        if (rc != PP_OK) {  // leave nothing in flight that still targets the ring or the scratch block
+            for (int k = 0; k < 3; ++k) cudaStreamSynchronize(ctx->copy_streams[k]);
+            cudaGetLastError();
+        }
+        return rc;
+    }
+    const size_t chunk = std::min(n, (size_t)1 << PP_EVAL_CHUNK_LOG2);
     const size_t per_slot = chunk * (8 * (size_t)n_in + 8 + 8 /*word, padded*/ + (tpq ? 24 : 0));
     int rc = pp_scratch_reserve(ctx, per_slot * 3 + 4096);
     if (rc) return rc;

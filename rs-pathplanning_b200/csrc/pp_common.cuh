@@ -100,6 +100,10 @@ struct pp_ctx {
     size_t scratch_bytes = 0;
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // pinned ring + copy threads of the batch entry points when the caller's arrays are pageable (pp_stage.hpp)
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    class pp_stage_pool *stage_pool = nullptr;
     // NCCL communicator this ctx is a rank of (group.cu); null = single device
     void *comm = nullptr;
     int comm_rank = -1, comm_size = 1;

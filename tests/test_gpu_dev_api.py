@@ -142,3 +142,28 @@ def test_error_paths(ctx, pp):
     with pytest.raises(pp.PathPlanningError):
         pp.Context(99)  # no such device
     c.close()
+
+
+def test_pageable_batches_take_the_staged_path_and_give_the_same_bits(ctx, pp):
+    """pp_dubins_eval on ordinary (pageable) arrays of >= 2 chunks goes through the pinned ring and the copy threads
+    (csrc/pp_stage.hpp); pinned arrays take the direct path.  Same bits either way, with a ragged last chunk, with
+    per-pair radii and t, p, q requested, and on the slot-reuse boundaries (exactly 3 and 4 chunks)."""
+    chunk = 1 << 20
+    for n, with_radii, want_tpq in ((3 * chunk + 12_345, True, True), (3 * chunk, False, False), (4 * chunk, False, True),
+                                    (2 * chunk, False, False)):
+        host = pp.synth.dubins_pairs(n, "mixed", seed=4242 + n % 7)
+        radii = (0.5 + (np.arange(n) % 5) * 0.25) if with_radii else None
+        pins = [pp.PinnedArray(n, np.float64) for _ in range(7 if with_radii else 6)]
+        for p, a in zip(pins, list(host) + ([radii] if with_radii else [])):
+            p.array[:] = a
+        pc, pw = pp.PinnedArray(n, np.float64), pp.PinnedArray(n, np.uint8)
+        pt = pp.PinnedArray(3 * n, np.float64) if want_tpq else None
+        out_pin = (pc.array, pw.array, pt.array.reshape(n, 3) if want_tpq else None)
+        ctx.dubins_eval(*[p.array for p in pins[:6]], radius=1.0, radius_arr=pins[6].array if with_radii else None,
+                        want_tpq=want_tpq, out=out_pin)
+        cost, word, tpq = ctx.dubins_eval(*host, radius=1.0, radius_arr=radii, want_tpq=want_tpq)  # pageable numpy
+        assert np.array_equal(cost, pc.array, equal_nan=True) and np.array_equal(word, pw.array)
+        if want_tpq:
+            assert np.array_equal(tpq, out_pin[2], equal_nan=True)
+        assert np.bincount(word, minlength=6)[:6].min() > n // 20  # every word occurs: nothing was left unwritten
+        del pins, pc, pw, pt, out_pin
