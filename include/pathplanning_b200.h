@@ -130,7 +130,10 @@ int pp_dubins_words(pp_ctx *ctx, size_t n, const double *alpha, const double *be
  * tie to 1e-9, or whose word is within 1e-9 of infeasible, the chosen word -- hence the sample count -- may differ
  * from the reference's; everywhere else word, cost and samples agree to 1e-9 relative.  radius_arr may be NULL -> scalar `radius` (DubinsConfig.turn_radius).
  * cost is radius-normalised as in the reference (src/dubins.rs:395); word = pp_word or PP_WORD_NONE
- * (reference returns None, src/dubins.rs:397; cost = +inf).  tpq (n*3) may be NULL. */
+ * (reference returns None, src/dubins.rs:397; cost = +inf).  tpq (n*3) may be NULL.
+ * Host memory of any kind: pinned buffers (pp_host_alloc) are copied from / to directly; batches of >= 2^21 pairs in
+ * ordinary pageable memory (Vec<f64>, malloc) are staged through the context's pinned ring by a few copy threads
+ * (PP_STAGE_THREADS overrides their number), about 3x the rate of handing such memory to cudaMemcpyAsync. */
 int pp_dubins_eval(pp_ctx *ctx, size_t n, const double *sx, const double *sy, const double *syaw,
                    const double *ex, const double *ey, const double *eyaw, const double *radius_arr,
                    double radius, double *cost, uint8_t *word, double *tpq);

@@ -418,9 +418,10 @@ static bool pp_is_pageable(const void *p) {
 // pinned ring of the staged path (grown on demand) and its copy threads (PP_STAGE_THREADS overrides; counts the caller)
 static int pp_stage_reserve(pp_ctx *ctx, size_t bytes) {
     if (!ctx->stage_pool) {
-        // a quarter of the host's hardware threads, between 2 and 8: enough to outrun the link from one NUMA node
-        // without starving the other ranks of an 8-GPU host
-        int t = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 4));
+        // half of the host's hardware threads, between 2 and 8 (swept on a 16-thread B200 host,
+        // profiles/r05_stage_threads.json: 2 -> 3.0e8, 4 -> 5.1e8, 6 and 8 -> 6.5e8, 16 -> 7.8e8 pairs/s; the driver's
+        // own pageable path: 2.1e8); the cap leaves room for the other ranks of an 8-GPU host
+        int t = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 2));
         if (const char *e = getenv("PP_STAGE_THREADS")) t = atoi(e);
         ctx->stage_pool = new pp_stage_pool(std::max(1, std::min(t, 32)));
     }
