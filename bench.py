@@ -675,7 +675,8 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
             out[name]["nn_grid_build_ms_after_upload"] = grid_build_ms
         if kname == "nn_grid" and not args.profile:
             # the same step end to end through the host C-ABI call (pp_rrt_extend on pinned host buffers: 16 B in and
-            # 13 B out per query cross PCIe inside the timed region); wall clock, max over ranks
+            # 13 B out per query cross PCIe inside the timed region, in 2^18-query chunks rotating over three streams
+            # so that uploads, the two kernels and downloads overlap); wall clock, max over ranks
             hq = [pp.PinnedArray(m, np.float64) for _ in range(2)]
             hq[0].array[:] = qx.cpu().numpy()
             hq[1].array[:] = qy.cpu().numpy()

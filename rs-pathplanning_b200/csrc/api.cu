@@ -402,6 +402,11 @@ int pp_dubins_eval_dev(pp_ctx *ctx, size_t n, const double *sx, const double *sy
 // host pointers: the batch is cut into chunks that rotate over three streams so that the H2D copy of
 // chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (both PCIe directions busy).
 // With pinned buffers (pp_host_alloc) the copies are truly asynchronous.
+#ifndef PP_EXTEND_CHUNK_LOG2
+#define PP_EXTEND_CHUNK_LOG2 18  // queries per pipelined chunk of the host-pointer extend step (4 MB up, 3.4 MB down); swept on
+                                 // the GPU (profiles/r05_extend_e2e.json): 2^15 1.11, 2^16 0.77, 2^17 0.63, 2^18 0.60, 2^19 0.62 ms,
+                                 // one chunk (the single-stream route) 0.79 ms per 2^20-query call from pinned memory
+#endif
 #ifndef PP_EVAL_CHUNK_LOG2
 #define PP_EVAL_CHUNK_LOG2 20  // pairs per pipelined chunk of the host-pointer entry (8 MB per input array)
 #endif
@@ -1335,6 +1340,40 @@ int pp_rrt_extend(pp_ctx *ctx, size_t m, const double *qx, const double *qy, uin
     int rc = pp_nn_prepare(ctx, m, &nn_flags);
     if (rc) return rc;
     cudaStream_t s = ctx->stream;
+    // Large batch on the default route (grid NN + grid verify: neither kernel touches the context's scratch block or
+    // tickets, so chunks may run side by side): cut it into chunks that rotate over the three copy streams, as
+    // pp_dubins_eval does -- the upload of chunk c+1, the two kernels of chunk c and the download of chunk c-1 overlap,
+    // instead of 16 B in, two kernels and 13 B out per query strictly one after the other.
+    const bool grid_route = (nn_flags & PP_NN_GRID) && !(nn_flags & (PP_NN_SCAN | PP_NN_PLAIN_F64 | PP_NN_UNSORTED)) &&
+                            !(collide_flags & (PP_COLLIDE_NO_CULL | PP_COLLIDE_UNSORTED | PP_COLLIDE_SCAN | PP_COLLIDE_FUSED));
+    int chunk_log2 = PP_EXTEND_CHUNK_LOG2;
+    if (const char *e = getenv("PP_EXTEND_CHUNK_LOG2")) chunk_log2 = std::max(12, std::min(26, atoi(e)));  // developer sweep
+    const size_t chunk = (size_t)1 << chunk_log2;
+    if (grid_route && m >= 2 * chunk) {
+        const size_t per_slot = chunk * (16 + 8 + 4 + 4 /*ok, padded*/);
+        rc = pp_scratch_reserve(ctx, per_slot * 3);
+        if (rc) return rc;
+        PP_CUDA(ctx, cudaStreamSynchronize(s));  // the node grid (built on the context stream) is complete; scratch is free
+        size_t c = 0;
+        for (size_t off = 0; off < m; off += chunk, ++c) {
+            const size_t cnt = std::min(chunk, m - off);
+            cudaStream_t cs = ctx->copy_streams[c % 3];
+            ctx->active_stream = cs;
+            char *base = (char *)ctx->scratch + (c % 3) * per_slot;
+            double *dqx = (double *)base, *dqy = dqx + chunk, *dyaw = dqy + chunk;
+            uint32_t *didx = (uint32_t *)(dyaw + chunk);
+            uint8_t *dok = (uint8_t *)(didx + chunk);
+            PP_CUDA(ctx, cudaMemcpyAsync(dqx, qx + off, cnt * 8, cudaMemcpyHostToDevice, cs));
+            PP_CUDA(ctx, cudaMemcpyAsync(dqy, qy + off, cnt * 8, cudaMemcpyHostToDevice, cs));
+            rc = pp_extend_step(ctx, cnt, dqx, dqy, didx, dyaw, dok, nn_flags, collide_flags, cs);
+            if (rc) break;
+            PP_CUDA(ctx, cudaMemcpyAsync(idx + off, didx, cnt * 4, cudaMemcpyDeviceToHost, cs));
+            if (yaw) PP_CUDA(ctx, cudaMemcpyAsync(yaw + off, dyaw, cnt * 8, cudaMemcpyDeviceToHost, cs));
+            PP_CUDA(ctx, cudaMemcpyAsync(ok + off, dok, cnt, cudaMemcpyDeviceToHost, cs));
+        }
+        for (int k = 0; k < 3; ++k) PP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_streams[k]));
+        return rc;
+    }
     PP_TMP(ctx, dq, s, m * 16);
     PP_TMP(ctx, di, s, m * 4);
     PP_TMP(ctx, dy, s, m * 8);
