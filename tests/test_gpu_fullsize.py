@@ -54,7 +54,7 @@ def test_c4_full_extend_step_properties(ctx, pp, O):
     ctx.tree_upload(nx, ny, nyaw)
     ctx.obstacles_upload(bounds, rings)
     idx, yaw, ok = ctx.rrt_extend(qx, qy, nn_flags=8, collide_flags=8)  # tiled brute-force scans (PP_NN_SCAN, PP_COLLIDE_SCAN)
-    idx_g, yaw_g, ok_g = ctx.rrt_extend(qx, qy)  # default: device-built node grid, then obstacle grid (two launches)
+    idx_g, yaw_g, ok_g = ctx.rrt_extend(qx, qy)  # default: device-built node grid, then obstacle grid (two launches per 2^18-query chunk, chunks pipelined over three streams)
     assert np.array_equal(idx, idx_g) and np.array_equal(ok, ok_g) and np.array_equal(yaw, yaw_g)
     idx_s, yaw_s, ok_s = ctx.rrt_extend(qx, qy, collide_flags=16)  # PP_COLLIDE_FUSED: binned queries, one fused launch
     assert np.array_equal(idx, idx_s) and np.array_equal(ok, ok_s) and np.array_equal(yaw, yaw_s)
