@@ -249,6 +249,10 @@ def run_own(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    # copy threads of the staged (pageable-memory) path: the ranks of one host share its cores, so each takes its
+    # share of half the hardware threads (the library's own default is what a single process would use)
+    stage_threads = max(2, min(8, (os.cpu_count() or 8) // (2 * world)))
+    os.environ.setdefault("PP_STAGE_THREADS", str(stage_threads))
     ctx = pp.Context(local)
     if world > 1:
         # the library's own communicator (ncclBroadcast of tree / tail / obstacles inside the C-ABI): rank 0 makes the
@@ -414,6 +418,7 @@ def run_own(args):
                                                       "what": "plain cudaMemcpyAsync of the same bytes from / to pageable "
                                                               "memory, no kernel: what the call cost before the staged path"},
                              "vs_driver_pageable_copy": e2e_pageable / ceil_pageable,
+                             "copy_threads_per_rank": int(os.environ["PP_STAGE_THREADS"]),
                              "frac_of_copy_ceiling": e2e_pageable / ceil_pinned},
             "gpu_launches": launches + e2e_launches + sum(w.get("gpu_launches", 0) for w in workloads.values())
             + strong.get("gpu_launches", 0),
