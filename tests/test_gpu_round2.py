@@ -215,3 +215,26 @@ def test_two_planners_side_by_side(pp, O):
         r.Space(b1, r.Robot(1.0, 1.0, 0.8), rings1)
     s1.close()
     s2.close()
+
+
+def test_host_extend_step_pipelined_chunks_equal_the_single_stream_route(ctx, pp, O):
+    """pp_rrt_extend on host arrays cuts a large batch on its default route into 2^18-query chunks that rotate over
+    three streams; the answers must be the bytes of the single-stream route (selected here by asking for the scan
+    verify, which returns the same flags) at sizes around the chunk boundaries, and the oracle's on a sub-sample."""
+    n_nodes, chunk = 1 << 16, 1 << 18
+    m = 3 * chunk + 777
+    qx, qy, nx, ny, nyaw = pp.synth.extend_inputs(m, n_nodes, world=400.0)
+    bounds, rings = pp.synth.circle_world(1500, world=400.0)
+    ctx.tree_upload(nx, ny, nyaw)
+    ctx.obstacles_upload(bounds, rings)
+    ref = ctx.rrt_extend(qx, qy, collide_flags=SCAN)
+    for k in (2 * chunk - 1, 2 * chunk, 2 * chunk + 1, m):  # the first is below the pipelined route's threshold
+        idx, yaw, ok = ctx.rrt_extend(qx[:k], qy[:k])
+        assert np.array_equal(idx, ref[0][:k]) and np.array_equal(ok, ref[2][:k])
+        assert np.array_equal(yaw, ref[1][:k], equal_nan=True)
+    sub = np.arange(0, m, 997)
+    oidx, _ = O.nn_brute(nx, ny, qx[sub], qy[sub])
+    assert np.array_equal(ref[0][sub], oidx)
+    W = O.OracleWorld(bounds, rings)
+    assert np.array_equal(ref[2][sub], W.verify_segments(qx[sub], qy[sub], nx[oidx], ny[oidx], culled=True))
+    assert 0.5 < ref[2].mean() < 0.99
