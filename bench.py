@@ -251,7 +251,7 @@ def run_own(args):
     dev = torch.device("cuda", local)
     # copy threads of the staged (pageable-memory) path: the ranks of one host share its cores, so each takes its
     # share of half the hardware threads (the library's own default is what a single process would use)
-    stage_threads = max(2, min(8, (os.cpu_count() or 8) // (2 * world)))
+    stage_threads = max(2, min(8, len(os.sched_getaffinity(0)) // (2 * world)))
     os.environ.setdefault("PP_STAGE_THREADS", str(stage_threads))
     ctx = pp.Context(local)
     if world > 1:
