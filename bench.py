@@ -544,6 +544,23 @@ def strong_block(args, torch, dist, pp, ctx, dev, rank, world):
     return out
 
 
+C1_POSE = (1.0, 1.0, np.pi / 4.0, -3.0, -3.0, -np.pi / 4.0, 1.0, 0.1)  # benches/all.rs:102-111 (c read as turn_radius)
+
+
+def single_path_latency(fn, reps=2000, warm=50):
+    """C1 (first row): wall clock per scalar dubins_path_planning call on the bench pose.
+    fn(*C1_POSE) -> (px, py, pyaw, word, cost) or an object with .x / .word / .cost"""
+    for _ in range(warm):
+        fn(*C1_POSE)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        p = fn(*C1_POSE)
+    dt = time.perf_counter() - t0
+    px, word, cost = (p[0], p[3], p[4]) if isinstance(p, tuple) else (p.x, p.word, p.cost)
+    return {"value": dt / reps * 1e6, "unit": "us/path", "higher_is_better": False, "calls": reps,
+            "samples": int(len(px)), "word": int(word), "cost": float(cost)}
+
+
 def cpu_baseline_leg(pp):
     """oracle port timed on the host cores, bounded sample of the same workload (rank 0, N = 1 only)"""
     O = graft.import_oracle()
@@ -590,7 +607,21 @@ def cpu_baseline_leg(pp):
               "sample": "2^16 queries of the C4 workload vs the 2^20-node tree and 10 k rings: exact grid NN + culled "
                         "Space::verify of the straight edge, all host threads; nn_brute: the first 2^11 of those queries by "
                         "exact brute force (SURVEY 8d asks for both NN comparators)"}
-    return {"value": best, "unit": "pairs/s", "cores": threads, "kind": "port", "extend": extend,
+    try:  # C1: the scalar call on one thread (through ctypes, as the GPU figure in workloads.c1_single_path is)
+        c1 = single_path_latency(O.dubins_path)
+        c1["what"] = ("oracle port, one thread: evaluate + sample the bench pose (95 samples); value = one call at a time "
+                      "through ctypes (what workloads.c1_single_path pays too), in_c_loop_us = the same call repeated "
+                      "inside one C loop (no Python), the figure to hold against criterion's")
+        reps = 20_000
+        pose = [np.full(reps, v) for v in C1_POSE[:6]]
+        O.dubins_count_batch(*[v[:256] for v in pose], C1_POSE[6], C1_POSE[7], nthreads=1)
+        t = time.perf_counter()
+        cnt = O.dubins_count_batch(*pose, C1_POSE[6], C1_POSE[7], nthreads=1)
+        c1["in_c_loop_us"] = (time.perf_counter() - t) / reps * 1e6
+        c1["in_c_loop_samples"] = int(cnt[0])
+    except Exception as e:
+        c1 = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return {"value": best, "unit": "pairs/s", "cores": threads, "kind": "port", "extend": extend, "c1_single_path": c1,
             "sample": "2^22 pairs of the C3 workload, all host threads (OpenMP static), best of 3; single thread on 2^20 pairs",
             "single_thread_value": single,
             "note": "C restatement of src/dubins.rs (oracle/pp_oracle.c, gcc -O3 -ffp-contract=off -fno-fast-math), not rustc output"}
@@ -814,6 +845,39 @@ def secondary(args, torch, dist, pp, ctx, dev, rank, world, fp64_peak, hbm_peak,
                      "traffic_source": fact(facts, "pp_dubins_fill_kernel", "dram_bytes")[1],
                      "per_unit": "24 B written per sample (+112 B plan record per path)"},
     }
+    # ---- C1: one scalar dubins_path_planning call (examples/dubins, benches/all.rs "Dubins::dubins_path_planning"): a
+    # batch of one through the host C-ABI -- one launch writing header + samples into mapped pinned memory, one stream
+    # synchronisation.  Expected SLOWER than the CPU's ~2 us: the value of the GPU path is in
+    # the batch entry points; this line states what the drop-in costs a caller who keeps calling it one pose at a time.
+    try:
+        l0 = ctx.launch_count
+        c1 = single_path_latency(ctx.dubins_path)
+        c1.update({"metric": "dubins_path_latency_us", "gpu_launches": ctx.launch_count - l0,
+                   "config": {"workload": "c1: pose (1, 1, 45 deg) -> (-3, -3, -45 deg), radius 1.0, step 0.1, one call "
+                                          "at a time through pp_dubins_path (ctypes call included)"}})
+        out["c1_single_path"] = c1
+    except Exception as e:
+        out["c1_single_path"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    # ---- the reference's own criterion benches (benches/all.rs: RRT::plan_one, RRT::plan_10,
+    # Dubins::dubins_path_planning on its bench world / pose) through the C++ mirror on this GPU: host/bench_all, a
+    # plain timing loop (warm-up 0.2 s, measure 1 s per bench; criterion's are 5 s / 15 s).  Scalar calls, one launch
+    # or a few per iteration: latency figures of the drop-in API, not throughput.  Rank 0 only, separate process.
+    if rank == 0:
+        try:
+            import re
+            exe = os.path.join(ROOT, "rs-pathplanning_b200", "host", "bench_all")
+            r = subprocess.run([exe, "0.2", "1.0"], capture_output=True, text=True, timeout=90)
+            rows = {m.group(1): float(m.group(2))
+                    for m in re.finditer(r"^(\S+)\s+time:\s+([0-9.]+) us/iter", r.stdout, re.M)}
+            if r.returncode != 0 or not rows:
+                raise RuntimeError(f"rc {r.returncode}: {(r.stderr or r.stdout)[-160:]}")
+            out["benches_all_cpp"] = {"unit": "us/iter", "higher_is_better": False, **rows,
+                                      "config": {"workload": "benches/all.rs entry points through host/pathplanning.hpp "
+                                                             "(bench world: 6 create_circle obstacles, 21 x 21 bounds, "
+                                                             "turn radius 0.8, step 0.1; bench pose: radius 1.0, step 0.1); "
+                                                             "the tree persists across iterations, as under criterion"}}
+        except Exception as e:
+            out["benches_all_cpp"] = {"error": f"{type(e).__name__}: {e}"[:240]}
     # ---- C2 (functional, host-driven): the examples/rrt shape -- 100 x 100 world, 50 create_circle obstacles, 10 k
     # iterations, fixed seed -- through the Python mirror's batched rounds (NN -> yaw -> fused Dubins verify ->
     # append -> goal connection per round).  Wall clock of the whole planner incl. the Python bookkeeping and every
