@@ -14,6 +14,7 @@ instead of thread_rng.
 """
 from __future__ import annotations
 
+import itertools
 import math
 from typing import Iterator, List, Optional, Sequence, Tuple
 
@@ -287,17 +288,23 @@ class RRT:  # src/rrt.rs:325-619
         if i >= RECURSION_LIMIT or not nodes:
             return [None] * len(nodes)
         chains = [list(NodeIter(n)) for n in nodes]
-        cands = [[Node(n.get_coord(), to_node) for to_node in ch] for n, ch in zip(nodes, chains)]
         sx, sy, syaw, ex, ey, eyaw, spans = [], [], [], [], [], [], []
-        for ch, cd in zip(chains, cands):
-            a = len(sx)
-            sx += [c.point[0] for c in cd] + [v.point[0] for v in ch[:-1]]
-            sy += [c.point[1] for c in cd] + [v.point[1] for v in ch[:-1]]
-            syaw += [c.yaw for c in cd] + [v.yaw for v in ch[:-1]]
-            ex += [v.point[0] for v in ch] + [v.parent.point[0] for v in ch[:-1]]
-            ey += [v.point[1] for v in ch] + [v.parent.point[1] for v in ch[:-1]]
-            eyaw += [v.yaw for v in ch] + [v.parent.yaw for v in ch[:-1]]
-            spans.append((a, len(ch)))
+        atan2 = math.atan2
+        for n, ch in zip(nodes, chains):
+            a, k = len(sx), len(ch)
+            x, y = n.point
+            cx = [v.point[0] for v in ch]
+            cy = [v.point[1] for v in ch]
+            cyaw = [v.yaw for v in ch]
+            # candidate k = Node::new(node.coord, chain[k]): same point, yaw aimed at chain[k] (src/rrt.rs:169-175);
+            # only the winning candidate is materialised as a Node below
+            sx += [x] * k + cx[:-1]
+            sy += [y] * k + cy[:-1]
+            syaw += [atan2(py - y, px - x) for px, py in zip(cx, cy)] + cyaw[:-1]
+            ex += cx + cx[1:]  # own edges: chain[j] -> chain[j + 1]
+            ey += cy + cy[1:]
+            eyaw += cyaw + cyaw[1:]
+            spans.append((a, k))
         ok = self.ctx.collide_dubins(sx, sy, syaw, ex, ey, eyaw, self.space.get_steer(), self.step_size).astype(bool)
         picks: List[int] = []
         for (a, n), ch in zip(spans, chains):
@@ -311,7 +318,7 @@ class RRT:  # src/rrt.rs:325-619
         deeper = self._optimize_many([chains[j][picks[j]] for j in live], i + 1)
         out: List[Optional[Node]] = [None] * len(nodes)
         for j, d in zip(live, deeper):
-            out[j] = Node(nodes[j].get_coord(), d) if d is not None else cands[j][picks[j]]
+            out[j] = Node(nodes[j].get_coord(), d if d is not None else chains[j][picks[j]])
         return out
 
     # -- check_finish (src/rrt.rs:428-438) for many nodes: batched optimize, one batched line_to_origin over all the
@@ -323,7 +330,7 @@ class RRT:  # src/rrt.rs:325-619
         opt = self._optimize_many(list(nodes), 0)
         tops = [Node.new_goal(g.get_coord(), o, self.goal_yaw) if o is not None else g for g, o in zip(goals, opt)]
         edges = [_chain_edges(t) for t in tops]
-        flat = [sum((e[c] for e in edges), []) for c in range(6)]
+        flat = [list(itertools.chain.from_iterable(e[c] for e in edges)) for c in range(6)]
         steer = self.space.get_steer()
         lines: List[Ring] = []
         if flat[0]:
